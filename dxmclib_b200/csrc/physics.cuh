@@ -1,0 +1,591 @@
+// physics.cuh — device-side primitives of the photon transport hot path (sm_100a).
+//
+// Every function states the reference function whose arithmetic it reproduces. Float expressions
+// keep the reference's operation order; the translation unit is compiled with -fmad=false so
+// nvcc does not fuse a*b+c (the CPU checkers are built with -ffp-contract=off), and geometry uses
+// explicit round-to-nearest intrinsics, which makes voxel-index sequences bit-exact.
+#pragma once
+
+#include "../../include/dxmcb200.h"
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace dxmcb200 {
+
+constexpr float kPi = 3.14159265358979323846f;
+constexpr float kTwoPi = kPi + kPi;
+constexpr float kElectronRestMass = 510.9989461f; // constants.hpp:63
+constexpr float kKevToAngstrom = 12.398520f; // constants.hpp:29
+constexpr float kEnergyCutoff = 1.0f; // transport.hpp:827
+constexpr float kRouletteThreshold = 5.0f; // transport.hpp:823
+constexpr float kRouletteProbability = 0.8f; // transport.hpp:819
+constexpr float kDirEpsilon = 1.0e-9f; // transport.hpp:831
+
+// ---- tables as the kernels see them -------------------------------------------------------
+struct LutView {
+    uint32_t nMaterials, nSegments, linearIndex;
+    float linearStep, linearEnergy;
+    const float* knots; // [nSegments]
+    const float* coeff; // [nMaterials][nSegments][6]
+    const float* maxCoeff; // [nSegments][2]
+    const float* rita; // [nMaterials][4][56]
+    const float* spline; // [nMaterials][63]
+    const float* shells; // [nMaterials][12][11]
+};
+
+struct WorldView {
+    uint32_t dim[3];
+    float spacing[3];
+    float ext[6];
+    const uint2* voxels; // {density bits, material | measurement<<8}
+};
+
+struct SpectrumView {
+    uint32_t n;
+    uint32_t threshold; // rejection threshold of the bounded integer draw
+    const float* probs;
+    const uint32_t* alias;
+    const float* energies;
+};
+
+struct HeelView {
+    float energyStart, energyStep;
+    uint32_t energySize;
+    float angleStart, angleStep;
+    uint32_t angleSize;
+    const float* weights;
+};
+
+struct BowtieView {
+    uint32_t n;
+    const float* angles;
+    const float* weights;
+};
+
+struct BeamView {
+    const SpectrumView* spectra;
+    const HeelView* heels;
+    const BowtieView* bowties;
+};
+
+struct Photon {
+    float px, py, pz;
+    float dx, dy, dz;
+    float energy, weight;
+};
+
+// ---- RNG: PCG32 XSH-RR, one stream per history (dxmcrandom.hpp:156-165, 67-73) -------------
+__host__ __device__ inline uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    return z ^ (z >> 31);
+}
+
+__host__ __device__ inline void historyStream(uint64_t seed, uint64_t exposure, uint64_t history, uint64_t& state, uint64_t& inc)
+{
+    const uint64_t golden = 0x9E3779B97F4A7C15ULL;
+    const uint64_t s = mix64(seed + golden * (exposure + 1));
+    state = mix64(s + golden * (history + 1));
+    inc = mix64(state + golden) | 1ULL;
+}
+
+struct Rng {
+    uint64_t state, inc;
+    __device__ __forceinline__ uint32_t next()
+    {
+        const uint64_t old = state;
+        state = old * 6364136223846793005ULL + inc;
+        const uint32_t xorshifted = static_cast<uint32_t>(((old >> 18u) ^ old) >> 27u);
+        const uint32_t rot = static_cast<uint32_t>(old >> 59u);
+        return __funnelshift_r(xorshifted, xorshifted, rot);
+    }
+    // u32 * 2^-32 rounded to float: can return exactly 1.0f, as the reference's does
+    __device__ __forceinline__ float uniform() { return __fmul_rn(__uint2float_rn(next()), 2.32830643653869628906e-010f); }
+    __device__ __forceinline__ float uniform(float maxv) { return __fmul_rn(uniform(), maxv); }
+    __device__ __forceinline__ float uniform(float minv, float maxv)
+    {
+        const float r = uniform();
+        const float range = __fsub_rn(maxv, minv);
+        return __fadd_rn(minv, __fmul_rn(r, range));
+    }
+};
+
+// ---- vector math (vectormath.hpp:68-99, 138-146, 197-221) -----------------------------------
+__device__ __forceinline__ void rotate(float& v0, float& v1, float& v2, float a0, float a1, float a2, float angle)
+{
+    float sang, cang;
+    sincosf(angle, &sang, &cang);
+    const float midt = (1.0f - cang) * (v0 * a0 + v1 * a1 + v2 * a2);
+    const float o0 = cang * v0 + midt * a0 + sang * (a1 * v2 - a2 * v1);
+    const float o1 = cang * v1 + midt * a1 + sang * (-a0 * v2 + a2 * v0);
+    const float o2 = cang * v2 + midt * a2 + sang * (a0 * v1 - a1 * v0);
+    v0 = o0;
+    v1 = o1;
+    v2 = o2;
+}
+
+// scatter the direction by polar angle theta and azimuth phi; the helper axis is NOT normalised,
+// exactly like the reference, so |dir| drifts below one after scatters (vectormath.hpp:197-221)
+__device__ __forceinline__ void peturb(Photon& p, float theta, float phi)
+{
+    const float ax = fabsf(p.dx), ay = fabsf(p.dy), az = fabsf(p.dz);
+    const int minInd = ax <= ay ? (ax <= az ? 0 : 2) : (ay <= az ? 1 : 2);
+    const float k0 = minInd == 0 ? 1.0f : 0.0f;
+    const float k1 = minInd == 1 ? 1.0f : 0.0f;
+    const float k2 = minInd == 2 ? 1.0f : 0.0f;
+    float x0 = p.dy * k2 - p.dz * k1;
+    float x1 = p.dz * k0 - p.dx * k2;
+    float x2 = p.dx * k1 - p.dy * k0;
+    rotate(x0, x1, x2, p.dx, p.dy, p.dz, phi);
+    float tsin, tcos;
+    sincosf(theta, &tsin, &tcos);
+    p.dx = p.dx * tcos + x0 * tsin;
+    p.dy = p.dy * tcos + x1 * tsin;
+    p.dz = p.dz * tcos + x2 * tsin;
+}
+
+// ---- geometry (transport.hpp:485-521, 702-728) ----------------------------------------------
+__device__ __forceinline__ bool insideWorld(const WorldView& w, float x, float y, float z)
+{
+    return (x > w.ext[0] && x < w.ext[1]) && (y > w.ext[2] && y < w.ext[3]) && (z > w.ext[4] && z < w.ext[5]);
+}
+
+__device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, float y, float z)
+{
+    const uint32_t ix = __float2uint_rz(__fdiv_rn(__fsub_rn(x, w.ext[0]), w.spacing[0]));
+    const uint32_t iy = __float2uint_rz(__fdiv_rn(__fsub_rn(y, w.ext[2]), w.spacing[1]));
+    const uint32_t iz = __float2uint_rz(__fdiv_rn(__fsub_rn(z, w.ext[4]), w.spacing[2]));
+    return iz * w.dim[0] * w.dim[1] + iy * w.dim[0] + ix;
+}
+
+__device__ __forceinline__ void advance(Photon& p, float step)
+{
+    p.px = __fadd_rn(p.px, __fmul_rn(p.dx, step));
+    p.py = __fadd_rn(p.py, __fmul_rn(p.dy, step));
+    p.pz = __fadd_rn(p.pz, __fmul_rn(p.dz, step));
+}
+
+// slab-method entry into the world box; false when the ray misses (transport.hpp:702-728)
+__device__ __forceinline__ bool transportToWorld(const WorldView& w, Photon& p)
+{
+    if (insideWorld(w, p.px, p.py, p.pz))
+        return true;
+    float amin = -3.402823466e+38f;
+    float amax = 3.402823466e+38f;
+    const float pos[3] = { p.px, p.py, p.pz };
+    const float dir[3] = { p.dx, p.dy, p.dz };
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        if (fabsf(dir[i]) > kDirEpsilon) {
+            const float a0 = __fdiv_rn(__fsub_rn(w.ext[i * 2], pos[i]), dir[i]);
+            const float an = __fdiv_rn(__fsub_rn(w.ext[i * 2 + 1], pos[i]), dir[i]);
+            amin = fmaxf(amin, fminf(a0, an));
+            amax = fminf(amax, fmaxf(a0, an));
+        }
+    }
+    if (amin < amax && amin > 0.0f) {
+        p.px = __fadd_rn(p.px, __fmul_rn(amin, p.dx));
+        p.py = __fadd_rn(p.py, __fmul_rn(amin, p.dy));
+        p.pz = __fadd_rn(p.pz, __fmul_rn(amin, p.dz));
+        return true;
+    }
+    return false;
+}
+
+// ---- attenuation tables (attenuationinterpolator.hpp:207-248) -------------------------------
+// first index with knots[i] > v, or n when none (std::upper_bound)
+__device__ __forceinline__ uint32_t upperBound(const float* __restrict__ a, uint32_t n, float v)
+{
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (v < a[mid])
+            hi = mid;
+        else
+            lo = mid + 1;
+    }
+    return lo;
+}
+
+__device__ __forceinline__ uint32_t segmentIndex(const LutView& l, float logE, bool clampLinear)
+{
+    if (logE > l.linearEnergy) {
+        const uint32_t i = __float2uint_rz(__fdiv_rn(__fsub_rn(logE, l.linearEnergy), l.linearStep)) + l.linearIndex;
+        return clampLinear ? min(i, l.nSegments - 1) : i;
+    }
+    const uint32_t pos = upperBound(l.knots, l.nSegments, logE);
+    return pos != l.nSegments ? pos : l.nSegments - 1;
+}
+
+// photo, Compton, Rayleigh mass attenuation of one material at log10(E)
+__device__ __forceinline__ void attenuation(const LutView& l, uint32_t material, float logE, float& photo, float& compton, float& rayleigh)
+{
+    const uint32_t index = segmentIndex(l, logE, true);
+    const float* c = l.coeff + (static_cast<size_t>(material) * l.nSegments + index) * 6;
+    photo = exp10f(__fadd_rn(c[0], __fmul_rn(c[1], logE)));
+    compton = exp10f(__fadd_rn(c[2], __fmul_rn(c[3], logE)));
+    rayleigh = exp10f(__fadd_rn(c[4], __fmul_rn(c[5], logE)));
+}
+
+// inverse of the Woodcock majorant; the linear branch is not clamped in the reference either
+__device__ __forceinline__ float maxAttenuationInverse(const LutView& l, float logE)
+{
+    uint32_t index = segmentIndex(l, logE, false);
+    index = min(index, l.nSegments - 1); // memory safety only; never binds for E <= max table energy
+    const float* c = l.maxCoeff + 2 * index;
+    return exp10f(__fadd_rn(c[0], __fmul_rn(c[1], logE)));
+}
+
+// Compton scatter function S(q)/Z, cubic spline (interpolation.hpp:169-176)
+__device__ __forceinline__ float scatterFactor(const LutView& l, uint32_t material, float q)
+{
+    const float* s = l.spline + material * DXMCB200_SPLINE_FLOATS;
+    const float start = s[60], step = s[61], stop = s[62];
+    const float x = fminf(fmaxf(q, start), stop);
+    const uint32_t index = x > start ? __float2uint_rz(__fdiv_rn(__fsub_rn(x, start), step)) : 0u;
+    const uint32_t offset = index < DXMCB200_SPLINE_N - 1 ? index * 4 : (DXMCB200_SPLINE_N - 2) * 4;
+    const float* c = s + offset;
+    // c0 + c1*x + c2*x*x + c3*x*x*x, left to right
+    float r = __fadd_rn(c[0], __fmul_rn(c[1], x));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(c[2], x), x));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(c[3], x), x), x));
+    return r;
+}
+
+// q^2 sampled from the squared form factor, truncated at maxValue (dxmcrandom.hpp:483-500)
+__device__ __forceinline__ float sampleFormFactor(const LutView& l, uint32_t material, float maxValue, Rng& rng)
+{
+    const float* x = l.rita + material * (4 * DXMCB200_RITA_N);
+    const float* e = x + DXMCB200_RITA_N;
+    const float* a = e + DXMCB200_RITA_N;
+    const float* b = a + DXMCB200_RITA_N;
+    const uint32_t maxIndex = upperBound(x, DXMCB200_RITA_N, maxValue);
+    const float modifier = maxIndex != DXMCB200_RITA_N ? e[maxIndex] : 1.0f;
+    float res;
+    do {
+        const float r1 = rng.uniform(modifier);
+        const int index = static_cast<int>(upperBound(e, DXMCB200_RITA_N, r1)) - 1;
+        const float v = r1 - e[index];
+        const float d = e[index + 1] - e[index];
+        const float ai = a[index], bi = b[index];
+        res = x[index] + (1.0f + ai + bi) * d * v / (d * d + ai * d * v + bi * v * v) * (x[index + 1] - x[index]);
+    } while (res > maxValue);
+    return res;
+}
+
+// ---- beam sampling (exposure.hpp:280-304, dxmcrandom.hpp:211-216, 322-326, beamfilters.hpp) ---
+__device__ __forceinline__ float sampleSpectrum(const SpectrumView& s, Rng& rng)
+{
+    const float r = rng.uniform();
+    uint32_t k;
+    for (;;) { // bounded integer by rejection, threshold as the reference computes it
+        const uint32_t u = rng.next();
+        if (u >= s.threshold) {
+            k = u % s.n;
+            break;
+        }
+    }
+    const uint32_t ind = r < s.probs[k] ? k : s.alias[k];
+    return ind < s.n - 1 ? rng.uniform(s.energies[ind], s.energies[ind + 1]) : s.energies[ind];
+}
+
+__device__ __forceinline__ float bowtieWeight(const BowtieView& b, float anglePlusMinus)
+{
+    const float angle = fabsf(anglePlusMinus);
+    uint32_t first = 0, last = b.n - 1;
+    uint32_t it = first + (last - first) / 2;
+    while (it != first) { // the reference's bisection (beamfilters.hpp:158-171)
+        if (angle < b.angles[it])
+            last = it;
+        else
+            first = it;
+        it = first + (last - first) / 2;
+    }
+    if (angle < b.angles[first])
+        return b.weights[0];
+    if (angle > b.angles[last])
+        return b.weights[b.n - 1];
+    const float x0 = b.angles[first], x1 = b.angles[last];
+    const float y0 = b.weights[first], y1 = b.weights[last];
+    return y0 + (angle - x0) * (y1 - y0) / (x1 - x0);
+}
+
+__device__ __forceinline__ float heelWeight(const HeelView& h, float angle, float energy)
+{
+    // size_t casts of negative floats are undefined in the reference; the two guards below override them
+    uint32_t eIndex = __float2uint_rz((energy - h.energyStart + 0.5f * h.energyStep) / h.energyStep);
+    if (eIndex >= h.energySize)
+        eIndex = h.energySize - 1;
+    if (energy < h.energyStart)
+        eIndex = 0;
+    uint32_t aIndex = __float2uint_rz((angle - h.angleStart) / h.angleStep);
+    if (aIndex >= h.angleSize)
+        aIndex = h.angleSize - 1;
+    if (angle < h.angleStart)
+        aIndex = 0;
+    const uint32_t wIndex = eIndex * h.angleSize + aIndex;
+    if (aIndex < h.angleSize - 1) {
+        const float a0 = h.angleStart + h.angleStep * aIndex;
+        const float a1 = h.angleStart + h.angleStep * (aIndex + 1);
+        const float w0 = h.weights[wIndex];
+        const float w1 = h.weights[wIndex + 1];
+        return w0 + (w1 - w0) * (angle - a0) / (a1 - a0);
+    }
+    return h.weights[wIndex];
+}
+
+__device__ __forceinline__ Photon sampleParticle(const dxmcb200_exposure& e, const BeamView& beams, Rng& rng)
+{
+    const float theta = rng.uniform(e.collimation[0], e.collimation[1]);
+    const float phi = rng.uniform(e.collimation[2], e.collimation[3]);
+    Photon p;
+    p.px = e.position[0];
+    p.py = e.position[1];
+    p.pz = e.position[2];
+    p.dx = e.beam_direction[0];
+    p.dy = e.beam_direction[1];
+    p.dz = e.beam_direction[2];
+    p.weight = e.weight;
+    rotate(p.dx, p.dy, p.dz, e.cosines[3], e.cosines[4], e.cosines[5], theta);
+    rotate(p.dx, p.dy, p.dz, e.cosines[0], e.cosines[1], e.cosines[2], phi);
+    p.energy = e.spectrum >= 0 ? sampleSpectrum(beams.spectra[e.spectrum], rng) : e.mono_energy;
+    if (e.bowtie >= 0)
+        p.weight *= bowtieWeight(beams.bowties[e.bowtie], theta);
+    if (e.heel >= 0)
+        p.weight *= heelWeight(beams.heels[e.heel], phi, p.energy);
+    return p;
+}
+
+// ---- interactions (transport.hpp:216-483) ------------------------------------------------------
+struct ShellView {
+    const float* s;
+    __device__ __forceinline__ float binding(int i) const { return s[i * DXMCB200_SHELL_FLOATS + 0]; }
+    __device__ __forceinline__ float nElectrons(int i) const { return s[i * DXMCB200_SHELL_FLOATS + 1]; }
+    __device__ __forceinline__ float j0(int i) const { return s[i * DXMCB200_SHELL_FLOATS + 2]; }
+    __device__ __forceinline__ float photoProb(int i) const { return s[i * DXMCB200_SHELL_FLOATS + 3]; }
+    __device__ __forceinline__ float yield(int i) const { return s[i * DXMCB200_SHELL_FLOATS + 4]; }
+    __device__ __forceinline__ float lineProb(int i, int k) const { return s[i * DXMCB200_SHELL_FLOATS + 5 + k]; }
+    __device__ __forceinline__ float lineEnergy(int i, int k) const { return s[i * DXMCB200_SHELL_FLOATS + 8 + k]; }
+};
+
+// returns energy imparted locally; p.energy is 0 or the fluorescence line energy afterwards
+template <int L>
+__device__ __forceinline__ float photoAbsorption(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    const float E = p.energy;
+    p.energy = 0.0f;
+    if constexpr (L < 2) {
+        return E;
+    } else {
+        const ShellView sh { l.shells + material * (DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS) };
+        float cum[DXMCB200_SHELLS];
+        float acc = 0.0f;
+#pragma unroll
+        for (int i = 0; i < DXMCB200_SHELLS; ++i) {
+            acc += E > sh.binding(i) ? sh.photoProb(i) : 0.0f;
+            cum[i] = acc;
+        }
+        const float sample = cum[DXMCB200_SHELLS - 1] * rng.uniform();
+        int idx = 0;
+        while (cum[idx] < sample && idx < DXMCB200_SHELLS - 1)
+            ++idx;
+        if (sh.binding(idx) > E || sh.binding(idx) < kEnergyCutoff)
+            return E;
+        const float r1 = rng.uniform();
+        if (r1 <= sh.yield(idx)) {
+            int line = 0;
+            float r3 = rng.uniform() - sh.lineProb(idx, line);
+            while (r3 > 0.0f && line < 2) {
+                ++line;
+                r3 -= sh.lineProb(idx, line);
+            }
+            p.energy = sh.lineEnergy(idx, line);
+            const float theta = rng.uniform(kPi);
+            const float phi = rng.uniform(kTwoPi);
+            peturb(p, theta, phi);
+            return E - p.energy;
+        }
+        return E;
+    }
+}
+
+template <int L>
+__device__ __forceinline__ void rayleighScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    float theta;
+    if constexpr (L == 0) {
+        bool reject = true;
+        while (reject) {
+            constexpr float extreme = (4.0f * 1.41421356237309504880f) / (3.0f * 1.73205080756887729353f);
+            const float r1 = rng.uniform(0.0f, extreme);
+            theta = rng.uniform(0.0f, kPi);
+            const float sinang = sinf(theta);
+            reject = r1 > ((2.0f - sinang * sinang) * sinang);
+        }
+    } else {
+        constexpr float kInv = 1.0f / kKevToAngstrom;
+        const float qmax = p.energy * kInv;
+        const float qmaxSquared = qmax * qmax;
+        float cosAngle;
+        do {
+            const float qSquared = sampleFormFactor(l, material, qmaxSquared, rng);
+            const float invE = kKevToAngstrom / p.energy;
+            cosAngle = 1.0f - 2.0f * qSquared * invE * invE;
+        } while ((1.0f + cosAngle * cosAngle) * 0.5f < rng.uniform());
+        theta = acosf(cosAngle);
+    }
+    const float phi = rng.uniform(kTwoPi);
+    peturb(p, theta, phi);
+}
+
+// EGSnrc-style impulse approximation with Doppler broadening (transport.hpp:342-483)
+__device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    const ShellView sh { l.shells + material * (DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS) };
+    float cum[DXMCB200_SHELLS];
+    float acc = 0.0f;
+#pragma unroll
+    for (int i = 0; i < DXMCB200_SHELLS; ++i) {
+        acc += (sh.binding(i) < p.energy && sh.j0(i) > 0.0f) ? sh.nElectrons(i) : 0.0f;
+        cum[i] = acc;
+    }
+    int shellIdx = 0;
+    const float shellSample = cum[DXMCB200_SHELLS - 1] * rng.uniform();
+    while (cum[shellIdx] < shellSample && shellIdx < DXMCB200_SHELLS - 1)
+        ++shellIdx;
+
+    const float U = sh.binding(shellIdx) / kElectronRestMass;
+    const float pb = sqrtf(2.0f * U + U * U);
+    const float J0 = sh.j0(shellIdx);
+    const float k = p.energy / kElectronRestMass;
+    if (U > k)
+        return 0.0f;
+
+    const float emin = 1.0f / (1.0f + 2.0f * k);
+    const float gmaxInv = 1.0f / (1.0f / emin + emin);
+    float e, cosAngle;
+    bool rejected;
+    do {
+        const float r1 = rng.uniform();
+        e = r1 + (1.0f - r1) * emin;
+        const float t = (1.0f - e) / (k * e);
+        const float sinAngleSqr = t * (2.0f - t);
+        cosAngle = 1.0f - t;
+        const float g = (1.0f / e + e - sinAngleSqr) * gmaxInv;
+        const float r2 = rng.uniform();
+        rejected = r2 > g;
+        if (!rejected) {
+            const float pi = (k * (k - U) * (1.0f - cosAngle) - U) / sqrtf(2.0f * k * (k - U) * (1.0f - cosAngle) + U * U);
+            const float kc = k * e;
+            const float qc = sqrtf(k * k + kc * kc - 2.0f * k * kc * cosAngle);
+            const float alpha = qc * (1.0f + kc * (kc - k * cosAngle) / (qc * qc)) / k;
+            const float bPart = 1.0f + 2.0f * J0 * fabsf(pi);
+            const float b = (bPart * bPart + 1.0f) / 2.0f;
+            const float expb = expf(-b);
+
+            float S;
+            if (pi <= -pb) {
+                S = (1.0f - alpha * pb) * expb / 2.0f;
+            } else if (pi < pb) {
+                const float pabs = fabsf(pb);
+                const float piabs = fabsf(pi);
+                constexpr float sp2 = 1.0f / (0.564189583547756286948f / 1.41421356237309504880f);
+                const float part1 = alpha * sp2 / (4.0f * J0);
+                constexpr float a1 = 0.34802f, a2 = -0.0958798f, a3 = 0.7478556f;
+                const float sqrte = sqrtf(2.71828182845904523536f);
+                const float tp = 1.0f / (1.0f + 0.332673f * (1.0f + 2.0f * J0 * pabs));
+                const float tpi = 1.0f / (1.0f + 0.332673f * (1.0f + 2.0f * J0 * piabs));
+                const float part2p = sqrte - expb * tp * (a1 + a2 * tp + a3 * tp * tp);
+                const float part2pi = sqrte - expb * tpi * (a1 + a2 * tpi + a3 * tpi * tpi);
+                if (pi <= 0.0f)
+                    S = (1.0f - alpha * pi) * expb / 2.0f - part1 * (part2p - part2pi);
+                else
+                    S = 1.0f - (1.0f - alpha * pi) * expb / 2.0f - part1 * (part2p - part2pi);
+            } else {
+                S = 1.0f - (1.0f - alpha * pb) * expb / 2.0f;
+            }
+            const float r3 = rng.uniform();
+            rejected = r3 > S;
+            if (!rejected) {
+                float Fmax;
+                if (pi <= -pb)
+                    Fmax = 1.0f - alpha * pb;
+                else if (pi >= pb)
+                    Fmax = 1.0f + alpha * pb;
+                else
+                    Fmax = 1.0f + alpha * pi;
+                const float r4 = rng.uniform();
+                const float rBar2 = 2.0f * r4 * expb;
+                float pz;
+                if (rBar2 < 1.0f) {
+                    const float part = sqrtf(1.0f - 2.0f * logf(rBar2));
+                    pz = (1.0f - part) / (2.0f * J0) / kElectronRestMass;
+                } else {
+                    const float part = sqrtf(1.0f - 2.0f * logf(2.0f - rBar2));
+                    pz = (part - 1.0f) / (2.0f * J0) / kElectronRestMass;
+                }
+                float Fpz;
+                if (pz <= -pb)
+                    Fpz = 1.0f - alpha * pb;
+                else if (pz >= pb)
+                    Fpz = 1.0f + alpha * pb;
+                else
+                    Fpz = 1.0f + alpha * pz;
+                const float r5 = rng.uniform();
+                rejected = r5 > Fpz / Fmax;
+                if (!rejected) {
+                    const float part = sqrtf(1.0f - 2.0f * e * cosAngle + e * e * (1.0f - pz * pz * sinAngleSqr));
+                    const float kBar = kc / (1.0f - pz * pz * e * e) * (1.0f - pz * pz * e * cosAngle + pz * part);
+                    e = kBar / k;
+                }
+            }
+        }
+    } while (rejected);
+    const float theta = acosf(cosAngle);
+    const float phi = rng.uniform(kTwoPi);
+    peturb(p, theta, phi);
+    const float E = p.energy;
+    p.energy *= e;
+    return E - p.energy;
+}
+
+// Klein-Nishina rejection sampling, optionally weighted by the scatter function (transport.hpp:300-340)
+template <int L>
+__device__ __forceinline__ float comptonScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    if constexpr (L == 2) {
+        return comptonScatterIA(l, p, material, rng);
+    } else {
+        const float E = p.energy;
+        const float k = E / kElectronRestMass;
+        const float emin = 1.0f / (1.0f + 2.0f * k);
+        const float gmaxInv = 1.0f / (1.0f / emin + emin);
+        float e, cosAngle;
+        bool rejected;
+        do {
+            const float r1 = rng.uniform();
+            e = r1 + (1.0f - r1) * emin;
+            const float t = (1.0f - e) / (k * e);
+            const float sinthetasqr = t * (2.0f - t);
+            cosAngle = 1.0f - t;
+            const float g = (1.0f / e + e - sinthetasqr) * gmaxInv;
+            const float r2 = rng.uniform();
+            if constexpr (L == 1) {
+                constexpr float kInv = 1.0f / kKevToAngstrom;
+                const float q = E * kInv * sqrtf(0.5f - cosAngle * 0.5f);
+                rejected = r2 > g * scatterFactor(l, material, q);
+            } else {
+                rejected = r2 > g;
+            }
+        } while (rejected);
+        const float theta = acosf(cosAngle);
+        const float phi = rng.uniform(kTwoPi);
+        peturb(p, theta, phi);
+        p.energy *= e;
+        return E - p.energy;
+    }
+}
+
+} // namespace dxmcb200

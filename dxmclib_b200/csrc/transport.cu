@@ -1,0 +1,1143 @@
+// transport.cu — sm_100a photon-transport kernels and the C ABI runtime around them.
+//
+// Replaces the reference's worker threads (transport.hpp:729-778). One persistent launch
+// covers a range of exposures: every lane of every warp owns one photon history at a time and
+// pulls the next (exposure, history) pair from a global counter when its photon dies. Lanes are
+// regrouped inside the warp by stage so divergent work runs on batches of lanes:
+//   DEAD      waiting for a new history   (birth = Exposure::sampleParticle + AABB entry)
+//   STEP      Woodcock delta tracking      (one voxel record fetch per step)
+//   INTERACT  a real / forced interaction is pending (photo / Compton / Rayleigh sampling, scoring)
+// Births and interactions are executed only when at least kBirthBatch / kInteractBatch lanes wait
+// for them (or nothing else can run), which keeps the rejection-sampling code off the critical
+// path of the stepping lanes. Histories carry their own counter-derived PCG32 stream, and scoring
+// is 64-bit fixed-point integer atomics, so results do not depend on scheduling.
+#include "physics.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace dxmcb200;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr unsigned kFull = 0xffffffffu;
+
+enum LaneState : uint32_t { DEAD = 0, STEP = 1, INTERACT = 2 };
+
+struct Counters {
+    unsigned long long histories, inWorld, steps, lookups, interactions, scores;
+};
+
+struct KernelParams {
+    WorldView world;
+    LutView lut;
+    BeamView beams;
+    const dxmcb200_exposure* exposures; // absolute indexing
+    const uint64_t* prefix; // [nExp+1] cumulative histories of the launched range
+    uint64_t expBegin;
+    uint32_t nExp;
+    uint64_t totalHistories;
+    uint64_t seed;
+    unsigned long long* workCounter;
+    unsigned long long* acc; // [nVoxels][4]
+    Counters* counters;
+    float energyScale, energySqScale;
+};
+
+// ---- scoring: 64-bit fixed point (replaces safeValueAdd, transport.hpp:208-214) ------------------
+__device__ __forceinline__ void scoreEnergy(const KernelParams& P, uint32_t voxel, float energyImparted)
+{
+    const long long fe = __float2ll_rn(energyImparted * P.energyScale);
+    const unsigned long long fe2 = __float2ull_rn((energyImparted * energyImparted) * P.energySqScale);
+    unsigned long long* a = P.acc + static_cast<size_t>(voxel) * 4;
+    atomicAdd(a + 0, static_cast<unsigned long long>(fe));
+    atomicAdd(a + 1, fe2);
+    atomicAdd(a + 2, 1ULL);
+}
+
+struct Pending { // what an INTERACT lane needs from the step that found the event
+    float attPhoto, attCompton, attRayleigh;
+    float eventProbability;
+    uint32_t voxel;
+    uint32_t material; // bits 0-7 material, bit 8 forced
+};
+
+// computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
+template <int L, bool kStats>
+__device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores)
+{
+    const uint32_t mat = pe.material & 0xffu;
+    const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
+    const float r3 = rng.uniform(attTotal);
+    if (r3 < pe.attPhoto) {
+        const float e = photoAbsorption<L>(P.lut, p, mat, rng);
+        if constexpr (kStats)
+            ++nScores;
+        if (p.energy < kEnergyCutoff) {
+            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
+            p.energy = 0.0f;
+            return false;
+        }
+        scoreEnergy(P, pe.voxel, e * p.weight);
+        energyChanged = true;
+    } else if (r3 < (pe.attPhoto + pe.attCompton)) {
+        const float e = comptonScatter<L>(P.lut, p, mat, rng);
+        if constexpr (kStats)
+            ++nScores;
+        if (p.energy < kEnergyCutoff) {
+            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
+            p.energy = 0.0f;
+            return false;
+        }
+        scoreEnergy(P, pe.voxel, e * p.weight);
+        energyChanged = true;
+    } else {
+        rayleighScatter<L>(P.lut, p, mat, rng);
+    }
+    return true;
+}
+
+// computeInteractionsForced (transport.hpp:523-581)
+template <int L, bool kStats>
+__device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores)
+{
+    const uint32_t mat = pe.material & 0xffu;
+    const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
+    const float photoEventProbability = pe.attPhoto / attTotal;
+    const float weightCorrection = pe.eventProbability * photoEventProbability;
+    {
+        Photon forced = p;
+        const float eForced = photoAbsorption<L>(P.lut, forced, mat, rng);
+        if constexpr (kStats)
+            ++nScores;
+        if (forced.energy < kEnergyCutoff)
+            scoreEnergy(P, pe.voxel, (eForced + forced.energy) * forced.weight * weightCorrection);
+        else
+            scoreEnergy(P, pe.voxel, eForced * forced.weight * weightCorrection);
+    }
+    const float r1 = rng.uniform();
+    if (r1 < pe.eventProbability * (1.0f - photoEventProbability)) {
+        const float r2 = rng.uniform(pe.attCompton + pe.attRayleigh);
+        if (r2 < pe.attCompton) {
+            const float e = comptonScatter<L>(P.lut, p, mat, rng);
+            if constexpr (kStats)
+                ++nScores;
+            if (p.energy < kEnergyCutoff) {
+                scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
+                p.energy = 0.0f;
+                return false;
+            }
+            scoreEnergy(P, pe.voxel, e * p.weight);
+            energyChanged = true;
+        } else {
+            rayleighScatter<L>(P.lut, p, mat, rng);
+        }
+    }
+    p.weight *= (1.0f - weightCorrection);
+    return true;
+}
+
+// Russian roulette (transport.hpp:684-693); false when the photon is killed
+__device__ __forceinline__ bool roulette(Photon& p, Rng& rng)
+{
+    if (p.energy * p.weight < kRouletteThreshold) {
+        const float r4 = rng.uniform();
+        if (r4 < kRouletteProbability)
+            return false;
+        constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+        p.weight *= factor;
+    }
+    return true;
+}
+
+template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
+__global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constant__ KernelParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+
+    Rng rng { 0, 1 };
+    Photon p {};
+    Pending pe {};
+    float maxAttInv = 0.0f, logE = 0.0f;
+    uint32_t state = DEAD;
+    bool exhausted = false;
+    uint32_t cHist = 0, cWorld = 0, cSteps = 0, cLookups = 0, cInter = 0, cScores = 0;
+
+    for (;;) {
+        const unsigned deadMask = __ballot_sync(kFull, state == DEAD && !exhausted);
+        const unsigned stepMask = __ballot_sync(kFull, state == STEP);
+        const unsigned intMask = __ballot_sync(kFull, state == INTERACT);
+        if ((deadMask | stepMask | intMask) == 0)
+            break;
+
+        // ---- births: Exposure::sampleParticle + transportParticleToWorld (transport.hpp:733-741)
+        if (deadMask && (__popc(deadMask) >= kBirthBatch || stepMask == 0)) {
+            const int leader = __ffs(deadMask) - 1;
+            unsigned long long base = 0;
+            if (static_cast<int>(lane) == leader)
+                base = atomicAdd(P.workCounter, static_cast<unsigned long long>(__popc(deadMask)));
+            base = __shfl_sync(kFull, base, leader);
+            if (state == DEAD && !exhausted) {
+                const uint64_t g = base + __popc(deadMask & laneLt);
+                if (g >= P.totalHistories) {
+                    exhausted = true;
+                } else {
+                    // exposure owning history g: last prefix entry <= g
+                    uint32_t lo = 0, hi = P.nExp;
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(P.prefix + mid) <= g)
+                            lo = mid;
+                        else
+                            hi = mid;
+                    }
+                    const uint64_t history = g - __ldg(P.prefix + lo);
+                    const uint64_t exposure = P.expBegin + lo;
+                    historyStream(P.seed, exposure, history, rng.state, rng.inc);
+                    p = sampleParticle(P.exposures[exposure], P.beams, rng);
+                    if constexpr (kStats)
+                        ++cHist;
+                    if (transportToWorld(P.world, p)) {
+                        state = STEP;
+                        logE = log10f(p.energy);
+                        maxAttInv = maxAttenuationInverse(P.lut, logE);
+                        if constexpr (kStats)
+                            ++cWorld;
+                    }
+                }
+            }
+        }
+
+        // ---- interactions, batched
+        if (intMask && (__popc(intMask) >= kInteractBatch || stepMask == 0)) {
+            if (state == INTERACT) {
+                bool energyChanged = false;
+                bool alive;
+                if (pe.material & 0x100u)
+                    alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+                else
+                    alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+                if constexpr (kStats)
+                    ++cInter;
+                if (alive)
+                    alive = roulette(p, rng);
+                if (alive) {
+                    state = STEP;
+                    if (energyChanged) {
+                        logE = log10f(p.energy);
+                        maxAttInv = maxAttenuationInverse(P.lut, logE);
+                    }
+                } else {
+                    state = DEAD;
+                }
+            }
+        }
+
+        // ---- one Woodcock step (transport.hpp:655-682)
+        if (state == STEP) {
+            const float r1 = rng.uniform();
+            const float stepLength = -logf(r1) * maxAttInv * 10.0f;
+            advance(p, stepLength);
+            if constexpr (kStats)
+                ++cSteps;
+            if (!insideWorld(P.world, p.px, p.py, p.pz)) {
+                state = DEAD;
+            } else {
+                const uint32_t voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+                const uint2 rec = __ldg(P.world.voxels + voxel);
+                const float density = __uint_as_float(rec.x);
+                const uint32_t mat = rec.y & 0xffu;
+                const uint32_t measurement = (rec.y >> 8) & 0xffu;
+                if constexpr (kStats)
+                    ++cLookups;
+                float aP, aC, aR;
+                attenuation(P.lut, mat, logE, aP, aC, aR);
+                const float attTotal = (((0.0f + aP) + aC) + aR) * density;
+                const float eventProbability = attTotal * maxAttInv;
+                if (measurement == 0) {
+                    const float r2 = rng.uniform();
+                    if (r2 < eventProbability) {
+                        pe = Pending { aP, aC, aR, eventProbability, voxel, mat };
+                        state = INTERACT;
+                    } else if (!roulette(p, rng)) {
+                        state = DEAD;
+                    }
+                } else {
+                    pe = Pending { aP, aC, aR, eventProbability, voxel, mat | 0x100u };
+                    state = INTERACT;
+                }
+            }
+        }
+    }
+
+    if constexpr (kStats) {
+        auto warpSum = [](uint32_t v) {
+            unsigned long long s = v;
+            for (int o = 16; o > 0; o >>= 1)
+                s += __shfl_xor_sync(kFull, s, o);
+            return s;
+        };
+        const unsigned long long h = warpSum(cHist), w = warpSum(cWorld), s = warpSum(cSteps), l = warpSum(cLookups),
+                                 i = warpSum(cInter), sc = warpSum(cScores);
+        if (lane == 0) {
+            atomicAdd(&P.counters->histories, h);
+            atomicAdd(&P.counters->inWorld, w);
+            atomicAdd(&P.counters->steps, s);
+            atomicAdd(&P.counters->lookups, l);
+            atomicAdd(&P.counters->interactions, i);
+            atomicAdd(&P.counters->scores, sc);
+        }
+    }
+}
+
+// ---- small kernels -----------------------------------------------------------------------------
+__global__ void packVoxelsKernel(const float* __restrict__ density, const uint8_t* __restrict__ material,
+    const uint8_t* __restrict__ measurement, uint2* __restrict__ out, uint64_t n)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t m = material[i] | (measurement ? (static_cast<uint32_t>(measurement[i]) << 8) : 0u);
+        out[i] = make_uint2(__float_as_uint(density[i]), m);
+    }
+}
+
+// normalizeScoring / energyImpartedToDose (transport.hpp:780-816) fused with the fixed-point decode
+__global__ void resultKernel(const unsigned long long* __restrict__ acc, const uint2* __restrict__ voxels, uint64_t n, int mode,
+    float energyLsb, float energySqLsb, uint64_t histories, float calibration, float voxelVolume, float* __restrict__ dose,
+    uint32_t* __restrict__ nEvents, float* __restrict__ variance)
+{
+    const float hInv = 1.0f / static_cast<float>(histories - 1);
+    const float hdInv = 1.0e3f / static_cast<float>(histories);
+    const float hvInv = 1.0e6f / static_cast<float>(histories);
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const ulonglong4 a = reinterpret_cast<const ulonglong4*>(acc)[i];
+        const float e = static_cast<float>(static_cast<double>(static_cast<long long>(a.x)) * static_cast<double>(energyLsb));
+        const float e2 = static_cast<float>(static_cast<double>(a.y) * static_cast<double>(energySqLsb));
+        float d = e, v = e2;
+        if (mode == 0) {
+            d = e * hdInv;
+            v = (e2 * hvInv - d * d) * hInv;
+        } else if (mode == 1) {
+            const float de = __uint_as_float(voxels[i].x);
+            const float voxelMass = de * voxelVolume * 0.001f;
+            const float factor = calibration / voxelMass;
+            d = de > 0.0f ? e * factor : 0.0f;
+            v = de > 0.0f ? e2 * factor * factor : 0.0f;
+        }
+        if (dose)
+            dose[i] = d;
+        if (variance)
+            variance[i] = v;
+        if (nEvents)
+            nEvents[i] = static_cast<uint32_t>(a.z);
+    }
+}
+
+__global__ void rawKernel(const unsigned long long* __restrict__ acc, uint64_t n, long long* energy, unsigned long long* energySq,
+    unsigned long long* events)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const ulonglong4 a = reinterpret_cast<const ulonglong4*>(acc)[i];
+        if (energy)
+            energy[i] = static_cast<long long>(a.x);
+        if (energySq)
+            energySq[i] = a.y;
+        if (events)
+            events[i] = a.z;
+    }
+}
+
+__global__ void evalAttenuationKernel(LutView lut, uint64_t n, const uint8_t* material, const float* energy, float* out3, float* outMax)
+{
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    const float logE = log10f(energy[i]);
+    float a, b, c;
+    attenuation(lut, material[i], logE, a, b, c);
+    out3[3 * i + 0] = a;
+    out3[3 * i + 1] = b;
+    out3[3 * i + 2] = c;
+    outMax[i] = maxAttenuationInverse(lut, logE);
+}
+
+__global__ void traceIndicesKernel(WorldView w, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps,
+    long long* outIdx, float* outEntry)
+{
+    const uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (r >= nRays)
+        return;
+    Photon p {};
+    p.px = pos[3 * r];
+    p.py = pos[3 * r + 1];
+    p.pz = pos[3 * r + 2];
+    p.dx = dir[3 * r];
+    p.dy = dir[3 * r + 1];
+    p.dz = dir[3 * r + 2];
+    long long* o = outIdx + r * (nSteps + 1);
+    bool in = transportToWorld(w, p);
+    outEntry[3 * r] = p.px;
+    outEntry[3 * r + 1] = p.py;
+    outEntry[3 * r + 2] = p.pz;
+    // the entry point sits on the safe extent; the reference only indexes after the first step
+    o[0] = (in && insideWorld(w, p.px, p.py, p.pz)) ? static_cast<long long>(voxelIndex(w, p.px, p.py, p.pz)) : -1;
+    for (uint32_t k = 0; k < nSteps; ++k) {
+        if (in) {
+            advance(p, steps[k]);
+            in = insideWorld(w, p.px, p.py, p.pz);
+        }
+        o[k + 1] = in ? static_cast<long long>(voxelIndex(w, p.px, p.py, p.pz)) : -1;
+    }
+}
+
+__global__ void sampleParticlesKernel(dxmcb200_exposure e, BeamView beams, uint64_t exposureIndex, uint64_t seed, uint64_t n, float* out)
+{
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    Rng rng;
+    historyStream(seed, exposureIndex, i, rng.state, rng.inc);
+    const Photon p = sampleParticle(e, beams, rng);
+    float* o = out + 8 * i;
+    o[0] = p.px;
+    o[1] = p.py;
+    o[2] = p.pz;
+    o[3] = p.dx;
+    o[4] = p.dy;
+    o[5] = p.dz;
+    o[6] = p.energy;
+    o[7] = p.weight;
+}
+
+template <int L>
+__global__ void sampleInteractionKernel(LutView lut, int kind, uint8_t material, float energy, uint64_t seed, uint64_t n, float* out)
+{
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    Rng rng;
+    historyStream(seed, 0, i, rng.state, rng.inc);
+    Photon p {};
+    p.dz = 1.0f;
+    p.energy = energy;
+    p.weight = 1.0f;
+    float imparted = 0.0f;
+    if (kind == 0)
+        imparted = photoAbsorption<L>(lut, p, material, rng);
+    else if (kind == 1)
+        imparted = comptonScatter<L>(lut, p, material, rng);
+    else
+        rayleighScatter<L>(lut, p, material, rng);
+    float* o = out + 5 * i;
+    o[0] = imparted;
+    o[1] = p.energy;
+    o[2] = p.dx;
+    o[3] = p.dy;
+    o[4] = p.dz;
+}
+
+} // namespace
+
+// ================================================================================================
+// runtime
+// ================================================================================================
+struct dxmcb200_ctx {
+    int device = 0;
+    int smCount = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t evStart = nullptr, evStop = nullptr;
+    std::string error;
+
+    // world
+    WorldView world {};
+    uint64_t nVoxels = 0;
+    uint2* dVoxels = nullptr;
+    unsigned long long* dAcc = nullptr;
+
+    // luts
+    LutView lut {};
+    float* dLutBlob = nullptr;
+
+    // beams
+    BeamView beams {};
+    void* dBeamBlob = nullptr;
+
+    // exposures
+    dxmcb200_exposure* dExposures = nullptr;
+    uint64_t nExposuresResident = 0;
+    std::vector<dxmcb200_exposure> hExposures; // host copy of the resident table (for prefix sums)
+    uint64_t* dPrefix = nullptr;
+    uint64_t prefixCapacity = 0;
+
+    unsigned long long* dWorkCounter = nullptr;
+    Counters* dCounters = nullptr;
+
+    int energyBits = 20, energySqBits = 10;
+    bool collectStats = false;
+    uint64_t maxHistoriesPerLaunch = 2000000000ULL;
+
+    double lastRunMs = 0, totalMs = 0;
+    uint64_t launches = 0;
+};
+
+namespace {
+
+#define CU_CHECK(ctx, expr)                                                                        \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            (ctx)->error = std::string(#expr) + ": " + cudaGetErrorString(_e);                     \
+            return DXMCB200_ERR_CUDA;                                                              \
+        }                                                                                          \
+    } while (0)
+
+int gridFor(const dxmcb200_ctx* c, uint64_t n)
+{
+    const uint64_t blocks = (n + 255) / 256;
+    return static_cast<int>(std::min<uint64_t>(blocks, static_cast<uint64_t>(c->smCount) * 16));
+}
+
+template <typename T>
+T* advancePtr(char*& cursor, size_t count)
+{
+    // 16-byte aligned carve-out from a blob
+    size_t addr = reinterpret_cast<size_t>(cursor);
+    addr = (addr + 15) & ~static_cast<size_t>(15);
+    T* p = reinterpret_cast<T*>(addr);
+    cursor = reinterpret_cast<char*>(addr + count * sizeof(T));
+    return p;
+}
+
+template <int L, bool kStats>
+cudaError_t launchTransport(const dxmcb200_ctx* c, const KernelParams& P)
+{
+    constexpr int kBirthBatch = 8, kInteractBatch = 8;
+    auto kernel = transportKernel<L, kStats, kBirthBatch, kInteractBatch>;
+    int blocksPerSm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
+    if (e != cudaSuccess)
+        return e;
+    blocksPerSm = std::max(blocksPerSm, 1);
+    // persistent grid: a whole number of resident CTAs per SM, never more lanes than histories
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * blocksPerSm;
+    const uint64_t needed = (P.totalHistories + kThreads - 1) / kThreads;
+    blocks = std::max<uint64_t>(1, std::min(blocks, needed));
+    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
+    return cudaGetLastError();
+}
+
+int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmcb200_exposure* devExposures, uint64_t expBegin,
+    uint64_t expEnd, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
+{
+    if (!c->dVoxels || !c->dLutBlob)
+        return DXMCB200_ERR_STATE;
+    if (model < 0 || model > 2 || expEnd < expBegin)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    c->lastRunMs = 0;
+    uint64_t e0 = expBegin;
+    while (e0 < expEnd) {
+        if (cancel && *cancel)
+            return DXMCB200_ERR_CANCELLED;
+        // chunk of exposures bounded by histories per launch
+        std::vector<uint64_t> prefix;
+        prefix.push_back(0);
+        uint64_t e1 = e0;
+        while (e1 < expEnd && (prefix.back() == 0 || prefix.back() + hostExposures[e1].histories <= c->maxHistoriesPerLaunch)) {
+            prefix.push_back(prefix.back() + hostExposures[e1].histories);
+            ++e1;
+        }
+        const uint64_t total = prefix.back();
+        if (total > 0) {
+            if (prefix.size() > c->prefixCapacity) {
+                if (c->dPrefix)
+                    cudaFree(c->dPrefix);
+                c->prefixCapacity = std::max<uint64_t>(prefix.size(), 4096);
+                CU_CHECK(c, cudaMalloc(&c->dPrefix, c->prefixCapacity * sizeof(uint64_t)));
+            }
+            CU_CHECK(c, cudaMemcpyAsync(c->dPrefix, prefix.data(), prefix.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+            CU_CHECK(c, cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), c->stream));
+
+            KernelParams P {};
+            P.world = c->world;
+            P.lut = c->lut;
+            P.beams = c->beams;
+            P.exposures = devExposures;
+            P.prefix = c->dPrefix;
+            P.expBegin = e0;
+            P.nExp = static_cast<uint32_t>(e1 - e0);
+            P.totalHistories = total;
+            P.seed = seed;
+            P.workCounter = c->dWorkCounter;
+            P.acc = c->dAcc;
+            P.counters = c->dCounters;
+            P.energyScale = std::ldexp(1.0f, c->energyBits);
+            P.energySqScale = std::ldexp(1.0f, c->energySqBits);
+
+            CU_CHECK(c, cudaEventRecord(c->evStart, c->stream));
+            cudaError_t le;
+            if (c->collectStats) {
+                le = model == 0 ? launchTransport<0, true>(c, P) : model == 1 ? launchTransport<1, true>(c, P) : launchTransport<2, true>(c, P);
+            } else {
+                le = model == 0 ? launchTransport<0, false>(c, P) : model == 1 ? launchTransport<1, false>(c, P) : launchTransport<2, false>(c, P);
+            }
+            CU_CHECK(c, le);
+            CU_CHECK(c, cudaEventRecord(c->evStop, c->stream));
+            CU_CHECK(c, cudaStreamSynchronize(c->stream)); // also keeps `prefix` alive until the copy is done
+            float ms = 0;
+            CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+            c->lastRunMs += ms;
+            c->totalMs += ms;
+            ++c->launches;
+        }
+        e0 = e1;
+        if (cb)
+            cb(e0 - expBegin, user);
+    }
+    return DXMCB200_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int dxmcb200_device_count(int* count)
+{
+    if (!count)
+        return DXMCB200_ERR_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        *count = 0;
+        return DXMCB200_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_create(int device, dxmcb200_ctx** out)
+{
+    if (!out)
+        return DXMCB200_ERR_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n)
+        return DXMCB200_ERR_NO_DEVICE; // there is deliberately no CPU fallback
+    auto* c = new (std::nothrow) dxmcb200_ctx;
+    if (!c)
+        return DXMCB200_ERR_STATE;
+    c->device = device;
+    if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess
+        || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->evStart) != cudaSuccess
+        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dWorkCounter, sizeof(unsigned long long)) != cudaSuccess
+        || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemset(c->dCounters, 0, sizeof(Counters)) != cudaSuccess) {
+        dxmcb200_destroy(c);
+        return DXMCB200_ERR_CUDA;
+    }
+    const char* stats = std::getenv("DXMCB200_STATS");
+    c->collectStats = stats && stats[0] == '1';
+    *out = c;
+    return DXMCB200_OK;
+}
+
+void dxmcb200_destroy(dxmcb200_ctx* c)
+{
+    if (!c)
+        return;
+    cudaSetDevice(c->device);
+    cudaFree(c->dVoxels);
+    cudaFree(c->dAcc);
+    cudaFree(c->dLutBlob);
+    cudaFree(c->dBeamBlob);
+    cudaFree(c->dExposures);
+    cudaFree(c->dPrefix);
+    cudaFree(c->dWorkCounter);
+    cudaFree(c->dCounters);
+    if (c->evStart)
+        cudaEventDestroy(c->evStart);
+    if (c->evStop)
+        cudaEventDestroy(c->evStop);
+    if (c->stream)
+        cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+const char* dxmcb200_last_error(dxmcb200_ctx* c) { return c ? c->error.c_str() : "null context"; }
+
+int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
+{
+    if (!c || !w || !w->density || !w->material)
+        return DXMCB200_ERR_ARG;
+    const uint64_t n = w->dim[0] * w->dim[1] * w->dim[2];
+    if (n == 0 || n >= (1ULL << 32)) {
+        c->error = "voxel count must be in [1, 2^32)";
+        return DXMCB200_ERR_ARG;
+    }
+    CU_CHECK(c, cudaSetDevice(c->device));
+    if (n != c->nVoxels) {
+        cudaFree(c->dVoxels);
+        cudaFree(c->dAcc);
+        c->dVoxels = nullptr;
+        c->dAcc = nullptr;
+        c->nVoxels = 0;
+        CU_CHECK(c, cudaMalloc(&c->dVoxels, n * sizeof(uint2)));
+        CU_CHECK(c, cudaMalloc(&c->dAcc, n * 4 * sizeof(unsigned long long)));
+        c->nVoxels = n;
+    }
+    float* dDensity = nullptr;
+    uint8_t* dMat = nullptr;
+    uint8_t* dMeas = nullptr;
+    CU_CHECK(c, cudaMalloc(&dDensity, n * sizeof(float)));
+    CU_CHECK(c, cudaMalloc(&dMat, n));
+    if (w->measurement)
+        CU_CHECK(c, cudaMalloc(&dMeas, n));
+    CU_CHECK(c, cudaMemcpyAsync(dDensity, w->density, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU_CHECK(c, cudaMemcpyAsync(dMat, w->material, n, cudaMemcpyHostToDevice, c->stream));
+    if (w->measurement)
+        CU_CHECK(c, cudaMemcpyAsync(dMeas, w->measurement, n, cudaMemcpyHostToDevice, c->stream));
+    packVoxelsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, c->dVoxels, n);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, n * 4 * sizeof(unsigned long long), c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dDensity);
+    cudaFree(dMat);
+    cudaFree(dMeas);
+    for (int i = 0; i < 3; ++i) {
+        c->world.dim[i] = static_cast<uint32_t>(w->dim[i]);
+        c->world.spacing[i] = w->spacing[i];
+    }
+    for (int i = 0; i < 6; ++i)
+        c->world.ext[i] = w->extent_safe[i];
+    c->world.voxels = c->dVoxels;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
+{
+    if (!c || !l || !l->knots || !l->coefficients || !l->max_coefficients || !l->rita || !l->spline || !l->shells || l->n_materials == 0
+        || l->n_segments == 0)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const size_t nKnots = l->n_segments;
+    const size_t nCoeff = static_cast<size_t>(l->n_materials) * l->n_segments * 6;
+    const size_t nMax = static_cast<size_t>(l->n_segments) * 2;
+    const size_t nRita = static_cast<size_t>(l->n_materials) * 4 * DXMCB200_RITA_N;
+    const size_t nSpline = static_cast<size_t>(l->n_materials) * DXMCB200_SPLINE_FLOATS;
+    const size_t nShell = static_cast<size_t>(l->n_materials) * DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS;
+    // one blob, every table 16-byte aligned
+    auto pad = [](size_t n) { return (n + 3) & ~static_cast<size_t>(3); };
+    const size_t total = pad(nKnots) + pad(nCoeff) + pad(nMax) + pad(nRita) + pad(nSpline) + pad(nShell);
+    std::vector<float> blob(total, 0.0f);
+    size_t off = 0;
+    auto put = [&](const float* src, size_t n) {
+        std::memcpy(blob.data() + off, src, n * sizeof(float));
+        const size_t at = off;
+        off += pad(n);
+        return at;
+    };
+    const size_t oKnots = put(l->knots, nKnots), oCoeff = put(l->coefficients, nCoeff), oMax = put(l->max_coefficients, nMax),
+                 oRita = put(l->rita, nRita), oSpline = put(l->spline, nSpline), oShell = put(l->shells, nShell);
+    cudaFree(c->dLutBlob);
+    c->dLutBlob = nullptr;
+    CU_CHECK(c, cudaMalloc(&c->dLutBlob, total * sizeof(float)));
+    CU_CHECK(c, cudaMemcpy(c->dLutBlob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    c->lut.nMaterials = l->n_materials;
+    c->lut.nSegments = l->n_segments;
+    c->lut.linearIndex = l->linear_index;
+    c->lut.linearStep = l->linear_step;
+    c->lut.linearEnergy = l->linear_energy;
+    c->lut.knots = c->dLutBlob + oKnots;
+    c->lut.coeff = c->dLutBlob + oCoeff;
+    c->lut.maxCoeff = c->dLutBlob + oMax;
+    c->lut.rita = c->dLutBlob + oRita;
+    c->lut.spline = c->dLutBlob + oSpline;
+    c->lut.shells = c->dLutBlob + oShell;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_set_beam_tables(dxmcb200_ctx* c, uint32_t nSpectra, const dxmcb200_spectrum* spectra, uint32_t nHeel, const dxmcb200_heel* heel,
+    uint32_t nBowtie, const dxmcb200_bowtie* bowtie)
+{
+    if (!c || (nSpectra && !spectra) || (nHeel && !heel) || (nBowtie && !bowtie))
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    // size of the blob: view structs followed by their arrays
+    size_t bytes = 64;
+    bytes += nSpectra * sizeof(SpectrumView) + nHeel * sizeof(HeelView) + nBowtie * sizeof(BowtieView) + 48;
+    for (uint32_t i = 0; i < nSpectra; ++i)
+        bytes += static_cast<size_t>(spectra[i].n) * 12 + 48;
+    for (uint32_t i = 0; i < nHeel; ++i)
+        bytes += static_cast<size_t>(heel[i].energy_size) * heel[i].angle_size * 4 + 16;
+    for (uint32_t i = 0; i < nBowtie; ++i)
+        bytes += static_cast<size_t>(bowtie[i].n) * 8 + 32;
+    std::vector<char> host(bytes, 0);
+    cudaFree(c->dBeamBlob);
+    c->dBeamBlob = nullptr;
+    CU_CHECK(c, cudaMalloc(&c->dBeamBlob, bytes));
+    char* dBase = static_cast<char*>(c->dBeamBlob);
+    char* cursor = host.data();
+    auto toDevice = [&](const void* hostPtr) { return dBase + (static_cast<const char*>(hostPtr) - host.data()); };
+
+    auto* sv = advancePtr<SpectrumView>(cursor, nSpectra);
+    auto* hv = advancePtr<HeelView>(cursor, nHeel);
+    auto* bv = advancePtr<BowtieView>(cursor, nBowtie);
+    for (uint32_t i = 0; i < nSpectra; ++i) {
+        const auto& s = spectra[i];
+        if (s.n == 0 || !s.probs || !s.alias || !s.energies)
+            return DXMCB200_ERR_ARG;
+        float* probs = advancePtr<float>(cursor, s.n);
+        uint32_t* alias = advancePtr<uint32_t>(cursor, s.n);
+        float* energies = advancePtr<float>(cursor, s.n);
+        std::memcpy(probs, s.probs, s.n * 4);
+        std::memcpy(alias, s.alias, s.n * 4);
+        std::memcpy(energies, s.energies, s.n * 4);
+        sv[i].n = s.n;
+        // RandomState::randomUniform<std::size_t>(max): threshold = uint32(-max % max) in 64-bit arithmetic
+        // (dxmcrandom.hpp:87), i.e. 2^64 mod n truncated to 32 bits
+        const uint64_t n64 = s.n;
+        sv[i].threshold = static_cast<uint32_t>((0 - n64) % n64);
+        sv[i].probs = reinterpret_cast<const float*>(toDevice(probs));
+        sv[i].alias = reinterpret_cast<const uint32_t*>(toDevice(alias));
+        sv[i].energies = reinterpret_cast<const float*>(toDevice(energies));
+    }
+    for (uint32_t i = 0; i < nHeel; ++i) {
+        const auto& h = heel[i];
+        const size_t n = static_cast<size_t>(h.energy_size) * h.angle_size;
+        if (n == 0 || !h.weights)
+            return DXMCB200_ERR_ARG;
+        float* w = advancePtr<float>(cursor, n);
+        std::memcpy(w, h.weights, n * 4);
+        hv[i] = HeelView { h.energy_start, h.energy_step, h.energy_size, h.angle_start, h.angle_step, h.angle_size,
+            reinterpret_cast<const float*>(toDevice(w)) };
+    }
+    for (uint32_t i = 0; i < nBowtie; ++i) {
+        const auto& b = bowtie[i];
+        if (b.n == 0 || !b.angles || !b.weights)
+            return DXMCB200_ERR_ARG;
+        float* a = advancePtr<float>(cursor, b.n);
+        float* w = advancePtr<float>(cursor, b.n);
+        std::memcpy(a, b.angles, b.n * 4);
+        std::memcpy(w, b.weights, b.n * 4);
+        bv[i] = BowtieView { b.n, reinterpret_cast<const float*>(toDevice(a)), reinterpret_cast<const float*>(toDevice(w)) };
+    }
+    if (static_cast<size_t>(cursor - host.data()) > bytes) {
+        c->error = "beam table blob overflow";
+        return DXMCB200_ERR_STATE;
+    }
+    CU_CHECK(c, cudaMemcpy(c->dBeamBlob, host.data(), bytes, cudaMemcpyHostToDevice));
+    c->beams.spectra = reinterpret_cast<const SpectrumView*>(toDevice(sv));
+    c->beams.heels = reinterpret_cast<const HeelView*>(toDevice(hv));
+    c->beams.bowties = reinterpret_cast<const BowtieView*>(toDevice(bv));
+    return DXMCB200_OK;
+}
+
+int dxmcb200_suggest_fixed_point(uint64_t totalHistories, double maxEnergyWeight, int* energyBits, int* energySqBits)
+{
+    if (!energyBits || !energySqBits || maxEnergyWeight <= 0)
+        return DXMCB200_ERR_ARG;
+    // Russian roulette can multiply weights by 5 only while E*w < 5 keV, so one history never scores more than
+    // max(maxEnergyWeight, 25) keV into one voxel in total
+    const double perHistory = std::max(maxEnergyWeight, 25.0);
+    const double n = static_cast<double>(std::max<uint64_t>(totalHistories, 1));
+    const double boundE = n * perHistory;
+    const double boundE2 = n * perHistory * perHistory;
+    const int be = static_cast<int>(std::floor(62.0 - std::log2(boundE)));
+    const int b2 = static_cast<int>(std::floor(63.0 - std::log2(boundE2)));
+    *energyBits = std::clamp(be, 0, 40);
+    *energySqBits = std::clamp(b2, 0, 40);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_set_fixed_point(dxmcb200_ctx* c, int energyBits, int energySqBits)
+{
+    if (!c || energyBits < 0 || energyBits > 40 || energySqBits < 0 || energySqBits > 40)
+        return DXMCB200_ERR_ARG;
+    c->energyBits = energyBits;
+    c->energySqBits = energySqBits;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_clear(dxmcb200_ctx* c)
+{
+    if (!c)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    if (c->dAcc)
+        CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, c->nVoxels * 4 * sizeof(unsigned long long), c->stream));
+    CU_CHECK(c, cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->totalMs = 0;
+    c->lastRunMs = 0;
+    c->launches = 0;
+    return DXMCB200_OK;
+}
+
+void dxmcb200_history_stream(uint64_t seed, uint64_t exposure, uint64_t history, uint64_t out[2])
+{
+    uint64_t s, i;
+    historyStream(seed, exposure, history, s, i);
+    out[0] = s;
+    out[1] = i;
+}
+
+int dxmcb200_upload_exposures(dxmcb200_ctx* c, const dxmcb200_exposure* exposures, uint64_t n)
+{
+    if (!c || !exposures || n == 0)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    if (n > c->nExposuresResident) {
+        cudaFree(c->dExposures);
+        c->dExposures = nullptr;
+        c->nExposuresResident = 0;
+        CU_CHECK(c, cudaMalloc(&c->dExposures, n * sizeof(dxmcb200_exposure)));
+    }
+    CU_CHECK(c, cudaMemcpy(c->dExposures, exposures, n * sizeof(dxmcb200_exposure), cudaMemcpyHostToDevice));
+    c->nExposuresResident = n;
+    c->hExposures.assign(exposures, exposures + n);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_run_resident(dxmcb200_ctx* c, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed)
+{
+    if (!c || !c->dExposures || expEnd > c->nExposuresResident)
+        return DXMCB200_ERR_STATE;
+    return runRange(c, c->hExposures.data(), c->dExposures, expBegin, expEnd, model, seed, nullptr, nullptr, nullptr);
+}
+
+int dxmcb200_run(dxmcb200_ctx* c, const dxmcb200_exposure* exposures, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed,
+    const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
+{
+    if (!c || !exposures || expEnd < expBegin)
+        return DXMCB200_ERR_ARG;
+    if (expEnd == expBegin)
+        return DXMCB200_OK;
+    const int up = dxmcb200_upload_exposures(c, exposures, expEnd);
+    if (up != DXMCB200_OK)
+        return up;
+    return runRange(c, exposures, c->dExposures, expBegin, expEnd, model, seed, cancel, cb, user);
+}
+
+int dxmcb200_last_run_ms(dxmcb200_ctx* c, double* ms)
+{
+    if (!c || !ms)
+        return DXMCB200_ERR_ARG;
+    *ms = c->lastRunMs;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, float calibration, float* dose, uint32_t* nEvents, float* variance)
+{
+    if (!c || !c->dAcc || mode < 0 || mode > 2)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const uint64_t n = c->nVoxels;
+    float* dDose = nullptr;
+    float* dVar = nullptr;
+    uint32_t* dEv = nullptr;
+    if (dose)
+        CU_CHECK(c, cudaMalloc(&dDose, n * sizeof(float)));
+    if (variance)
+        CU_CHECK(c, cudaMalloc(&dVar, n * sizeof(float)));
+    if (nEvents)
+        CU_CHECK(c, cudaMalloc(&dEv, n * sizeof(uint32_t)));
+    const float voxelVolume = c->world.spacing[0] * c->world.spacing[1] * c->world.spacing[2] / 1000.0f;
+    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, n, mode, std::ldexp(1.0f, -c->energyBits),
+        std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, dDose, dEv, dVar);
+    CU_CHECK(c, cudaGetLastError());
+    if (dose)
+        CU_CHECK(c, cudaMemcpyAsync(dose, dDose, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (variance)
+        CU_CHECK(c, cudaMemcpyAsync(variance, dVar, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    if (nEvents)
+        CU_CHECK(c, cudaMemcpyAsync(nEvents, dEv, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dDose);
+    cudaFree(dVar);
+    cudaFree(dEv);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_raw(dxmcb200_ctx* c, int64_t* energy, uint64_t* energySq, uint64_t* events)
+{
+    if (!c || !c->dAcc)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const uint64_t n = c->nVoxels;
+    long long* dE = nullptr;
+    unsigned long long* dE2 = nullptr;
+    unsigned long long* dN = nullptr;
+    if (energy)
+        CU_CHECK(c, cudaMalloc(&dE, n * 8));
+    if (energySq)
+        CU_CHECK(c, cudaMalloc(&dE2, n * 8));
+    if (events)
+        CU_CHECK(c, cudaMalloc(&dN, n * 8));
+    rawKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, n, dE, dE2, dN);
+    CU_CHECK(c, cudaGetLastError());
+    if (energy)
+        CU_CHECK(c, cudaMemcpyAsync(energy, dE, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (energySq)
+        CU_CHECK(c, cudaMemcpyAsync(energySq, dE2, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (events)
+        CU_CHECK(c, cudaMemcpyAsync(events, dN, n * 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(dE);
+    cudaFree(dE2);
+    cudaFree(dN);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_accumulators(dxmcb200_ctx* c, void** devicePtr, uint64_t* nU64)
+{
+    if (!c || !c->dAcc || !devicePtr || !nU64)
+        return DXMCB200_ERR_STATE;
+    *devicePtr = c->dAcc;
+    *nU64 = c->nVoxels * 4;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_reduce(dxmcb200_ctx* c, void* comm)
+{
+    if (!c || !c->dAcc || !comm)
+        return DXMCB200_ERR_STATE;
+    // ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); ncclUint64 = 5, ncclSum = 0
+    using AllReduceFn = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+    static AllReduceFn fn = nullptr;
+    if (!fn) {
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h)
+            h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h)
+            fn = reinterpret_cast<AllReduceFn>(dlsym(h, "ncclAllReduce"));
+        if (!fn) {
+            c->error = "libnccl not found";
+            return DXMCB200_ERR_NCCL;
+        }
+    }
+    CU_CHECK(c, cudaSetDevice(c->device));
+    if (fn(c->dAcc, c->dAcc, c->nVoxels * 4, 5, 0, comm, c->stream) != 0) {
+        c->error = "ncclAllReduce failed";
+        return DXMCB200_ERR_NCCL;
+    }
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_stats(dxmcb200_ctx* c, dxmcb200_stats* s)
+{
+    if (!c || !s)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    Counters h {};
+    CU_CHECK(c, cudaMemcpy(&h, c->dCounters, sizeof(Counters), cudaMemcpyDeviceToHost));
+    s->histories = h.histories;
+    s->histories_in_world = h.inWorld;
+    s->steps = h.steps;
+    s->lookups = h.lookups;
+    s->interactions = h.interactions;
+    s->score_events = h.scores;
+    s->kernel_launches = c->launches;
+    s->kernel_ms = c->totalMs;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_eval_attenuation(dxmcb200_ctx* c, uint64_t n, const uint8_t* material, const float* energy, float* out3, float* outMax)
+{
+    if (!c || !c->dLutBlob || !material || !energy || !out3 || !outMax || n == 0)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    uint8_t* dM = nullptr;
+    float *dE = nullptr, *dO = nullptr, *dX = nullptr;
+    CU_CHECK(c, cudaMalloc(&dM, n));
+    CU_CHECK(c, cudaMalloc(&dE, n * 4));
+    CU_CHECK(c, cudaMalloc(&dO, n * 12));
+    CU_CHECK(c, cudaMalloc(&dX, n * 4));
+    CU_CHECK(c, cudaMemcpy(dM, material, n, cudaMemcpyHostToDevice));
+    CU_CHECK(c, cudaMemcpy(dE, energy, n * 4, cudaMemcpyHostToDevice));
+    evalAttenuationKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->lut, n, dM, dE, dO, dX);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaMemcpy(out3, dO, n * 12, cudaMemcpyDeviceToHost));
+    CU_CHECK(c, cudaMemcpy(outMax, dX, n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(dM);
+    cudaFree(dE);
+    cudaFree(dO);
+    cudaFree(dX);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_trace_indices(dxmcb200_ctx* c, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps,
+    int64_t* outIdx, float* outEntry)
+{
+    if (!c || !c->dVoxels || !pos || !dir || !steps || !outIdx || !outEntry || nRays == 0)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    float *dP = nullptr, *dD = nullptr, *dS = nullptr, *dEn = nullptr;
+    long long* dI = nullptr;
+    CU_CHECK(c, cudaMalloc(&dP, nRays * 12));
+    CU_CHECK(c, cudaMalloc(&dD, nRays * 12));
+    CU_CHECK(c, cudaMalloc(&dS, std::max<size_t>(nSteps, 1) * 4));
+    CU_CHECK(c, cudaMalloc(&dEn, nRays * 12));
+    CU_CHECK(c, cudaMalloc(&dI, nRays * (nSteps + 1) * 8));
+    CU_CHECK(c, cudaMemcpy(dP, pos, nRays * 12, cudaMemcpyHostToDevice));
+    CU_CHECK(c, cudaMemcpy(dD, dir, nRays * 12, cudaMemcpyHostToDevice));
+    if (nSteps)
+        CU_CHECK(c, cudaMemcpy(dS, steps, nSteps * 4, cudaMemcpyHostToDevice));
+    traceIndicesKernel<<<static_cast<unsigned>((nRays + 127) / 128), 128, 0, c->stream>>>(c->world, nRays, dP, dD, nSteps, dS, dI, dEn);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaMemcpy(outIdx, dI, nRays * (nSteps + 1) * 8, cudaMemcpyDeviceToHost));
+    CU_CHECK(c, cudaMemcpy(outEntry, dEn, nRays * 12, cudaMemcpyDeviceToHost));
+    cudaFree(dP);
+    cudaFree(dD);
+    cudaFree(dS);
+    cudaFree(dEn);
+    cudaFree(dI);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_sample_particles(dxmcb200_ctx* c, const dxmcb200_exposure* e, uint64_t exposureIndex, uint64_t seed, uint64_t n, float* out)
+{
+    if (!c || !e || !out || n == 0)
+        return DXMCB200_ERR_ARG;
+    if ((e->spectrum >= 0 || e->heel >= 0 || e->bowtie >= 0) && !c->dBeamBlob)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    float* dO = nullptr;
+    CU_CHECK(c, cudaMalloc(&dO, n * 32));
+    sampleParticlesKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(*e, c->beams, exposureIndex, seed, n, dO);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaMemcpy(out, dO, n * 32, cudaMemcpyDeviceToHost));
+    cudaFree(dO);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_sample_interaction(dxmcb200_ctx* c, int kind, int model, uint8_t material, float energy, uint64_t seed, uint64_t n, float* out)
+{
+    if (!c || !c->dLutBlob || !out || n == 0 || kind < 0 || kind > 2 || model < 0 || model > 2 || material >= c->lut.nMaterials)
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    float* dO = nullptr;
+    CU_CHECK(c, cudaMalloc(&dO, n * 20));
+    const unsigned grid = static_cast<unsigned>((n + 255) / 256);
+    if (model == 0)
+        sampleInteractionKernel<0><<<grid, 256, 0, c->stream>>>(c->lut, kind, material, energy, seed, n, dO);
+    else if (model == 1)
+        sampleInteractionKernel<1><<<grid, 256, 0, c->stream>>>(c->lut, kind, material, energy, seed, n, dO);
+    else
+        sampleInteractionKernel<2><<<grid, 256, 0, c->stream>>>(c->lut, kind, material, energy, seed, n, dO);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaMemcpy(out, dO, n * 20, cudaMemcpyDeviceToHost));
+    cudaFree(dO);
+    return DXMCB200_OK;
+}
+
+} // extern "C"

@@ -11,6 +11,7 @@ using namespace xrl_lite;
 #endif
 
 #include <algorithm>
+#include <execution>
 #include <numeric>
 
 namespace dxmcb200::matdb {
@@ -266,25 +267,25 @@ std::array<Shell, 12> electronConfiguration(const std::string& name)
     for (std::size_t i = 0; i < std::min(all.size(), result.size()); ++i)
         result[i] = all[i];
 
-    double electrons = 0;
-    for (const auto& s : result)
-        electrons += s.numberElectrons;
+    const double electrons = std::transform_reduce(result.cbegin(), result.cend(), 0.0, std::plus<>(), [](const Shell& s) { return s.numberElectrons; });
     for (auto& s : result)
         s.numberElectrons /= electrons;
 
     // photo-ionisation probability: occupancy-weighted sum of the partial cross section on
     // 0.5, 1.5, ... 399.5 keV; unfilled slots keep their default weight of 1 in the normalisation
+    // (the sums use the same library reductions as the reference so the doubles agree to the last bit)
+    std::vector<double> energy(400);
+    std::iota(energy.begin(), energy.end(), 0.5);
     for (auto& s : result) {
         if (s.Z > 0) {
-            double sum = 0;
-            for (int k = 0; k < 400; ++k)
-                sum += CSb_Photo_Partial(s.Z, s.shell, 0.5 + k, nullptr);
+            const int Z = s.Z, shell = s.shell;
+            const double sum = std::transform_reduce(std::execution::par_unseq, energy.cbegin(), energy.cend(), 0.0, std::plus<>(),
+                [=](const double e) { return CSb_Photo_Partial(Z, shell, e, nullptr); });
             s.photoIonizationProbability = s.numberElectrons * sum;
         }
     }
-    double total = 0;
-    for (const auto& s : result)
-        total += s.photoIonizationProbability;
+    const double total = std::transform_reduce(std::execution::par_unseq, result.cbegin(), result.cend(), 0.0, std::plus<>(),
+        [](const Shell& s) { return s.photoIonizationProbability; });
     if (total > 0)
         for (auto& s : result)
             s.photoIonizationProbability /= total;

@@ -1,38 +1,20 @@
-// ref_harness.cpp — TEST INFRASTRUCTURE, not product code.
-//
-// Implements include/dxmcb200_scene.h on top of the UNMODIFIED reference headers in
-// /root/reference/include (never copied into this repo) and the reference's own
-// src/material.cpp, compiled where they lie by oracle/Makefile into
-// oracle/_ref/libdxmc_ref.so. xraylib, which the reference needs and this image lacks, is
-// supplied by oracle/xraylib_compat/xraylib.h -> dxmclib_b200/host/xrl_lite (the same data
-// source the product uses), so both implementations see identical cross sections.
-//
-// Built with -fno-access-control so protected/private members of the reference classes
-// (Transport::transport<L>, AttenuationLutInterpolator::m_coefficients, ...) can be driven
-// with a seeded RandomState and dumped for bit-exact comparison.
+// scene_capi.cpp — include/dxmcb200_scene.h implemented on the drop-in C++ classes in
+// dxmclib_b200/include/dxmc/ (World, Material, AttenuationLut, sources, Transport). This is the
+// FFI surface of the product: Python (tests/, bench.py) and any other host language reach the CUDA
+// path through these calls. oracle/ref_harness.cpp implements the same header on the unmodified
+// reference for comparison; nothing here touches oracle/.
 #include "dxmcb200_scene.h"
 
 #include "dxmc.hpp"
+#include "dxmc/attenuationlut.hpp"
 
-#include <atomic>
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <string>
 #include <thread>
 
 using namespace dxmc;
-
-// Portability shim (NOT a change of behaviour): BowTieFilter<T>::normalizeData (reference
-// beamfilters.hpp:88-92) calls std::reduce over pair<T,T> elements with a (double, pair) folding
-// lambda. MSVC's STL, on which the reference is developed, accepts that and folds left to right;
-// libstdc++ rejects it with a static_assert, so the member cannot be instantiated with g++. This
-// explicit specialisation supplies the same left fold with std::accumulate.
-template <>
-void dxmc::BowTieFilter<float>::normalizeData()
-{
-    const auto mean = std::accumulate(m_data.begin(), m_data.end(), 0.0, [](auto a, auto el) { return a + el.second; }) / m_data.size();
-    std::transform(m_data.begin(), m_data.end(), m_data.begin(), [=](const auto& el) { return std::make_pair(el.first, static_cast<float>(el.second / mean)); });
-}
 
 struct dxs_scene {
     std::unique_ptr<World<float>> world = std::make_unique<World<float>>();
@@ -44,12 +26,19 @@ struct dxs_scene {
 };
 
 namespace {
+thread_local std::string g_lastError;
+
+// exceptions never cross the C boundary; a device failure stays loud through its own status code
 template <typename F>
 int guarded(F f)
 {
     try {
         return f();
+    } catch (const std::exception& e) {
+        g_lastError = e.what();
+        return g_lastError.rfind("dxmcb200:", 0) == 0 ? DXS_ERR_DEVICE : DXS_ERR_STATE;
     } catch (...) {
+        g_lastError = "unknown exception";
         return DXS_ERR_STATE;
     }
 }
@@ -70,72 +59,12 @@ void applyTube(Tube<float>& t, const dxs_tube& p)
         t.setSnFiltration(p.sn_mm);
 }
 
-template <int L>
-void seededRun(Transport<float>& tr, const World<float>& w, const Source<float>* src, Result<float>& res, std::uint64_t seed)
-{
-    std::uint64_t s[2] = { seed, seed ^ 0x9E3779B97F4A7C15ULL };
-    RandomState state(s);
-    const auto& basis = w.directionCosines();
-    const auto n = src->totalExposures();
-    for (std::uint64_t i = 0; i < n; ++i) {
-        auto exposure = src->getExposure(i);
-        exposure.alignToDirectionCosines(basis);
-        tr.template transport<L>(w, exposure, state, res);
-    }
-}
-// The product's per-history stream keying (include/dxmcb200.h dxmcb200_history_stream), restated here so
-// the reference's own sampling code can be driven with the very same random numbers as the kernels.
-inline std::uint64_t mix64(std::uint64_t z)
-{
-    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
-    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
-    return z ^ (z >> 31);
-}
-inline void historyStream(std::uint64_t seed, std::uint64_t exposure, std::uint64_t history, std::uint64_t out[2])
-{
-    const std::uint64_t golden = 0x9E3779B97F4A7C15ULL;
-    const std::uint64_t s = mix64(seed + golden * (exposure + 1));
-    out[0] = mix64(s + golden * (history + 1));
-    out[1] = mix64(out[0] + golden) | 1ULL;
-}
-
-// Reference transport with one RandomState per history, seeded like the B200 kernels: the body of
-// Transport::transport<L> (transport.hpp:729-743) with the state re-created per history. Exposures are
-// spread over host threads; scoring uses the reference's own atomic adds.
-template <int L>
-void counterStreamRun(Transport<float>& tr, const World<float>& w, const Source<float>* src, Result<float>& res, std::uint64_t seed, unsigned nThreads)
-{
-    const auto& basis = w.directionCosines();
-    const auto n = src->totalExposures();
-    std::atomic<std::uint64_t> next { 0 };
-    auto worker = [&]() {
-        for (std::uint64_t i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
-            auto exposure = src->getExposure(i);
-            exposure.alignToDirectionCosines(basis);
-            const auto nHist = exposure.numberOfHistories();
-            for (std::uint64_t h = 0; h < nHist; ++h) {
-                std::uint64_t s[2];
-                historyStream(seed, i, h, s);
-                RandomState state(s);
-                auto particle = exposure.sampleParticle(state);
-                if (tr.transportParticleToWorld(w, particle))
-                    tr.template woodcockParticleTracking<L>(w, particle, state, res);
-            }
-        }
-    };
-    std::vector<std::thread> pool;
-    for (unsigned t = 1; t < std::max(nThreads, 1u); ++t)
-        pool.emplace_back(worker);
-    worker();
-    for (auto& t : pool)
-        t.join();
-}
 } // namespace
 
 extern "C" {
 
-const char* dxs_backend(void) { return "dxmclib-reference"; }
-const char* dxs_last_error(void) { return ""; }
+const char* dxs_backend(void) { return "dxmc-b200"; }
+const char* dxs_last_error(void) { return g_lastError.c_str(); }
 
 dxs_scene* dxs_create(void) { return new (std::nothrow) dxs_scene; }
 void dxs_destroy(dxs_scene* s) { delete s; }
@@ -398,35 +327,35 @@ int dxs_lut_table(dxs_scene* s, int what, float* out, uint64_t* count)
     if (!s || !s->lutValid)
         return DXS_ERR_STATE;
     std::vector<float> v;
-    const auto& ip = s->lut.m_attenuationData;
+    const auto& ip = s->lut.attenuationData();
     switch (what) {
     case 0:
-        v = ip.m_x;
+        v = ip.knots();
         break;
     case 1:
-        v = ip.m_coefficients;
+        v = ip.coefficients();
         break;
     case 2:
-        v = ip.m_maxCoefficients;
+        v = ip.maxCoefficients();
         break;
     case 3:
-        v = { static_cast<float>(ip.m_linearIndex), ip.m_linearStep, ip.m_linearEnergy, static_cast<float>(ip.m_resolution) };
+        v = { static_cast<float>(ip.linearIndex()), ip.linearStep(), ip.linearEnergy(), static_cast<float>(ip.resolution()) };
         break;
     case 4:
-        for (const auto& r : s->lut.m_formFactor) {
-            v.insert(v.end(), r.m_x.begin(), r.m_x.end());
-            v.insert(v.end(), r.m_e.begin(), r.m_e.end());
-            v.insert(v.end(), r.m_a.begin(), r.m_a.end());
-            v.insert(v.end(), r.m_b.begin(), r.m_b.end());
+        for (const auto& r : s->lut.formFactorSamplers()) {
+            v.insert(v.end(), r.x().begin(), r.x().end());
+            v.insert(v.end(), r.e().begin(), r.e().end());
+            v.insert(v.end(), r.a().begin(), r.a().end());
+            v.insert(v.end(), r.b().begin(), r.b().end());
         }
         break;
     case 5:
-        for (const auto& c : s->lut.m_comptonScatterFactor) {
-            v.insert(v.end(), c.m_coefficients.begin(), c.m_coefficients.end());
-            v.insert(v.end(), c.m_x.begin(), c.m_x.end());
-            v.push_back(c.m_step);
-            v.push_back(c.m_start);
-            v.push_back(c.m_stop);
+        for (const auto& c : s->lut.scatterFunctions()) {
+            v.insert(v.end(), c.coefficients().begin(), c.coefficients().end());
+            v.insert(v.end(), c.knots().begin(), c.knots().end());
+            v.push_back(c.step());
+            v.push_back(c.start());
+            v.push_back(c.stop());
         }
         break;
     default:
@@ -683,54 +612,10 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
         tr.setLowEnergyCorrectionModel(static_cast<LOWENERGYCORRECTION>(model));
         tr.setOutputMode(outputMode == DXS_OUT_DOSE ? Transport<float>::OUTPUTMODE::DOSE : Transport<float>::OUTPUTMODE::EV_PER_HISTORY);
         s->world->makeValid();
-        Result<float> res;
-        const bool counterStreams = nWorkers == DXS_WORKERS_COUNTER_STREAMS;
-        if (seed == 0 && !counterStreams) {
-            res = tr(*s->world, s->source.get(), nullptr, useCalibration != 0);
-        } else {
-            // the body of Transport::operator() (transport.hpp:138-201) with the worker pool replaced
-            // by one seeded worker
-            const World<float>& w = *s->world;
-            res = Result<float>(w.size());
-            auto* src = s->source.get();
-            if (w.isValid()) {
-                src->updateFromWorld(w);
-                src->validate();
-                if (src->isValid()) {
-                    res.numberOfHistories = src->historiesPerExposure() * src->totalExposures();
-                    tr.m_attenuationLut.generate(w, src->maxPhotonEnergyProduced());
-                    const auto t0 = std::chrono::system_clock::now();
-                    if (counterStreams) {
-                        const unsigned nt = std::max(std::thread::hardware_concurrency(), 1u);
-                        if (model == 0)
-                            counterStreamRun<0>(tr, w, src, res, seed, nt);
-                        else if (model == 1)
-                            counterStreamRun<1>(tr, w, src, res, seed, nt);
-                        else
-                            counterStreamRun<2>(tr, w, src, res, seed, nt);
-                    } else if (model == 0)
-                        seededRun<0>(tr, w, src, res, seed);
-                    else if (model == 1)
-                        seededRun<1>(tr, w, src, res, seed);
-                    else
-                        seededRun<2>(tr, w, src, res, seed);
-                    res.simulationTime = std::chrono::system_clock::now() - t0;
-                    if (outputMode == DXS_OUT_DOSE) {
-                        if (useCalibration) {
-                            const float cal = src->getCalibrationValue(static_cast<LOWENERGYCORRECTION>(model), nullptr);
-                            tr.energyImpartedToDose(w, res, cal);
-                            res.dose_units = "mGy";
-                        } else {
-                            tr.energyImpartedToDose(w, res);
-                            res.dose_units = "keV/kg";
-                        }
-                    } else {
-                        tr.normalizeScoring(res);
-                        res.dose_units = "eV/history";
-                    }
-                }
-            }
-        }
+        if (seed != 0)
+            tr.setSeed(seed);
+        (void)nWorkers; // n_workers selects host threads / stream mode in the reference harness only
+        Result<float> res = tr(*s->world, s->source.get(), nullptr, useCalibration != 0);
         const auto n = res.dose.size();
         if (dose)
             std::memcpy(dose, res.dose.data(), n * sizeof(float));

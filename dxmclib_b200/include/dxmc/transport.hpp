@@ -1,0 +1,423 @@
+// transport.hpp — Transport<T>: run a Source through a World on a B200 and return per-voxel dose.
+//
+// Drop-in for the reference's Transport<T> (include/dxmc/transport.hpp:114-840): same setters,
+// same call operator, same Result<T>, same output units and post-processing. What differs is the
+// middle: where the reference spawns std::thread workers that pull exposures (parallellRun,
+// :765-778), this class flattens the world, the look-up tables, the beam tables and ALL exposures
+// into the POD structs of include/dxmcb200.h and hands them to the CUDA runtime in
+// libdxmcb200.so. There is no CPU path: without a CUDA device the call throws.
+//
+// Additions (no existing signature changed): setDevice(), setSeed(), lastStats().
+#pragma once
+#include "dxmc/attenuationlut.hpp"
+#include "dxmc/exposure.hpp"
+#include "dxmc/lowenergycorrectionmodel.hpp"
+#include "dxmc/particle.hpp"
+#include "dxmc/progressbar.hpp"
+#include "dxmc/vectormath.hpp"
+#include "dxmc/world.hpp"
+#include "dxmcb200.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <map>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <string_view>
+#include <thread>
+#include <vector>
+
+namespace dxmc {
+
+template <Floating T = double>
+struct Result {
+    std::vector<T> dose;
+    std::vector<std::uint32_t> nEvents;
+    std::vector<T> variance;
+    std::uint64_t numberOfHistories { 0 };
+    std::chrono::duration<float> simulationTime { 0 };
+    std::string_view dose_units = "";
+
+    Result() = default;
+    Result(std::size_t size)
+        : dose(size, T { 0 })
+        , nEvents(size, 0)
+        , variance(size, T { 0 })
+    {
+    }
+    [[nodiscard]] std::vector<T> relativeError() const
+    {
+        std::vector<T> err(dose.size());
+        for (std::size_t i = 0; i < dose.size(); ++i)
+            err[i] = dose[i] > 0 ? std::sqrt(variance[i]) / dose[i] : 0;
+        return err;
+    }
+};
+
+template <Floating T>
+class Source;
+
+namespace detail {
+    // device the next default-constructed Transport uses; the CT calibration run inherits the outer one
+    inline int& currentDevice()
+    {
+        thread_local int device = 0;
+        return device;
+    }
+
+    struct ContextDeleter {
+        void operator()(dxmcb200_ctx* c) const { dxmcb200_destroy(c); }
+    };
+    using ContextPtr = std::unique_ptr<dxmcb200_ctx, ContextDeleter>;
+
+    inline void check(dxmcb200_ctx* c, int status, const char* what)
+    {
+        if (status != DXMCB200_OK && status != DXMCB200_ERR_CANCELLED)
+            throw std::runtime_error(std::string("dxmcb200: ") + what + " failed (" + std::to_string(status) + "): " + dxmcb200_last_error(c));
+    }
+
+    // everything the device needs besides the voxel arrays, in the layout of include/dxmcb200.h
+    struct FlatTables {
+        std::vector<float> knots, coefficients, maxCoefficients, rita, spline, shells;
+        dxmcb200_luts luts {};
+
+        struct Spectrum {
+            std::vector<float> probs, energies;
+            std::vector<std::uint32_t> alias;
+        };
+        struct Heel {
+            dxmcb200_heel desc {};
+            std::vector<float> weights;
+        };
+        struct Bowtie {
+            std::vector<float> angles, weights;
+        };
+        std::vector<Spectrum> spectra;
+        std::vector<Heel> heels;
+        std::vector<Bowtie> bowties;
+        std::vector<dxmcb200_exposure> exposures;
+        double maxWeight = 0; // largest possible photon birth weight
+    };
+
+    template <typename V>
+    inline void appendFloats(std::vector<float>& out, const V& v)
+    {
+        for (const auto x : v)
+            out.push_back(static_cast<float>(x));
+    }
+}
+
+template <Floating T = double>
+class Transport {
+public:
+    enum class OUTPUTMODE { EV_PER_HISTORY, DOSE };
+
+    Transport()
+        : m_nThreads(std::max<std::uint64_t>(std::thread::hardware_concurrency(), 1))
+        , m_device(detail::currentDevice())
+    {
+    }
+
+    // kept for source compatibility; the B200 path has no host workers
+    void setNumberOfWorkers(std::uint64_t n) { m_nThreads = std::max(n, std::uint64_t { 1 }); }
+    std::size_t numberOfWorkers() const { return m_nThreads; }
+    void setLowEnergyCorrectionModel(LOWENERGYCORRECTION model) { m_lowenergyCorrection = model; }
+    LOWENERGYCORRECTION lowEnergyCorrectionModel() const { return m_lowenergyCorrection; }
+    void setOutputMode(OUTPUTMODE mode) { m_outputmode = mode; }
+    OUTPUTMODE outputMode() const { return m_outputmode; }
+
+    // ---- B200 additions
+    void setDevice(int device) { m_device = device; }
+    int device() const { return m_device; }
+    // master seed of the per-history counter streams (the reference seeds from std::random_device)
+    void setSeed(std::uint64_t seed) { m_seed = seed; }
+    std::uint64_t seed() const { return m_seed; }
+    const dxmcb200_stats& lastStats() const { return m_stats; }
+
+    template <typename U>
+        requires std::is_base_of_v<World<T>, U>
+    Result<T> operator()(const U& world, Source<T>* source, ProgressBar<T>* progressbar = nullptr, bool useSourceDoseCalibration = true)
+    {
+        Result<T> result(world.size());
+        if (!world.isValid() || !source)
+            return result;
+        source->updateFromWorld(world);
+        source->validate();
+        if (!source->isValid())
+            return result;
+        result.numberOfHistories = source->historiesPerExposure() * source->totalExposures();
+        m_attenuationLut.generate(world, source->maxPhotonEnergyProduced());
+
+        const std::uint64_t totalExposures = source->totalExposures();
+        detail::FlatTables flat;
+        flattenLuts(flat);
+        flattenExposures(world, *source, totalExposures, flat);
+
+        dxmcb200_ctx* raw = nullptr;
+        const int created = dxmcb200_create(m_device, &raw);
+        if (created != DXMCB200_OK)
+            throw std::runtime_error("dxmcb200: no usable CUDA device " + std::to_string(m_device) + " (status " + std::to_string(created)
+                + "); this library has no CPU fallback");
+        detail::ContextPtr ctx(raw);
+        uploadWorld(ctx.get(), world);
+        detail::check(ctx.get(), dxmcb200_set_luts(ctx.get(), &flat.luts), "set_luts");
+        uploadBeamTables(ctx.get(), flat);
+        int energyBits = 20, energySqBits = 10;
+        dxmcb200_suggest_fixed_point(result.numberOfHistories, flat.maxWeight * static_cast<double>(source->maxPhotonEnergyProduced()), &energyBits,
+            &energySqBits);
+        detail::check(ctx.get(), dxmcb200_set_fixed_point(ctx.get(), energyBits, energySqBits), "set_fixed_point");
+
+        if (progressbar) {
+            progressbar->setTotalExposures(totalExposures);
+            progressbar->setDoseData(result.dose.data(), world.dimensions(), world.spacing());
+        }
+        struct Progress {
+            ProgressBar<T>* bar;
+            std::uint64_t reported = 0;
+            volatile int cancel = 0;
+        } progress { progressbar };
+        auto callback = [](std::uint64_t done, void* user) {
+            auto* p = static_cast<Progress*>(user);
+            if (p->bar) {
+                p->bar->exposureCompleted(done - p->reported);
+                p->reported = done;
+                p->cancel = p->bar->cancel() ? 1 : 0;
+            }
+        };
+        if (progressbar && progressbar->cancel())
+            progress.cancel = 1;
+
+        const auto start = std::chrono::system_clock::now();
+        const int ran = dxmcb200_run(ctx.get(), flat.exposures.data(), 0, totalExposures, static_cast<int>(m_lowenergyCorrection), m_seed,
+            &progress.cancel, callback, &progress);
+        result.simulationTime = std::chrono::system_clock::now() - start;
+        detail::check(ctx.get(), ran, "run");
+        dxmcb200_get_stats(ctx.get(), &m_stats);
+
+        if (progressbar) {
+            progressbar->clearDoseData();
+            if (progressbar->cancel() || ran == DXMCB200_ERR_CANCELLED) {
+                result.numberOfHistories = 0;
+                return result; // all zeros, like a cancelled reference run
+            }
+        }
+
+        int mode = 0;
+        float calibration = 1.0f;
+        if (m_outputmode == OUTPUTMODE::DOSE) {
+            mode = 1;
+            if (useSourceDoseCalibration) {
+                const int outer = detail::currentDevice();
+                detail::currentDevice() = m_device; // a CT calibration run constructs its own Transport
+                calibration = static_cast<float>(source->getCalibrationValue(m_lowenergyCorrection, progressbar));
+                detail::currentDevice() = outer;
+                result.dose_units = "mGy";
+            } else {
+                result.dose_units = "keV/kg";
+            }
+        } else {
+            result.dose_units = "eV/history";
+        }
+        download(ctx.get(), mode, result, calibration);
+        return result;
+    }
+
+    const AttenuationLut<T>& attenuationLut() const { return m_attenuationLut; }
+    AttenuationLut<T>& attenuationLut() { return m_attenuationLut; }
+
+protected:
+    void flattenLuts(detail::FlatTables& f) const
+    {
+        const auto& lut = m_attenuationLut;
+        const auto& ip = lut.attenuationData();
+        const std::size_t nMat = lut.formFactorSamplers().size();
+        detail::appendFloats(f.knots, ip.knots());
+        detail::appendFloats(f.coefficients, ip.coefficients());
+        detail::appendFloats(f.maxCoefficients, ip.maxCoefficients());
+        for (std::size_t m = 0; m < nMat; ++m) {
+            const auto& r = lut.formFactorSamplers()[m];
+            detail::appendFloats(f.rita, r.x());
+            detail::appendFloats(f.rita, r.e());
+            detail::appendFloats(f.rita, r.a());
+            detail::appendFloats(f.rita, r.b());
+            const auto& s = lut.scatterFunctions()[m];
+            detail::appendFloats(f.spline, s.coefficients());
+            f.spline.push_back(static_cast<float>(s.start()));
+            f.spline.push_back(static_cast<float>(s.step()));
+            f.spline.push_back(static_cast<float>(s.stop()));
+            for (const auto& sh : lut.electronShellConfiguration(m)) {
+                const T row[DXMCB200_SHELL_FLOATS] = { sh.bindingEnergy, sh.numberElectrons, sh.hartreeFockOrbital_0, sh.photoIonizationProbability,
+                    sh.fluorescenceYield, sh.fluorLineProbabilities[0], sh.fluorLineProbabilities[1], sh.fluorLineProbabilities[2], sh.fluorLineEnergies[0],
+                    sh.fluorLineEnergies[1], sh.fluorLineEnergies[2] };
+                detail::appendFloats(f.shells, row);
+            }
+        }
+        f.luts.n_materials = static_cast<std::uint32_t>(nMat);
+        f.luts.n_segments = static_cast<std::uint32_t>(ip.resolution());
+        f.luts.linear_index = static_cast<std::uint32_t>(ip.linearIndex());
+        f.luts.linear_step = static_cast<float>(ip.linearStep());
+        f.luts.linear_energy = static_cast<float>(ip.linearEnergy());
+        f.luts.knots = f.knots.data();
+        f.luts.coefficients = f.coefficients.data();
+        f.luts.max_coefficients = f.maxCoefficients.data();
+        f.luts.rita = f.rita.data();
+        f.luts.spline = f.spline.data();
+        f.luts.shells = f.shells.data();
+    }
+
+    // getExposure(i) + alignToDirectionCosines for every exposure (reference transport.hpp:756-757),
+    // with the beam tables the exposures point to collected once each
+    template <typename U>
+    void flattenExposures(const U& world, const Source<T>& source, std::uint64_t totalExposures, detail::FlatTables& f) const
+    {
+        std::map<const void*, std::int32_t> spectrumIdx, heelIdx, bowtieIdx;
+        std::vector<double> spectrumMax, heelMax, bowtieMax; // per-table largest weight factor
+        f.exposures.reserve(totalExposures);
+        for (std::uint64_t i = 0; i < totalExposures; ++i) {
+            auto e = source.getExposure(i);
+            e.alignToDirectionCosines(world.directionCosines());
+            dxmcb200_exposure pod {};
+            for (int k = 0; k < 3; ++k) {
+                pod.position[k] = static_cast<float>(e.position()[k]);
+                pod.beam_direction[k] = static_cast<float>(e.beamDirection()[k]);
+            }
+            for (int k = 0; k < 6; ++k)
+                pod.cosines[k] = static_cast<float>(e.directionCosines()[k]);
+            for (int k = 0; k < 4; ++k)
+                pod.collimation[k] = static_cast<float>(e.collimationAngles()[k]);
+            pod.weight = static_cast<float>(e.beamIntensityWeight());
+            pod.mono_energy = static_cast<float>(e.monoenergeticPhotonEnergy());
+            pod.histories = e.numberOfHistories();
+            pod.spectrum = pod.heel = pod.bowtie = -1;
+            double w = std::abs(static_cast<double>(pod.weight));
+
+            if (const auto* s = e.specterDistribution()) {
+                auto [it, isNew] = spectrumIdx.try_emplace(s, static_cast<std::int32_t>(f.spectra.size()));
+                if (isNew) {
+                    detail::FlatTables::Spectrum fs;
+                    detail::appendFloats(fs.probs, s->probabilityData());
+                    detail::appendFloats(fs.energies, s->energies());
+                    for (auto a : s->aliasingData())
+                        fs.alias.push_back(static_cast<std::uint32_t>(a));
+                    f.spectra.push_back(std::move(fs));
+                }
+                pod.spectrum = it->second;
+            }
+            if (const auto* h = e.heelFilter()) {
+                auto [it, isNew] = heelIdx.try_emplace(h, static_cast<std::int32_t>(f.heels.size()));
+                if (isNew) {
+                    detail::FlatTables::Heel fh;
+                    fh.desc.energy_start = static_cast<float>(h->energyStart());
+                    fh.desc.energy_step = static_cast<float>(h->energyStep());
+                    fh.desc.energy_size = static_cast<std::uint32_t>(h->energySize());
+                    fh.desc.angle_start = static_cast<float>(h->angleStart());
+                    fh.desc.angle_step = static_cast<float>(h->angleStep());
+                    fh.desc.angle_size = static_cast<std::uint32_t>(h->angleSize());
+                    detail::appendFloats(fh.weights, h->weights());
+                    heelMax.push_back(*std::max_element(fh.weights.begin(), fh.weights.end()));
+                    f.heels.push_back(std::move(fh));
+                }
+                pod.heel = it->second;
+                w *= std::max(1.0, heelMax[it->second]);
+            }
+            if (const auto* b = e.beamFilter()) {
+                auto [it, isNew] = bowtieIdx.try_emplace(b, static_cast<std::int32_t>(f.bowties.size()));
+                if (isNew) {
+                    detail::FlatTables::Bowtie fb;
+                    if (const auto* bt = dynamic_cast<const BowTieFilter<T>*>(b)) {
+                        for (const auto& [angle, weight] : bt->data()) {
+                            fb.angles.push_back(static_cast<float>(angle));
+                            fb.weights.push_back(static_cast<float>(weight));
+                        }
+                    } else {
+                        // any other BeamFilter is tabulated on |angle| in [0, pi/2] (symmetric filters only)
+                        constexpr int n = 2048;
+                        for (int k = 0; k < n; ++k) {
+                            const T a = (PI_VAL<T>() / 2) * k / (n - 1);
+                            fb.angles.push_back(static_cast<float>(a));
+                            fb.weights.push_back(static_cast<float>(b->sampleIntensityWeight(a)));
+                        }
+                    }
+                    bowtieMax.push_back(*std::max_element(fb.weights.begin(), fb.weights.end()));
+                    f.bowties.push_back(std::move(fb));
+                }
+                pod.bowtie = it->second;
+                w *= std::max(1.0, bowtieMax[it->second]);
+            }
+            f.maxWeight = std::max(f.maxWeight, w);
+            f.exposures.push_back(pod);
+        }
+        if (f.maxWeight <= 0)
+            f.maxWeight = 1;
+    }
+
+    template <typename U>
+    void uploadWorld(dxmcb200_ctx* ctx, const U& world) const
+    {
+        dxmcb200_world w {};
+        for (int i = 0; i < 3; ++i) {
+            w.dim[i] = world.dimensions()[i];
+            w.spacing[i] = static_cast<float>(world.spacing()[i]);
+        }
+        for (int i = 0; i < 6; ++i)
+            w.extent_safe[i] = static_cast<float>(world.matrixExtentSafe()[i]);
+        std::vector<float> converted;
+        if constexpr (std::is_same_v<T, float>) {
+            w.density = world.densityArray()->data();
+        } else {
+            converted.assign(world.densityArray()->begin(), world.densityArray()->end());
+            w.density = converted.data();
+        }
+        w.material = world.materialIndexArray()->data();
+        w.measurement = world.measurementMapArray() ? world.measurementMapArray()->data() : nullptr;
+        detail::check(ctx, dxmcb200_set_world(ctx, &w), "set_world");
+    }
+
+    void uploadBeamTables(dxmcb200_ctx* ctx, const detail::FlatTables& f) const
+    {
+        std::vector<dxmcb200_spectrum> s;
+        std::vector<dxmcb200_heel> h;
+        std::vector<dxmcb200_bowtie> b;
+        for (const auto& x : f.spectra)
+            s.push_back({ static_cast<std::uint32_t>(x.probs.size()), x.probs.data(), x.alias.data(), x.energies.data() });
+        for (const auto& x : f.heels) {
+            auto d = x.desc;
+            d.weights = x.weights.data();
+            h.push_back(d);
+        }
+        for (const auto& x : f.bowties)
+            b.push_back({ static_cast<std::uint32_t>(x.angles.size()), x.angles.data(), x.weights.data() });
+        detail::check(ctx,
+            dxmcb200_set_beam_tables(ctx, static_cast<std::uint32_t>(s.size()), s.data(), static_cast<std::uint32_t>(h.size()), h.data(),
+                static_cast<std::uint32_t>(b.size()), b.data()),
+            "set_beam_tables");
+    }
+
+    void download(dxmcb200_ctx* ctx, int mode, Result<T>& result, float calibration) const
+    {
+        if constexpr (std::is_same_v<T, float>) {
+            detail::check(ctx,
+                dxmcb200_get_result(ctx, mode, result.numberOfHistories, calibration, result.dose.data(), result.nEvents.data(), result.variance.data()),
+                "get_result");
+        } else {
+            std::vector<float> dose(result.dose.size()), variance(result.variance.size());
+            detail::check(ctx, dxmcb200_get_result(ctx, mode, result.numberOfHistories, calibration, dose.data(), result.nEvents.data(), variance.data()),
+                "get_result");
+            std::copy(dose.begin(), dose.end(), result.dose.begin());
+            std::copy(variance.begin(), variance.end(), result.variance.begin());
+        }
+    }
+
+private:
+    AttenuationLut<T> m_attenuationLut;
+    std::uint64_t m_nThreads;
+    OUTPUTMODE m_outputmode = OUTPUTMODE::DOSE;
+    LOWENERGYCORRECTION m_lowenergyCorrection = LOWENERGYCORRECTION::LIVERMORE;
+    int m_device = 0;
+    std::uint64_t m_seed = 0xD1C02026ULL;
+    dxmcb200_stats m_stats {};
+};
+}

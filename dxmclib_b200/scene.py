@@ -60,7 +60,7 @@ class ResultInfo(C.Structure):
 
 # every symbol include/dxmcb200_scene.h declares (the CPU test suite checks the export list against this)
 SCENE_SYMBOLS = [
-    "dxs_backend", "dxs_create", "dxs_destroy", "dxs_world_geometry", "dxs_world_add_material",
+    "dxs_backend", "dxs_last_error", "dxs_create", "dxs_destroy", "dxs_world_geometry", "dxs_world_add_material",
     "dxs_world_add_element", "dxs_world_arrays", "dxs_world_ctdi_phantom", "dxs_world_validate",
     "dxs_world_dimensions", "dxs_world_get_arrays", "dxs_world_ctdi_holes", "dxs_material_attenuation",
     "dxs_material_form_factor_sq", "dxs_material_scatter_factor", "dxs_material_binding_energies",
@@ -80,14 +80,15 @@ def load(path: str) -> C.CDLL:
         return _libs[path]
     if not os.path.exists(path):
         raise FileNotFoundError(f"{path} is not built (run `python -c 'import __graft_entry__ as g; g.build()'`)")
-    lib = C.CDLL(path, mode=C.RTLD_GLOBAL)
+    lib = C.CDLL(path)  # RTLD_LOCAL: product and reference libraries export the same C++ names
     lib.dxs_backend.restype = C.c_char_p
+    lib.dxs_last_error.restype = C.c_char_p
     lib.dxs_create.restype = C.c_void_p
     lib.dxs_destroy.argtypes = [C.c_void_p]
     lib.dxs_destroy.restype = None
     for name in SCENE_SYMBOLS:
         fn = getattr(lib, name)
-        if name not in ("dxs_backend", "dxs_create", "dxs_destroy"):
+        if name not in ("dxs_backend", "dxs_last_error", "dxs_create", "dxs_destroy"):
             fn.restype = C.c_int
     _libs[path] = lib
     return lib
@@ -107,7 +108,12 @@ class SceneError(RuntimeError):
 
 def _chk(code: int, what: str):
     if code != 0:
-        raise SceneError(f"{what} failed with status {code}")
+        msg = ""
+        for lib in _libs.values():
+            m = lib.dxs_last_error().decode()
+            if m:
+                msg = ": " + m
+        raise SceneError(f"{what} failed with status {code}{msg}")
 
 
 def _f32(a, n=None):

@@ -1,0 +1,209 @@
+/* dxmcb200.h — C ABI of the B200 photon-transport runtime (libdxmcb200.so).
+ *
+ * This is the seam the reference crosses at Transport<T>::parallellRun
+ * (reference include/dxmc/transport.hpp:765-778): everything the reference's worker threads read
+ * (world arrays, attenuation look-up tables, beam tables, exposures) goes in as plain data,
+ * the three per-voxel result arrays come out. POD only, no C++ or torch types, no exceptions;
+ * every function returns 0 on success or a negative dxmcb200_status.
+ *
+ * Callers: the drop-in C++ classes in dxmclib_b200/include/dxmc/ (Transport<T>::operator()),
+ * and any FFI (ctypes in tests/ and bench.py). There is NO CPU fallback: without a CUDA device
+ * dxmcb200_create fails with DXMCB200_ERR_NO_DEVICE.
+ *
+ * Threading: one ctx per device per host thread. dxmcb200_run is synchronous for the caller and
+ * asynchronous on the ctx's own CUDA stream inside.
+ */
+#ifndef DXMCB200_H
+#define DXMCB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dxmcb200_ctx dxmcb200_ctx;
+
+enum dxmcb200_status {
+    DXMCB200_OK = 0,
+    DXMCB200_ERR_ARG = -1,
+    DXMCB200_ERR_NO_DEVICE = -2,
+    DXMCB200_ERR_CUDA = -3,
+    DXMCB200_ERR_STATE = -4,
+    DXMCB200_ERR_CANCELLED = -5,
+    DXMCB200_ERR_NCCL = -6
+};
+
+/* ---- inputs ----------------------------------------------------------------------------- */
+
+/* World<T> as the hot loop sees it (reference world.hpp:37-68, transport.hpp:485-521, 643-645).
+ * Voxel order is x fastest: idx = z*nx*ny + y*nx + x (transport.hpp:514). Arrays are HOST pointers
+ * and are copied (packed into one 8-byte record per voxel on the device). measurement may be NULL. */
+typedef struct dxmcb200_world {
+    uint64_t dim[3];
+    float spacing[3];
+    float extent_safe[6]; /* World::matrixExtentSafe(): x0 x1 y0 y1 z0 z1 */
+    const float* density;
+    const uint8_t* material;
+    const uint8_t* measurement;
+} dxmcb200_world;
+
+enum { DXMCB200_RITA_N = 56, DXMCB200_SPLINE_N = 16, DXMCB200_SHELLS = 12, DXMCB200_SHELL_FLOATS = 11,
+    DXMCB200_SPLINE_FLOATS = 63 };
+
+/* AttenuationLut<T> flattened (reference attenuationlut.hpp:267-274, attenuationinterpolator.hpp:37-45).
+ * All arrays are HOST pointers, copied. */
+typedef struct dxmcb200_luts {
+    uint32_t n_materials;
+    uint32_t n_segments;        /* m_resolution after generate(): number of log-log segments */
+    uint32_t linear_index;      /* m_linearIndex */
+    float linear_step;          /* m_linearStep */
+    float linear_energy;        /* m_linearEnergy (log10 keV) */
+    const float* knots;         /* m_x: [n_segments] upper segment edges, log10 keV */
+    const float* coefficients;  /* m_coefficients: [n_materials][n_segments][photo,compton,rayleigh][b,a] */
+    const float* max_coefficients; /* m_maxCoefficients: [n_segments][b,a] of the Woodcock majorant inverse */
+    const float* rita;          /* form-factor sampler RITA<T,56>: [n_materials][x|e|a|b][56] (dxmcrandom.hpp:334-339) */
+    const float* spline;        /* scatter function CubicSplineInterpolator<T,16>: [n_materials][60 coeffs, start, step, stop] */
+    const float* shells;        /* ElectronShellConfiguration<T>[12] per material: [n_materials][12]
+                                   {binding, nElectrons, J0, photoIonProb, yield, lineProb[3], lineEnergy[3]} */
+} dxmcb200_luts;
+
+/* SpecterDistribution<T> (alias table, reference dxmcrandom.hpp:173-330) */
+typedef struct dxmcb200_spectrum {
+    uint32_t n;
+    const float* probs;    /* m_probs */
+    const uint32_t* alias; /* m_alias */
+    const float* energies; /* m_energies */
+} dxmcb200_spectrum;
+
+/* HeelFilter<T> (reference beamfilters.hpp:436-538) */
+typedef struct dxmcb200_heel {
+    float energy_start, energy_step;
+    uint32_t energy_size;
+    float angle_start, angle_step;
+    uint32_t angle_size;
+    const float* weights; /* [energy_size][angle_size] */
+} dxmcb200_heel;
+
+/* BowTieFilter<T> (reference beamfilters.hpp:78-199): sorted |angle|, normalised weight */
+typedef struct dxmcb200_bowtie {
+    uint32_t n;
+    const float* angles;
+    const float* weights;
+} dxmcb200_bowtie;
+
+/* Exposure<T> after alignToDirectionCosines (reference exposure.hpp:36-304) */
+typedef struct dxmcb200_exposure {
+    float position[3];
+    float cosines[6];
+    float beam_direction[3];
+    float collimation[4]; /* x0 x1 y0 y1 */
+    float weight;         /* m_beamIntensityWeight */
+    float mono_energy;    /* used when spectrum < 0 */
+    int32_t spectrum;     /* index into the spectra table or -1 */
+    int32_t heel;         /* index into the heel table or -1 */
+    int32_t bowtie;       /* index into the bowtie table or -1 */
+    uint32_t reserved;
+    uint64_t histories;
+} dxmcb200_exposure;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+int dxmcb200_device_count(int* count);
+int dxmcb200_create(int device, dxmcb200_ctx** out);
+void dxmcb200_destroy(dxmcb200_ctx*);
+const char* dxmcb200_last_error(dxmcb200_ctx*);
+
+int dxmcb200_set_world(dxmcb200_ctx*, const dxmcb200_world*);
+int dxmcb200_set_luts(dxmcb200_ctx*, const dxmcb200_luts*);
+int dxmcb200_set_beam_tables(dxmcb200_ctx*, uint32_t n_spectra, const dxmcb200_spectrum* spectra, uint32_t n_heel,
+    const dxmcb200_heel* heel, uint32_t n_bowtie, const dxmcb200_bowtie* bowtie);
+
+/* Scoring is 64-bit fixed point: energy [keV*weight] is added as round(e * 2^energy_bits), energy^2 as
+ * round(e^2 * 2^energy_sq_bits) (replaces the float atomics of transport.hpp:208-214, 598-609), so the
+ * grids are bit-reproducible for any thread order and any GPU partition. Must be set before the
+ * first run and be the same on all ranks; dxmcb200_suggest_fixed_point picks the largest scale that
+ * cannot overflow for `total_histories` photons of at most `max_energy_weight` keV*weight each. */
+int dxmcb200_suggest_fixed_point(uint64_t total_histories, double max_energy_weight, int* energy_bits, int* energy_sq_bits);
+int dxmcb200_set_fixed_point(dxmcb200_ctx*, int energy_bits, int energy_sq_bits);
+
+/* zero the accumulators and counters */
+int dxmcb200_clear(dxmcb200_ctx*);
+
+/* ---- the hot path ------------------------------------------------------------------------- */
+typedef void (*dxmcb200_progress_cb)(uint64_t exposures_done, void* user);
+
+/* Counter-based per-history stream (replaces the per-thread std::random_device seeding of
+ * transport.hpp:749): PCG32 (dxmcrandom.hpp:156-165) with {state, increment} =
+ * dxmcb200_history_stream(seed, exposure index, history index). */
+void dxmcb200_history_stream(uint64_t seed, uint64_t exposure, uint64_t history, uint64_t out_state[2]);
+
+/* Transport exposures[exp_begin, exp_end) of the array `exposures` (indexed absolutely, so any
+ * partition of the exposure range over GPUs reproduces the same streams) and add into the ctx's
+ * accumulators. low_energy_model: 0 none, 1 Livermore, 2 impulse approximation
+ * (lowenergycorrectionmodel.hpp). cancel (may be NULL) is polled between launches. */
+int dxmcb200_run(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t exp_begin, uint64_t exp_end,
+    int low_energy_model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user);
+
+/* Same with the exposure table already resident on the device (uploaded once by
+ * dxmcb200_upload_exposures); used by bench.py's device-resident timing. */
+int dxmcb200_upload_exposures(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t n);
+int dxmcb200_run_resident(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed);
+
+/* milliseconds the transport kernels of the last run took (CUDA events on the ctx stream) */
+int dxmcb200_last_run_ms(dxmcb200_ctx*, double* kernel_ms);
+
+/* ---- outputs ------------------------------------------------------------------------------ */
+/* Result<T> with the reference's post-processing (transport.hpp:187-200):
+ *   output_mode 0  EV_PER_HISTORY  normalizeScoring (transport.hpp:780-794), n = total_histories
+ *   output_mode 1  DOSE            energyImpartedToDose (transport.hpp:796-816) with `calibration`
+ *   output_mode 2  raw             dose = sum(e*w) keV, variance = sum((e*w)^2), no scaling
+ * Any output pointer may be NULL. Host pointers. */
+int dxmcb200_get_result(dxmcb200_ctx*, int output_mode, uint64_t total_histories, float calibration, float* dose,
+    uint32_t* n_events, float* variance);
+/* raw fixed-point grids (host pointers, any may be NULL) */
+int dxmcb200_get_raw(dxmcb200_ctx*, int64_t* energy, uint64_t* energy_sq, uint64_t* events);
+/* device address of the accumulator block: n_voxels records of 4 x u64 {energy, energy_sq, events, 0}.
+ * Multi-GPU: sum these blocks over ranks (integers: any order gives identical bits) with
+ * torch.distributed / NCCL, or call dxmcb200_reduce. */
+int dxmcb200_accumulators(dxmcb200_ctx*, void** device_ptr, uint64_t* n_u64);
+/* ncclAllReduce(sum, uint64) of the accumulator block on the ctx stream; comm is an ncclComm_t.
+ * libnccl is loaded on first use. */
+int dxmcb200_reduce(dxmcb200_ctx*, void* nccl_comm);
+
+typedef struct dxmcb200_stats {
+    uint64_t histories;        /* photons born */
+    uint64_t histories_in_world; /* photons that reached the voxel grid */
+    uint64_t steps;            /* Woodcock steps taken */
+    uint64_t lookups;          /* in-world voxel look-ups (L of the roofline model) */
+    uint64_t interactions;     /* real interactions sampled */
+    uint64_t score_events;     /* scoring events (S of the roofline model) */
+    uint64_t kernel_launches;
+    double kernel_ms;          /* summed over all runs since dxmcb200_clear */
+} dxmcb200_stats;
+int dxmcb200_get_stats(dxmcb200_ctx*, dxmcb200_stats*);
+
+/* ---- stand-alone device entry points used by the parity tests ------------------------------
+ * Each evaluates one hot-path primitive on the GPU for n inputs (host pointers in/out). */
+/* a9/a10: AttenuationLutInterpolator::operator() and maxAttenuationInverse (attenuationinterpolator.hpp:207-248) */
+int dxmcb200_eval_attenuation(dxmcb200_ctx*, uint64_t n, const uint8_t* material, const float* energy,
+    float* out_photo_compton_rayleigh /* [n][3] */, float* out_max_inverse /* [n] */);
+/* a6/a7/a5: for ray r, entry point by transportParticleToWorld then positions pos += dir*step[k], reporting
+ * indexFromPosition or -1 once outside (transport.hpp:485-521, 702-728). steps are shared by all rays. */
+int dxmcb200_trace_indices(dxmcb200_ctx*, uint64_t n_rays, const float* pos /*[n][3]*/, const float* dir /*[n][3]*/,
+    uint32_t n_steps, const float* steps, int64_t* out_indices /*[n][n_steps+1], slot 0 = entry voxel*/,
+    float* out_entry /*[n][3]*/);
+/* a4: Exposure::sampleParticle for histories [0,n) of exposure `exposure_index` of `exposure`:
+ * out [n][8] = pos[3], dir[3], energy, weight (exposure.hpp:280-304) */
+int dxmcb200_sample_particles(dxmcb200_ctx*, const dxmcb200_exposure* exposure, uint64_t exposure_index, uint64_t seed,
+    uint64_t n, float* out);
+/* a13-a16: one interaction of kind (0 photo, 1 Compton, 2 Rayleigh) for n photons of `energy` in
+ * `material` travelling along +z, history streams (seed, exposure 0, history i):
+ * out [n][5] = energy imparted, new energy, new dir[3] */
+int dxmcb200_sample_interaction(dxmcb200_ctx*, int kind, int low_energy_model, uint8_t material, float energy, uint64_t seed,
+    uint64_t n, float* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -41,6 +41,8 @@ enum dxs_output { DXS_OUT_EV_PER_HISTORY = 0, DXS_OUT_DOSE = 1 };
 
 /* which implementation this library is: "dxmc-b200" or "dxmclib-reference" */
 const char* dxs_backend(void);
+/* message of the last failed call on this thread ("" when none) */
+const char* dxs_last_error(void);
 
 dxs_scene* dxs_create(void);
 void dxs_destroy(dxs_scene*);
@@ -168,7 +170,12 @@ int dxs_source_calibration(dxs_scene*, int model, float* out);
  * not reproducible; with seed!=0 the reference harness runs the workers' loop (getExposure, align,
  * transport<L>) on ONE thread with RandomState{seed, seed^0x9E3779B97F4A7C15}; seed==0 runs the
  * stock multi-threaded operator(). The B200 implementation keys its per-history counter streams on
- * `seed` in both cases. n_workers<=0: hardware_concurrency (reference default). */
+ * `seed` in both cases. n_workers==0: hardware_concurrency (reference default).
+ * n_workers==DXS_WORKERS_COUNTER_STREAMS: the reference harness gives EVERY history its own RandomState
+ * seeded by the product's dxmcb200_history_stream(seed, exposure, history) and spreads exposures over all
+ * host threads, so both implementations consume identical random numbers history by history and
+ * differ only by libm-vs-CUDA rounding. */
+#define DXS_WORKERS_COUNTER_STREAMS (-1)
 typedef struct dxs_result_info {
     uint64_t histories;
     double seconds;          /* Result::simulationTime */
