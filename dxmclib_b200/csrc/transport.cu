@@ -1047,6 +1047,14 @@ int dxmcb200_get_stats(dxmcb200_ctx* c, dxmcb200_stats* s)
     return DXMCB200_OK;
 }
 
+int dxmcb200_enable_stats(dxmcb200_ctx* c, int on)
+{
+    if (!c)
+        return DXMCB200_ERR_ARG;
+    c->collectStats = on != 0;
+    return DXMCB200_OK;
+}
+
 int dxmcb200_eval_attenuation(dxmcb200_ctx* c, uint64_t n, const uint8_t* material, const float* energy, float* out3, float* outMax)
 {
     if (!c || !c->dLutBlob || !material || !energy || !out3 || !outMax || n == 0)

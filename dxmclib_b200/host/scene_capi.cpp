@@ -23,6 +23,7 @@ struct dxs_scene {
     CTSource<float>* ct = nullptr;
     AttenuationLut<float> lut;
     bool lutValid = false;
+    std::unique_ptr<Transport<float>> prepared; // dxs_b200_prepare .. dxs_b200_release
 };
 
 namespace {
@@ -631,6 +632,81 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
         }
         return DXS_OK;
     });
+}
+
+int dxs_b200_prepare(dxs_scene* s, int device, int model, uint64_t seed, uint64_t totalHistoriesAllRanks)
+{
+    if (!s || !s->source)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        s->prepared = std::make_unique<Transport<float>>();
+        s->prepared->setDevice(device);
+        s->prepared->setLowEnergyCorrectionModel(static_cast<LOWENERGYCORRECTION>(model));
+        if (seed != 0)
+            s->prepared->setSeed(seed);
+        s->world->makeValid();
+        if (!s->prepared->prepare(*s->world, s->source.get(), totalHistoriesAllRanks)) {
+            s->prepared.reset();
+            return static_cast<int>(DXS_ERR_STATE);
+        }
+        return static_cast<int>(DXS_OK);
+    });
+}
+
+int dxs_b200_run(dxs_scene* s, uint64_t expBegin, uint64_t expEnd, double* kernelMs)
+{
+    if (!s || !s->prepared)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        s->prepared->run(expBegin, expEnd);
+        if (kernelMs)
+            dxmcb200_last_run_ms(s->prepared->context(), kernelMs);
+        return DXS_OK;
+    });
+}
+
+int dxs_b200_collect(dxs_scene* s, int outputMode, int useCalibration, uint64_t histories, float* dose, uint32_t* nEvents, float* variance,
+    dxs_result_info* info)
+{
+    if (!s || !s->prepared)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        auto& tr = *s->prepared;
+        tr.setOutputMode(outputMode == DXS_OUT_DOSE ? Transport<float>::OUTPUTMODE::DOSE : Transport<float>::OUTPUTMODE::EV_PER_HISTORY);
+        Result<float> res(s->world->size());
+        res.numberOfHistories = histories ? histories : tr.preparedHistories();
+        tr.collect(*s->world, s->source.get(), res, useCalibration != 0, nullptr);
+        const auto n = res.dose.size();
+        if (dose)
+            std::memcpy(dose, res.dose.data(), n * sizeof(float));
+        if (nEvents)
+            std::memcpy(nEvents, res.nEvents.data(), n * sizeof(std::uint32_t));
+        if (variance)
+            std::memcpy(variance, res.variance.data(), n * sizeof(float));
+        if (info) {
+            info->histories = res.numberOfHistories;
+            info->seconds = 0;
+            std::memset(info->units, 0, sizeof(info->units));
+            std::strncpy(info->units, std::string(res.dose_units).c_str(), sizeof(info->units) - 1);
+        }
+        return DXS_OK;
+    });
+}
+
+int dxs_b200_context(dxs_scene* s, void** ctx)
+{
+    if (!s || !s->prepared || !ctx)
+        return DXS_ERR_STATE;
+    *ctx = s->prepared->context();
+    return DXS_OK;
+}
+
+int dxs_b200_release(dxs_scene* s)
+{
+    if (!s)
+        return DXS_ERR_ARG;
+    s->prepared.reset();
+    return DXS_OK;
 }
 
 } // extern "C"

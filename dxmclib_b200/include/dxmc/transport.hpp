@@ -141,38 +141,72 @@ public:
         requires std::is_base_of_v<World<T>, U>
     Result<T> operator()(const U& world, Source<T>* source, ProgressBar<T>* progressbar = nullptr, bool useSourceDoseCalibration = true)
     {
+        if (!prepare(world, source))
+            return Result<T>(world.size());
         Result<T> result(world.size());
+        result.numberOfHistories = m_histories;
+        const bool completed = run(0, m_totalExposures, progressbar, &result, &world);
+        if (completed)
+            collect(world, source, result, useSourceDoseCalibration, progressbar);
+        else
+            result.numberOfHistories = 0; // cancelled: all zeros, like a cancelled reference run
+        release();
+        return result;
+    }
+
+    // ---- the three phases of operator(), public so that a caller can keep the world, tables and
+    // exposures resident on the GPU across runs (bench.py, multi-GPU drivers) -------------------------
+
+    // validate, build the look-up tables on the host, flatten and upload everything. Returns false for the
+    // inputs the reference answers with an all-zero Result (invalid world / null or invalid source).
+    // historiesAllRanks: total over all GPUs of a sharded run (sizes the fixed-point scale); 0 = this source.
+    template <typename U>
+        requires std::is_base_of_v<World<T>, U>
+    bool prepare(const U& world, Source<T>* source, std::uint64_t historiesAllRanks = 0)
+    {
+        release();
         if (!world.isValid() || !source)
-            return result;
+            return false;
         source->updateFromWorld(world);
         source->validate();
         if (!source->isValid())
-            return result;
-        result.numberOfHistories = source->historiesPerExposure() * source->totalExposures();
+            return false;
+        m_histories = source->historiesPerExposure() * source->totalExposures();
+        m_totalExposures = source->totalExposures();
         m_attenuationLut.generate(world, source->maxPhotonEnergyProduced());
 
-        const std::uint64_t totalExposures = source->totalExposures();
-        detail::FlatTables flat;
-        flattenLuts(flat);
-        flattenExposures(world, *source, totalExposures, flat);
+        m_flat = detail::FlatTables {};
+        flattenLuts(m_flat);
+        flattenExposures(world, *source, m_totalExposures, m_flat);
 
         dxmcb200_ctx* raw = nullptr;
         const int created = dxmcb200_create(m_device, &raw);
         if (created != DXMCB200_OK)
             throw std::runtime_error("dxmcb200: no usable CUDA device " + std::to_string(m_device) + " (status " + std::to_string(created)
                 + "); this library has no CPU fallback");
-        detail::ContextPtr ctx(raw);
-        uploadWorld(ctx.get(), world);
-        detail::check(ctx.get(), dxmcb200_set_luts(ctx.get(), &flat.luts), "set_luts");
-        uploadBeamTables(ctx.get(), flat);
+        m_ctx.reset(raw);
+        uploadWorld(m_ctx.get(), world);
+        detail::check(m_ctx.get(), dxmcb200_set_luts(m_ctx.get(), &m_flat.luts), "set_luts");
+        uploadBeamTables(m_ctx.get(), m_flat);
         int energyBits = 20, energySqBits = 10;
-        dxmcb200_suggest_fixed_point(result.numberOfHistories, flat.maxWeight * static_cast<double>(source->maxPhotonEnergyProduced()), &energyBits,
-            &energySqBits);
-        detail::check(ctx.get(), dxmcb200_set_fixed_point(ctx.get(), energyBits, energySqBits), "set_fixed_point");
+        dxmcb200_suggest_fixed_point(std::max(historiesAllRanks, m_histories), m_flat.maxWeight * static_cast<double>(source->maxPhotonEnergyProduced()),
+            &energyBits, &energySqBits);
+        detail::check(m_ctx.get(), dxmcb200_set_fixed_point(m_ctx.get(), energyBits, energySqBits), "set_fixed_point");
+        if (!m_flat.exposures.empty())
+            detail::check(m_ctx.get(), dxmcb200_upload_exposures(m_ctx.get(), m_flat.exposures.data(), m_flat.exposures.size()), "upload_exposures");
+        return true;
+    }
 
+    // transport exposures [begin, end) into the device accumulators; false when cancelled
+    template <typename U = World<T>>
+    bool run(std::uint64_t begin, std::uint64_t end, ProgressBar<T>* progressbar = nullptr, Result<T>* result = nullptr, const U* world = nullptr)
+    {
+        if (!m_ctx)
+            throw std::runtime_error("dxmcb200: Transport::run called before prepare");
         if (progressbar) {
-            progressbar->setTotalExposures(totalExposures);
-            progressbar->setDoseData(result.dose.data(), world.dimensions(), world.spacing());
+            progressbar->setTotalExposures(end - begin);
+            if (result && world)
+                progressbar->setDoseData(result->dose.data(), world->dimensions(), world->spacing());
         }
         struct Progress {
             ProgressBar<T>* bar;
@@ -189,22 +223,32 @@ public:
         };
         if (progressbar && progressbar->cancel())
             progress.cancel = 1;
-
         const auto start = std::chrono::system_clock::now();
-        const int ran = dxmcb200_run(ctx.get(), flat.exposures.data(), 0, totalExposures, static_cast<int>(m_lowenergyCorrection), m_seed,
-            &progress.cancel, callback, &progress);
-        result.simulationTime = std::chrono::system_clock::now() - start;
-        detail::check(ctx.get(), ran, "run");
-        dxmcb200_get_stats(ctx.get(), &m_stats);
-
+        const int ran = dxmcb200_run(m_ctx.get(), m_flat.exposures.data(), begin, end, static_cast<int>(m_lowenergyCorrection), m_seed, &progress.cancel,
+            callback, &progress);
+        if (result)
+            result->simulationTime = std::chrono::system_clock::now() - start;
+        detail::check(m_ctx.get(), ran, "run");
+        dxmcb200_get_stats(m_ctx.get(), &m_stats);
         if (progressbar) {
             progressbar->clearDoseData();
-            if (progressbar->cancel() || ran == DXMCB200_ERR_CANCELLED) {
-                result.numberOfHistories = 0;
-                return result; // all zeros, like a cancelled reference run
-            }
+            if (progressbar->cancel())
+                return false;
         }
+        return ran != DXMCB200_ERR_CANCELLED;
+    }
 
+    // decode the accumulators with the reference's post-processing for the current output mode
+    template <typename U>
+        requires std::is_base_of_v<World<T>, U>
+    void collect(const U& world, Source<T>* source, Result<T>& result, bool useSourceDoseCalibration = true, ProgressBar<T>* progressbar = nullptr)
+    {
+        if (!m_ctx)
+            throw std::runtime_error("dxmcb200: Transport::collect called before prepare");
+        if (result.dose.size() != world.size())
+            result = Result<T>(world.size());
+        if (result.numberOfHistories == 0)
+            result.numberOfHistories = m_histories;
         int mode = 0;
         float calibration = 1.0f;
         if (m_outputmode == OUTPUTMODE::DOSE) {
@@ -221,9 +265,14 @@ public:
         } else {
             result.dose_units = "eV/history";
         }
-        download(ctx.get(), mode, result, calibration);
-        return result;
+        download(m_ctx.get(), mode, result, calibration);
     }
+
+    // device context of a prepared Transport, for direct C-ABI calls (accumulator address, stats, raw grids)
+    dxmcb200_ctx* context() const { return m_ctx.get(); }
+    std::uint64_t preparedExposures() const { return m_totalExposures; }
+    std::uint64_t preparedHistories() const { return m_histories; }
+    void release() { m_ctx.reset(); }
 
     const AttenuationLut<T>& attenuationLut() const { return m_attenuationLut; }
     AttenuationLut<T>& attenuationLut() { return m_attenuationLut; }
@@ -419,5 +468,9 @@ private:
     int m_device = 0;
     std::uint64_t m_seed = 0xD1C02026ULL;
     dxmcb200_stats m_stats {};
+    detail::ContextPtr m_ctx;
+    detail::FlatTables m_flat;
+    std::uint64_t m_totalExposures = 0;
+    std::uint64_t m_histories = 0;
 };
 }

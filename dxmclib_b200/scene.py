@@ -20,6 +20,7 @@ REFERENCE_LIB = os.path.join(ROOT, "oracle", "_ref", "libdxmc_ref.so")
 
 MODEL_NONE, MODEL_LIVERMORE, MODEL_IA = 0, 1, 2
 OUT_EV_PER_HISTORY, OUT_DOSE = 0, 1
+WORKERS_COUNTER_STREAMS = -1  # reference harness only: one RandomState per history, keyed like the kernels' streams
 
 _f32p = C.POINTER(C.c_float)
 _f64p = C.POINTER(C.c_double)
@@ -69,6 +70,7 @@ SCENE_SYMBOLS = [
     "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
     "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport",
+    "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
 ]
 
 _libs: dict[str, C.CDLL] = {}
@@ -390,3 +392,35 @@ class Scene:
                                     dose.ctypes.data_as(_f32p), None if ev is None else ev.ctypes.data_as(_u32p),
                                     None if var is None else var.ctypes.data_as(_f32p), C.byref(info)), "dxs_transport")
         return Result(dose, ev, var, int(info.histories), float(info.seconds), info.units.decode())
+
+    # ---- B200 extensions (product library only)
+    def b200_prepare(self, device=0, model=MODEL_LIVERMORE, seed=0, total_histories_all_ranks=0):
+        _chk(self.lib.dxs_b200_prepare(self.h, int(device), int(model), C.c_uint64(seed), C.c_uint64(total_histories_all_ranks)),
+             "dxs_b200_prepare")
+        return self
+
+    def b200_run(self, exp_begin, exp_end) -> float:
+        """Transport exposures [exp_begin, exp_end); returns the CUDA-event time of the kernels in ms."""
+        ms = C.c_double(0)
+        _chk(self.lib.dxs_b200_run(self.h, C.c_uint64(exp_begin), C.c_uint64(exp_end), C.byref(ms)), "dxs_b200_run")
+        return float(ms.value)
+
+    def b200_collect(self, output=OUT_EV_PER_HISTORY, use_calibration=False, histories=0, want_events=True,
+                     want_variance=True) -> Result:
+        n = int(np.prod(self.dim))
+        dose = np.zeros(n, np.float32)
+        ev = np.zeros(n, np.uint32) if want_events else None
+        var = np.zeros(n, np.float32) if want_variance else None
+        info = ResultInfo()
+        _chk(self.lib.dxs_b200_collect(self.h, output, int(use_calibration), C.c_uint64(histories), dose.ctypes.data_as(_f32p),
+                                       None if ev is None else ev.ctypes.data_as(_u32p),
+                                       None if var is None else var.ctypes.data_as(_f32p), C.byref(info)), "dxs_b200_collect")
+        return Result(dose, ev, var, int(info.histories), 0.0, info.units.decode())
+
+    def b200_context(self) -> C.c_void_p:
+        ctx = C.c_void_p()
+        _chk(self.lib.dxs_b200_context(self.h, C.byref(ctx)), "dxs_b200_context")
+        return ctx
+
+    def b200_release(self):
+        _chk(self.lib.dxs_b200_release(self.h), "dxs_b200_release")

@@ -182,6 +182,10 @@ typedef struct dxmcb200_stats {
     double kernel_ms;          /* summed over all runs since dxmcb200_clear */
 } dxmcb200_stats;
 int dxmcb200_get_stats(dxmcb200_ctx*, dxmcb200_stats*);
+/* The per-history work counters (histories .. score_events) cost registers, so the transport kernel is
+ * compiled twice; on != 0 selects the counting variant for subsequent runs (default off, or
+ * DXMCB200_STATS=1 in the environment at create time). kernel_launches / kernel_ms are always kept. */
+int dxmcb200_enable_stats(dxmcb200_ctx*, int on);
 
 /* ---- stand-alone device entry points used by the parity tests ------------------------------
  * Each evaluates one hot-path primitive on the GPU for n inputs (host pointers in/out). */

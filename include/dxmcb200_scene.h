@@ -184,6 +184,21 @@ typedef struct dxs_result_info {
 int dxs_transport(dxs_scene*, int model, int output_mode, int use_calibration, uint64_t seed, int n_workers,
     float* dose, uint32_t* n_events, float* variance, dxs_result_info* info);
 
+/* ---- B200 extensions: the phases of Transport::operator() kept apart so a caller can hold the world,
+ * tables and exposures resident on the GPU (bench.py device-resident timing, multi-GPU sharding).
+ * The reference harness answers DXS_ERR_UNSUPPORTED. -------------------------------------------------- */
+/* Transport::prepare: validate, build + upload LUTs, world, beam tables and ALL exposures on `device`.
+ * total_histories_all_ranks sizes the fixed-point scale for a run sharded over several GPUs (0: this scene). */
+int dxs_b200_prepare(dxs_scene*, int device, int model, uint64_t seed, uint64_t total_histories_all_ranks);
+/* Transport::run on exposures [begin, end); kernel_ms (may be NULL) = CUDA-event time of the transport kernels */
+int dxs_b200_run(dxs_scene*, uint64_t exp_begin, uint64_t exp_end, double* kernel_ms);
+/* Transport::collect: decode accumulators into Result arrays (any pointer may be NULL) */
+int dxs_b200_collect(dxs_scene*, int output_mode, int use_calibration, uint64_t histories, float* dose, uint32_t* n_events,
+    float* variance, dxs_result_info* info);
+/* the prepared dxmcb200_ctx* (include/dxmcb200.h) for direct C-ABI calls: accumulators, stats, clear */
+int dxs_b200_context(dxs_scene*, void** ctx);
+int dxs_b200_release(dxs_scene*);
+
 #ifdef __cplusplus
 }
 #endif
