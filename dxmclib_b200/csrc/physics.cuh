@@ -22,21 +22,51 @@ constexpr float kRouletteThreshold = 5.0f; // transport.hpp:823
 constexpr float kRouletteProbability = 0.8f; // transport.hpp:819
 constexpr float kDirEpsilon = 1.0e-9f; // transport.hpp:831
 
+// ---- arithmetic helpers -----------------------------------------------------------------------
+// trunc(fl(a / s)) for a >= 0, s > 0 — the value static_cast<size_t>(a / s) has in the reference — without
+// an IEEE division on the common path. q = a * (1/s) is within ~1.5 ulp of the true quotient, so its
+// truncation can only disagree with the truncation of the correctly rounded quotient when q lies within a
+// few ulp of an integer; only then the exact division is evaluated. `inv` must be __frcp_rn(s).
+__device__ __forceinline__ uint32_t truncDiv(float a, float s, float inv)
+{
+    const float q = __fmul_rn(a, inv);
+    if (fabsf(__fsub_rn(q, rintf(q))) <= __fmul_rn(q, 4.8e-7f)) // within 4 ulp of an integer (rare)
+        return __float2uint_rz(__fdiv_rn(a, s));
+    return __float2uint_rz(q);
+}
+
+// 10^x to ~2 ulp: x*log2(10) split into a rounded product and its exact residual, MUFU.EX2 on the
+// former, first-order correction with the latter
+__device__ __forceinline__ float fastExp10(float x)
+{
+    constexpr float kLog2_10Hi = 3.3219280242919921875f;
+    constexpr float kLog2_10Lo = 7.0595370e-8f;
+    const float t = __fmul_rn(x, kLog2_10Hi);
+    float r = __fmaf_rn(x, kLog2_10Hi, -t);
+    r = __fmaf_rn(x, kLog2_10Lo, r);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(t));
+    return __fmaf_rn(__fmul_rn(e, r), 0.693147180559945f, e);
+}
+
 // ---- tables as the kernels see them -------------------------------------------------------
+constexpr int kSplineStride = 64; // device copy: 60 coefficients, start, step, stop, 1/step
+
 struct LutView {
     uint32_t nMaterials, nSegments, linearIndex;
-    float linearStep, linearEnergy;
+    float linearStep, linearEnergy, invLinearStep;
     const float* knots; // [nSegments]
     const float* coeff; // [nMaterials][nSegments][6]
     const float* maxCoeff; // [nSegments][2]
     const float* rita; // [nMaterials][4][56]
-    const float* spline; // [nMaterials][63]
+    const float* spline; // [nMaterials][kSplineStride]
     const float* shells; // [nMaterials][12][11]
 };
 
 struct WorldView {
     uint32_t dim[3];
     float spacing[3];
+    float invSpacing[3]; // __frcp_rn(spacing)
     float ext[6];
     const uint2* voxels; // {density bits, material | measurement<<8}
 };
@@ -154,9 +184,9 @@ __device__ __forceinline__ bool insideWorld(const WorldView& w, float x, float y
 
 __device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, float y, float z)
 {
-    const uint32_t ix = __float2uint_rz(__fdiv_rn(__fsub_rn(x, w.ext[0]), w.spacing[0]));
-    const uint32_t iy = __float2uint_rz(__fdiv_rn(__fsub_rn(y, w.ext[2]), w.spacing[1]));
-    const uint32_t iz = __float2uint_rz(__fdiv_rn(__fsub_rn(z, w.ext[4]), w.spacing[2]));
+    const uint32_t ix = truncDiv(__fsub_rn(x, w.ext[0]), w.spacing[0], w.invSpacing[0]);
+    const uint32_t iy = truncDiv(__fsub_rn(y, w.ext[2]), w.spacing[1], w.invSpacing[1]);
+    const uint32_t iz = truncDiv(__fsub_rn(z, w.ext[4]), w.spacing[2], w.invSpacing[2]);
     return iz * w.dim[0] * w.dim[1] + iy * w.dim[0] + ix;
 }
 
@@ -212,7 +242,7 @@ __device__ __forceinline__ uint32_t upperBound(const float* __restrict__ a, uint
 __device__ __forceinline__ uint32_t segmentIndex(const LutView& l, float logE, bool clampLinear)
 {
     if (logE > l.linearEnergy) {
-        const uint32_t i = __float2uint_rz(__fdiv_rn(__fsub_rn(logE, l.linearEnergy), l.linearStep)) + l.linearIndex;
+        const uint32_t i = truncDiv(__fsub_rn(logE, l.linearEnergy), l.linearStep, l.invLinearStep) + l.linearIndex;
         return clampLinear ? min(i, l.nSegments - 1) : i;
     }
     const uint32_t pos = upperBound(l.knots, l.nSegments, logE);
@@ -223,10 +253,12 @@ __device__ __forceinline__ uint32_t segmentIndex(const LutView& l, float logE, b
 __device__ __forceinline__ void attenuation(const LutView& l, uint32_t material, float logE, float& photo, float& compton, float& rayleigh)
 {
     const uint32_t index = segmentIndex(l, logE, true);
-    const float* c = l.coeff + (static_cast<size_t>(material) * l.nSegments + index) * 6;
-    photo = exp10f(__fadd_rn(c[0], __fmul_rn(c[1], logE)));
-    compton = exp10f(__fadd_rn(c[2], __fmul_rn(c[3], logE)));
-    rayleigh = exp10f(__fadd_rn(c[4], __fmul_rn(c[5], logE)));
+    // 6 floats per (material, segment): 24-byte records, so every {b, a} pair is 8-byte aligned
+    const float2* c = reinterpret_cast<const float2*>(l.coeff + (material * l.nSegments + index) * 6);
+    const float2 cp = __ldg(c), cc = __ldg(c + 1), cr = __ldg(c + 2);
+    photo = fastExp10(__fadd_rn(cp.x, __fmul_rn(cp.y, logE)));
+    compton = fastExp10(__fadd_rn(cc.x, __fmul_rn(cc.y, logE)));
+    rayleigh = fastExp10(__fadd_rn(cr.x, __fmul_rn(cr.y, logE)));
 }
 
 // inverse of the Woodcock majorant; the linear branch is not clamped in the reference either
@@ -234,23 +266,24 @@ __device__ __forceinline__ float maxAttenuationInverse(const LutView& l, float l
 {
     uint32_t index = segmentIndex(l, logE, false);
     index = min(index, l.nSegments - 1); // memory safety only; never binds for E <= max table energy
-    const float* c = l.maxCoeff + 2 * index;
-    return exp10f(__fadd_rn(c[0], __fmul_rn(c[1], logE)));
+    const float2 c = __ldg(reinterpret_cast<const float2*>(l.maxCoeff) + index);
+    return fastExp10(__fadd_rn(c.x, __fmul_rn(c.y, logE)));
 }
 
 // Compton scatter function S(q)/Z, cubic spline (interpolation.hpp:169-176)
 __device__ __forceinline__ float scatterFactor(const LutView& l, uint32_t material, float q)
 {
-    const float* s = l.spline + material * DXMCB200_SPLINE_FLOATS;
-    const float start = s[60], step = s[61], stop = s[62];
+    const float* s = l.spline + material * kSplineStride;
+    const float4 lim = __ldg(reinterpret_cast<const float4*>(s + 60)); // start, step, stop, 1/step
+    const float start = lim.x, stop = lim.z;
     const float x = fminf(fmaxf(q, start), stop);
-    const uint32_t index = x > start ? __float2uint_rz(__fdiv_rn(__fsub_rn(x, start), step)) : 0u;
+    const uint32_t index = x > start ? truncDiv(__fsub_rn(x, start), lim.y, lim.w) : 0u;
     const uint32_t offset = index < DXMCB200_SPLINE_N - 1 ? index * 4 : (DXMCB200_SPLINE_N - 2) * 4;
-    const float* c = s + offset;
+    const float4 c = __ldg(reinterpret_cast<const float4*>(s + offset));
     // c0 + c1*x + c2*x*x + c3*x*x*x, left to right
-    float r = __fadd_rn(c[0], __fmul_rn(c[1], x));
-    r = __fadd_rn(r, __fmul_rn(__fmul_rn(c[2], x), x));
-    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(c[3], x), x), x));
+    float r = __fadd_rn(c.x, __fmul_rn(c.y, x));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(c.z, x), x));
+    r = __fadd_rn(r, __fmul_rn(__fmul_rn(__fmul_rn(c.w, x), x), x));
     return r;
 }
 

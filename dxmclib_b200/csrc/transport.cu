@@ -43,6 +43,7 @@ struct KernelParams {
     const uint64_t* prefix; // [nExp+1] cumulative histories of the launched range
     uint64_t expBegin;
     uint32_t nExp;
+    uint32_t uniformHistories; // >0: every exposure of the launch has this many histories and the launch total is < 2^32
     uint64_t totalHistories;
     uint64_t seed;
     unsigned long long* workCounter;
@@ -191,15 +192,23 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
                     exhausted = true;
                 } else {
                     // exposure owning history g: last prefix entry <= g
-                    uint32_t lo = 0, hi = P.nExp;
-                    while (hi - lo > 1) {
-                        const uint32_t mid = (lo + hi) >> 1;
-                        if (__ldg(P.prefix + mid) <= g)
-                            lo = mid;
-                        else
-                            hi = mid;
+                    uint32_t lo = 0;
+                    uint64_t history;
+                    if (P.uniformHistories) {
+                        const uint32_t g32 = static_cast<uint32_t>(g);
+                        lo = g32 / P.uniformHistories;
+                        history = g32 - lo * P.uniformHistories;
+                    } else {
+                        uint32_t hi = P.nExp;
+                        while (hi - lo > 1) {
+                            const uint32_t mid = (lo + hi) >> 1;
+                            if (__ldg(P.prefix + mid) <= g)
+                                lo = mid;
+                            else
+                                hi = mid;
+                        }
+                        history = g - __ldg(P.prefix + lo);
                     }
-                    const uint64_t history = g - __ldg(P.prefix + lo);
                     const uint64_t exposure = P.expBegin + lo;
                     historyStream(P.seed, exposure, history, rng.state, rng.inc);
                     p = sampleParticle(P.exposures[exposure], P.beams, rng);
@@ -244,7 +253,8 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
         // ---- one Woodcock step (transport.hpp:655-682)
         if (state == STEP) {
             const float r1 = rng.uniform();
-            const float stepLength = -logf(r1) * maxAttInv * 10.0f;
+            // MUFU.LG2-based log: absolute error ~1e-7 of a mean free path, far below the float resolution of the position
+            const float stepLength = -__logf(r1) * maxAttInv * 10.0f;
             advance(p, stepLength);
             if constexpr (kStats)
                 ++cSteps;
@@ -515,10 +525,45 @@ T* advancePtr(char*& cursor, size_t count)
     return p;
 }
 
+template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
+cudaError_t launchTransportBatched(const dxmcb200_ctx* c, const KernelParams& P);
+
+// lanes that must wait before a birth / interaction stage runs; tunable for experiments with
+// DXMCB200_BATCH=<birth>,<interact> out of the compiled set
 template <int L, bool kStats>
 cudaError_t launchTransport(const dxmcb200_ctx* c, const KernelParams& P)
 {
-    constexpr int kBirthBatch = 8, kInteractBatch = 8;
+    static const int choice = [] {
+        const char* env = std::getenv("DXMCB200_BATCH");
+        int b = 8, i = 8;
+        if (env)
+            std::sscanf(env, "%d,%d", &b, &i);
+        return b * 100 + i;
+    }();
+    if constexpr (!kStats) {
+        switch (choice) {
+        case 408:
+            return launchTransportBatched<L, kStats, 4, 8>(c, P);
+        case 812:
+            return launchTransportBatched<L, kStats, 8, 12>(c, P);
+        case 816:
+            return launchTransportBatched<L, kStats, 8, 16>(c, P);
+        case 1216:
+            return launchTransportBatched<L, kStats, 12, 16>(c, P);
+        case 1616:
+            return launchTransportBatched<L, kStats, 16, 16>(c, P);
+        case 1624:
+            return launchTransportBatched<L, kStats, 16, 24>(c, P);
+        default:
+            break;
+        }
+    }
+    return launchTransportBatched<L, kStats, 8, 8>(c, P);
+}
+
+template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
+cudaError_t launchTransportBatched(const dxmcb200_ctx* c, const KernelParams& P)
+{
     auto kernel = transportKernel<L, kStats, kBirthBatch, kInteractBatch>;
     int blocksPerSm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
@@ -574,6 +619,10 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             P.expBegin = e0;
             P.nExp = static_cast<uint32_t>(e1 - e0);
             P.totalHistories = total;
+            bool uniform = total < (1ULL << 32);
+            for (uint64_t e = e0; e < e1 && uniform; ++e)
+                uniform = hostExposures[e].histories == hostExposures[e0].histories;
+            P.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[e0].histories) : 0u;
             P.seed = seed;
             P.workCounter = c->dWorkCounter;
             P.acc = c->dAcc;
@@ -711,6 +760,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     for (int i = 0; i < 3; ++i) {
         c->world.dim[i] = static_cast<uint32_t>(w->dim[i]);
         c->world.spacing[i] = w->spacing[i];
+        c->world.invSpacing[i] = 1.0f / w->spacing[i]; // IEEE single division on the host == __frcp_rn
     }
     for (int i = 0; i < 6; ++i)
         c->world.ext[i] = w->extent_safe[i];
@@ -728,7 +778,7 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
     const size_t nCoeff = static_cast<size_t>(l->n_materials) * l->n_segments * 6;
     const size_t nMax = static_cast<size_t>(l->n_segments) * 2;
     const size_t nRita = static_cast<size_t>(l->n_materials) * 4 * DXMCB200_RITA_N;
-    const size_t nSpline = static_cast<size_t>(l->n_materials) * DXMCB200_SPLINE_FLOATS;
+    const size_t nSpline = static_cast<size_t>(l->n_materials) * kSplineStride;
     const size_t nShell = static_cast<size_t>(l->n_materials) * DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS;
     // one blob, every table 16-byte aligned
     auto pad = [](size_t n) { return (n + 3) & ~static_cast<size_t>(3); };
@@ -741,8 +791,15 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
         off += pad(n);
         return at;
     };
+    // device spline records are padded to 64 floats and carry 1/step for the division-free segment index
+    std::vector<float> spline(nSpline, 0.0f);
+    for (uint32_t m = 0; m < l->n_materials; ++m) {
+        std::memcpy(spline.data() + static_cast<size_t>(m) * kSplineStride, l->spline + static_cast<size_t>(m) * DXMCB200_SPLINE_FLOATS,
+            DXMCB200_SPLINE_FLOATS * sizeof(float));
+        spline[static_cast<size_t>(m) * kSplineStride + 63] = 1.0f / l->spline[static_cast<size_t>(m) * DXMCB200_SPLINE_FLOATS + 61];
+    }
     const size_t oKnots = put(l->knots, nKnots), oCoeff = put(l->coefficients, nCoeff), oMax = put(l->max_coefficients, nMax),
-                 oRita = put(l->rita, nRita), oSpline = put(l->spline, nSpline), oShell = put(l->shells, nShell);
+                 oRita = put(l->rita, nRita), oSpline = put(spline.data(), nSpline), oShell = put(l->shells, nShell);
     cudaFree(c->dLutBlob);
     c->dLutBlob = nullptr;
     CU_CHECK(c, cudaMalloc(&c->dLutBlob, total * sizeof(float)));
@@ -752,6 +809,7 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
     c->lut.linearIndex = l->linear_index;
     c->lut.linearStep = l->linear_step;
     c->lut.linearEnergy = l->linear_energy;
+    c->lut.invLinearStep = 1.0f / l->linear_step;
     c->lut.knots = c->dLutBlob + oKnots;
     c->lut.coeff = c->dLutBlob + oCoeff;
     c->lut.maxCoeff = c->dLutBlob + oMax;
