@@ -23,11 +23,10 @@ namespace {
     {
         c.elements.assign(Z, Z + n);
         c.numberFraction.resize(n);
-        double sum = 0;
-        for (int i = 0; i < n; ++i) {
+        for (int i = 0; i < n; ++i)
             c.numberFraction[i] = massFractions[i] / AtomicWeight(Z[i], nullptr);
-            sum += c.numberFraction[i];
-        }
+        // std::reduce, like the reference: its pairwise-by-four association decides the last bit of the sum
+        const double sum = std::reduce(c.numberFraction.cbegin(), c.numberFraction.cend());
         for (auto& f : c.numberFraction)
             f /= sum;
     }
@@ -166,22 +165,21 @@ std::vector<std::string> nistCompoundNames()
     return names;
 }
 
+// the two sums below go through the same library reductions the reference calls (with and without an execution
+// policy), so that the association order of the double additions — and with it the last bit — is the same
 double formFactorSquared(const Composition& c, double q)
 {
-    double sum = 0;
-    for (std::size_t i = 0; i < c.elements.size(); ++i) {
-        const double f = FF_Rayl(c.elements[i], q, nullptr);
-        sum += c.numberFraction[i] * f * f;
-    }
-    return sum;
+    return std::transform_reduce(std::execution::par_unseq, c.elements.cbegin(), c.elements.cend(), c.numberFraction.cbegin(), 0.0, std::plus<>(),
+        [=](const int Z, const double nf) {
+            const double f = FF_Rayl(Z, q, nullptr);
+            return nf * f * f;
+        });
 }
 
 double normalizedScatterFactor(const Composition& c, double q)
 {
-    double sum = 0;
-    for (std::size_t i = 0; i < c.elements.size(); ++i)
-        sum += c.numberFraction[i] * SF_Compt(c.elements[i], q, nullptr) / c.elements[i];
-    return sum;
+    return std::transform_reduce(c.elements.cbegin(), c.elements.cend(), c.numberFraction.cbegin(), 0.0, std::plus<>(),
+        [=](const int Z, const double nf) { return nf * SF_Compt(Z, q, nullptr) / Z; });
 }
 
 std::vector<double> bindingEnergies(const std::string& name, double minValue)

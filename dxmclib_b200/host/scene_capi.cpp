@@ -560,7 +560,50 @@ int dxs_source_exposure(dxs_scene* s, uint64_t i, dxs_exposure* out)
         for (int k = 0; k < 4; ++k)
             out->collimation[k] = e.collimationAngles()[k];
         out->weight = e.beamIntensityWeight();
+        out->mono_energy = e.monoenergeticPhotonEnergy();
+        out->has_spectrum = e.specterDistribution() != nullptr;
+        out->has_heel = e.heelFilter() != nullptr;
+        out->has_bowtie = e.beamFilter() != nullptr;
         out->histories = e.numberOfHistories();
+        return DXS_OK;
+    });
+}
+
+int dxs_source_table(dxs_scene* s, int what, float* out, uint64_t* count)
+{
+    if (!s || !s->source || what < 0 || what > 6)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        s->world->makeValid();
+        s->source->updateFromWorld(*s->world);
+        s->source->validate();
+        const auto e = s->source->getExposure(0);
+        std::vector<float> v;
+        if (what <= 2) {
+            if (const auto* sp = e.specterDistribution()) {
+                if (what == 0)
+                    v = sp->probabilityData();
+                else if (what == 1)
+                    v.assign(sp->aliasingData().begin(), sp->aliasingData().end());
+                else
+                    v = sp->energies();
+            }
+        } else if (what <= 4) {
+            if (const auto* h = e.heelFilter()) {
+                if (what == 3)
+                    v = { h->energyStart(), h->energyStep(), static_cast<float>(h->energySize()), h->angleStart(), h->angleStep(),
+                        static_cast<float>(h->angleSize()) };
+                else
+                    v = h->weights();
+            }
+        } else if (const auto* b = dynamic_cast<const BowTieFilter<float>*>(e.beamFilter())) {
+            for (const auto& [angle, weight] : b->data())
+                v.push_back(what == 5 ? angle : weight);
+        }
+        if (count)
+            *count = v.size();
+        if (out)
+            std::copy(v.begin(), v.end(), out);
         return DXS_OK;
     });
 }

@@ -52,7 +52,8 @@ class CTParams(C.Structure):
 
 class Exposure(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("cosines", C.c_float * 6), ("beam_direction", C.c_float * 3),
-                ("collimation", C.c_float * 4), ("weight", C.c_float), ("histories", C.c_uint64)]
+                ("collimation", C.c_float * 4), ("weight", C.c_float), ("mono_energy", C.c_float), ("has_spectrum", C.c_int32),
+                ("has_heel", C.c_int32), ("has_bowtie", C.c_int32), ("histories", C.c_uint64)]
 
 
 class ResultInfo(C.Structure):
@@ -69,7 +70,7 @@ SCENE_SYMBOLS = [
     "dxs_lut_max_inverse", "dxs_lut_scatter_factor", "dxs_lut_sample_form_factor", "dxs_lut_table",
     "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
-    "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport",
+    "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport",
     "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
 ]
 
@@ -364,7 +365,16 @@ class Scene:
         return {"position": np.array(e.position[:], np.float32), "cosines": np.array(e.cosines[:], np.float32),
                 "beam_direction": np.array(e.beam_direction[:], np.float32),
                 "collimation": np.array(e.collimation[:], np.float32), "weight": np.float32(e.weight),
-                "histories": int(e.histories)}
+                "mono_energy": np.float32(e.mono_energy), "has_spectrum": bool(e.has_spectrum), "has_heel": bool(e.has_heel),
+                "has_bowtie": bool(e.has_bowtie), "histories": int(e.histories)}
+
+    def source_table(self, what) -> np.ndarray:
+        n = C.c_uint64(0)
+        _chk(self.lib.dxs_source_table(self.h, int(what), None, C.byref(n)), "dxs_source_table")
+        out = np.zeros(n.value, np.float32)
+        if n.value:
+            _chk(self.lib.dxs_source_table(self.h, int(what), out.ctypes.data_as(_f32p), C.byref(n)), "dxs_source_table")
+        return out
 
     def spectrum(self):
         n = C.c_int(0)

@@ -157,9 +157,19 @@ typedef struct dxs_exposure {
     float beam_direction[3];
     float collimation[4];
     float weight;
+    float mono_energy;      /* m_monoenergeticPhotonEnergy */
+    int32_t has_spectrum;   /* m_specterDistribution != nullptr */
+    int32_t has_heel;       /* m_heelFilter != nullptr */
+    int32_t has_bowtie;     /* m_beamFilter != nullptr */
     uint64_t histories;
 } dxs_exposure;
 int dxs_source_exposure(dxs_scene*, uint64_t i, dxs_exposure* out);
+/* The sampling tables exposure 0 points to, for bit-exact comparison and for building dxmcb200_* inputs by hand.
+ * what: 0 spectrum m_probs, 1 spectrum m_alias (as floats), 2 spectrum m_energies   (dxmcrandom.hpp:277-329)
+ *       3 heel {energyStart, energyStep, energySize, angleStart, angleStep, angleSize}, 4 heel m_weights (beamfilters.hpp:438-448)
+ *       5 bow-tie |angle|, 6 bow-tie normalised weight                                 (beamfilters.hpp:80, 199)
+ * A missing table has count 0. out==NULL returns the count only. */
+int dxs_source_table(dxs_scene*, int what, float* out, uint64_t* count);
 /* the source's normalised spectrum after validate() (tube model or user spectrum); NULL out for count */
 int dxs_source_spectrum(dxs_scene*, float* energies, float* weights, int* count);
 /* Source::getCalibrationValue(model) */

@@ -1,0 +1,229 @@
+"""Shared helpers of the test suite: scene builders (the same calls go to the product and to the reference
+library), flattening of a scene into the plain-data inputs of include/dxmcb200.h, and statistics helpers."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from dxmclib_b200 import cabi  # noqa: E402
+from dxmclib_b200 import scene as S  # noqa: E402
+
+SEED = 20261017
+
+# TG-195 style tissue formulas the reference's validation uses (validation/validation.cpp:320-322, 1321-1340)
+AIR = "C0.0150228136551869N78.439632744437O21.0780510531616Ar0.467293388746132"
+SOFT = "H62.9539171935344C12.9077870263354N1.16702581276482O22.7840718642933Na0.026328553360443P0.0390933975009805S0.0566470278101205Cl0.0341543557411274K0.0309747686593447"
+BONE = "H39.229963C15.009010N3.487490O31.621690Na0.050590Mg0.095705P3.867606S0.108832Ca6.529115"
+THYROID = "H63.845575C6.130922N1.060311O28.814466Na0.053834P0.019979S0.019302Cl0.034909K0.015827I0.004876"
+
+# a 120 kVp-like spectrum (bin lower edges keV, relative weights) for IsotropicSource::setSpecter
+SPECTRUM_E = np.arange(15.0, 121.0, 5.0, dtype=np.float32)
+SPECTRUM_W = np.array([0.2, 1.5, 4.5, 7.8, 10.0, 11.2, 11.4, 10.9, 14.5, 12.8, 8.2, 7.0, 5.9, 4.9, 4.0, 3.2, 2.4, 1.7, 1.0, 0.5, 0.2, 0.05],
+                      dtype=np.float32)
+
+
+def have_reference() -> bool:
+    return os.path.exists(S.REFERENCE_LIB)
+
+
+def have_gpu() -> bool:
+    try:
+        return cabi.device_count() > 0
+    except Exception:
+        return False
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scenes
+# ---------------------------------------------------------------------------------------------------------
+def layered_box(lib, n=32):
+    """The reference example's geometry (examples/pencilbeam/pencilbeam.cpp:21-58): air / water / aluminium thirds."""
+    sc = S.Scene(lib)
+    sc.world((n, n, n), (1, 1, 1))
+    sc.add_material("Air, Dry (near sea level)").add_material("Water, Liquid").add_element(13)
+    d = [sc.material_density(i) for i in range(3)]
+    mat = np.zeros((n, n, n), np.uint8)
+    mat[n // 3: 2 * n // 3] = 1
+    mat[2 * n // 3:] = 2
+    sc.arrays(np.array(d, np.float32)[mat], mat)
+    assert sc.validate()
+    return sc
+
+
+def pencil_scene(lib, n=32, histories=20000, exposures=4, energy=60.0):
+    sc = layered_box(lib, n)
+    sc.source_pencil((0.3, 0.2, -float(n)), (1, 0, 0, 0, 1, 0), energy, histories, exposures)
+    return sc
+
+
+def tissue_block(lib, dim=(24, 20, 28), spacing=(4.0, 5.0, 3.0), origin=(3.0, -2.0, 10.0), forced=False, cosines=(1, 0, 0, 0, 1, 0)):
+    """Soft tissue block with a bone insert, an iodine-loaded insert and varying density; anisotropic voxels,
+    off-centre origin. With forced=True a slab of voxels is flagged in the measurement map."""
+    sc = S.Scene(lib)
+    sc.world(dim, spacing, origin, cosines)
+    sc.add_material(AIR, 0.001205).add_material(SOFT, 1.03).add_material(BONE, 1.92).add_material(THYROID, 1.05)
+    nx, ny, nz = dim
+    mat = np.ones((nz, ny, nx), np.uint8)
+    mat[:2] = 0
+    mat[nz // 3: nz // 2, ny // 4: ny // 2, nx // 4: nx // 2] = 2
+    mat[nz // 2: 3 * nz // 4, ny // 2: 3 * ny // 4, nx // 2: 3 * nx // 4] = 3
+    dens = np.array([0.001205, 1.03, 1.92, 1.05], np.float32)[mat]
+    zz = np.arange(nz, dtype=np.float32)[:, None, None]
+    dens = (dens * (1.0 + 0.1 * np.sin(zz / 3.0))).astype(np.float32)  # smoothly varying density
+    meas = None
+    if forced:
+        meas = np.zeros((nz, ny, nx), np.uint8)
+        meas[nz // 2 - 2: nz // 2 + 2, :, nx // 3: 2 * nx // 3] = 1
+    sc.arrays(dens, mat, meas)
+    assert sc.validate()
+    return sc
+
+
+def isotropic_scene(lib, histories=20000, exposures=3, forced=False, ct=False, mono=None):
+    sc = tissue_block(lib, forced=forced)
+    if mono is not None:
+        w, e = np.array([1.0], np.float32), np.array([mono], np.float32)
+    else:
+        w, e = SPECTRUM_W, SPECTRUM_E
+    sc.source_isotropic((2.0, 1.0, -300.0) if not ct else (0.0, -300.0, 10.0), (1, 0, 0, 0, 1, 0) if not ct else (1, 0, 0, 0, 0, 1),
+                        (-0.12, 0.14, -0.10, 0.11), w, e, histories, exposures, ct=ct)
+    return sc
+
+
+def ct_scene(lib, spiral=True, histories=5000, aec=True, xcare=True, tilt=5.0, dim=(40, 40, 30), spacing=(10.0, 10.0, 8.0)):
+    """Small CT configuration exercising tube spectrum, heel effect, bow-tie, AEC, XCare and gantry tilt."""
+    from dxmclib_b200 import phantoms
+
+    sc = S.Scene(lib)
+    sc.world(dim, spacing)
+    for name, dens in phantoms.ANTHROPOMORPHIC_MATERIALS:
+        sc.add_material(name, dens)
+    mat, dens = phantoms.anthropomorphic(dim, spacing)
+    sc.arrays(dens, mat)
+    assert sc.validate()
+    scan = dim[2] * spacing[2]
+    sc.source_ct(spiral=spiral, voltage=110.0, al_mm=6.0, cu_mm=0.1, sdd=1100.0, collimation=38.4, fov=480.0, pitch=0.9, step=38.4,
+                 scan_length=scan, position=(2.0, -3.0, -scan / 2 if spiral else -scan / 2 + 19.2), exposure_step_deg=12.0,
+                 start_angle_deg=20.0, gantry_tilt_deg=tilt, histories=histories, model_heel=True, ctdi_vol=12.0, use_xcare=xcare,
+                 xcare_filter_angle_deg=180.0, xcare_span_deg=110.0, xcare_ramp_deg=15.0, xcare_low_weight=0.55)
+    a, w = phantoms.bowtie_profile()
+    sc.source_bowtie(a, w)
+    if aec:
+        z = np.arange(dim[2], dtype=np.float32)
+        sc.source_aec(1.0 + 0.5 * np.sin(2 * np.pi * z / dim[2]))
+    return sc
+
+
+def ctdi_scene(lib, histories=4000, diameter=160):
+    sc = S.Scene(lib)
+    sc.ctdi_phantom(diameter)
+    sc.source_ct(spiral=False, voltage=120.0, al_mm=7.0, collimation=40.0, scan_length=40.0, position=(0, 0, 0), exposure_step_deg=10.0,
+                 histories=histories, model_heel=True, ctdi_phantom_diameter=diameter)
+    return sc
+
+
+# ---------------------------------------------------------------------------------------------------------
+# scene -> plain data (include/dxmcb200.h layout)
+# ---------------------------------------------------------------------------------------------------------
+def flatten_scene(sc: S.Scene, max_energy=None) -> dict:
+    """Everything dxmcb200_set_world / set_luts / set_beam_tables / run need, read back through the scene API
+    (works for the product and for the reference library)."""
+    dim, spacing, ext = sc.dimensions()
+    dens, mat, meas = sc.get_arrays()
+    sc.lut_generate(float(max_energy if max_energy is not None else sc.max_energy()))
+    knots, coeff, maxc, lin, rita, spl = (sc.lut_table(i) for i in range(6))
+    n_seg = knots.size
+    n_mat = coeff.size // (n_seg * 6)
+    raw = spl.reshape(n_mat, 79)  # 60 coefficients, 16 knots, step, start, stop
+    spline = np.zeros((n_mat, 63), np.float32)
+    spline[:, :60] = raw[:, :60]
+    spline[:, 60], spline[:, 61], spline[:, 62] = raw[:, 77], raw[:, 76], raw[:, 78]
+    shells = np.stack([sc.material_shells(i)[:, :11].astype(np.float32) for i in range(n_mat)])
+    flat = {
+        "dim": dim, "spacing": spacing, "extent_safe": ext, "density": dens, "material": mat,
+        "measurement": meas if meas.any() else None,
+        "luts": {"n_materials": n_mat, "n_segments": n_seg, "linear_index": int(lin[0]), "linear_step": float(lin[1]),
+                 "linear_energy": float(lin[2]), "knots": knots, "coefficients": coeff, "max_coefficients": maxc, "rita": rita,
+                 "spline": np.ascontiguousarray(spline), "shells": np.ascontiguousarray(shells)},
+        "spectra": [], "heels": [], "bowties": [],
+    }
+    t = [sc.source_table(i) for i in range(7)]
+    if t[0].size:
+        flat["spectra"].append((t[0], t[1].astype(np.uint32), t[2]))
+    if t[3].size:
+        d = t[3]
+        flat["heels"].append((float(d[0]), float(d[1]), int(d[2]), float(d[3]), float(d[4]), int(d[5]), t[4]))
+    if t[5].size:
+        flat["bowties"].append((t[5], t[6]))
+    return flat
+
+
+def exposures_of(sc: S.Scene, n=None):
+    out = []
+    total = sc.total_exposures()
+    for i in range(total if n is None else min(n, total)):
+        e = sc.exposure(i)
+        x = cabi.Exposure()
+        x.position[:] = e["position"].tolist()
+        x.cosines[:] = e["cosines"].tolist()
+        x.beam_direction[:] = e["beam_direction"].tolist()
+        x.collimation[:] = e["collimation"].tolist()
+        x.weight = float(e["weight"])
+        x.mono_energy = float(e["mono_energy"])
+        x.spectrum = 0 if e["has_spectrum"] else -1
+        x.heel = 0 if e["has_heel"] else -1
+        x.bowtie = 0 if e["has_bowtie"] else -1
+        x.histories = e["histories"]
+        out.append(x)
+    return out
+
+
+def load_context(ctx: cabi.Context, flat: dict):
+    """Upload a flattened scene into a dxmcb200_ctx through the C ABI."""
+    import ctypes as C
+
+    f32p = C.POINTER(C.c_float)
+    ctx.set_world(flat["dim"], flat["spacing"], flat["extent_safe"], flat["density"], flat["material"], flat["measurement"])
+    lt = flat["luts"]
+    l = cabi.Luts()
+    l.n_materials, l.n_segments, l.linear_index = lt["n_materials"], lt["n_segments"], lt["linear_index"]
+    l.linear_step, l.linear_energy = lt["linear_step"], lt["linear_energy"]
+    for k in ("knots", "coefficients", "max_coefficients", "rita", "spline", "shells"):
+        setattr(l, k, lt[k].ctypes.data_as(f32p))
+    ctx._chk(ctx.l.dxmcb200_set_luts(ctx.h, C.byref(l)), "dxmcb200_set_luts")
+    ctx.n_materials = lt["n_materials"]
+    ctx.set_beam_tables(flat["spectra"], flat["heels"], flat["bowties"])
+    ctx._flat = flat
+
+
+# ---------------------------------------------------------------------------------------------------------
+# statistics
+# ---------------------------------------------------------------------------------------------------------
+def bit_equal(a: np.ndarray, b: np.ndarray) -> bool:
+    a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+    return a.shape == b.shape and a.dtype == b.dtype and a.tobytes() == b.tobytes()
+
+
+def dose_sigma(sum_e, sum_e2, n_events):
+    """Standard deviation of a voxel's summed energy from the per-event second moment: var(sum) ~ sum(e^2) (Poisson-like
+    event counts), the estimator the reference's variance array feeds."""
+    return np.sqrt(np.maximum(sum_e2, 0.0))
+
+
+def compare_dose(a_sum, a_sum2, b_sum, b_sum2, rel_err_limit=0.02, n_sigma=3.0):
+    """north_star criterion: per-voxel agreement within n_sigma of the combined Monte Carlo uncertainty in all voxels whose
+    relative error is under rel_err_limit. Returns (fraction outside, number tested, worst z)."""
+    sa, sb = dose_sigma(a_sum, a_sum2, None), dose_sigma(b_sum, b_sum2, None)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        rel = np.where(b_sum > 0, sb / b_sum, np.inf)
+    sel = rel < rel_err_limit
+    if not sel.any():
+        return 0.0, 0, 0.0
+    z = np.abs(a_sum[sel] - b_sum[sel]) / np.sqrt(sa[sel] ** 2 + sb[sel] ** 2)
+    return float((z > n_sigma).mean()), int(sel.sum()), float(z.max())
