@@ -186,6 +186,36 @@ int dxs_world_ctdi_holes(dxs_scene* s, int position, uint64_t* out, uint64_t* co
     return DXS_OK;
 }
 
+int dxs_trace_indices(dxs_scene* s, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps, int64_t* outIdx,
+    float* outEntry)
+{
+    if (!s || !pos || !dir || !outIdx || !outEntry || (nSteps && !steps))
+        return DXS_ERR_ARG;
+    return guarded([&] {
+        s->world->makeValid();
+        const World<float>& w = *s->world;
+        if (!w.isValid())
+            return static_cast<int>(DXS_ERR_STATE);
+        dxmcb200_ctx* raw = nullptr;
+        if (dxmcb200_create(dxmc::detail::currentDevice(), &raw) != DXMCB200_OK)
+            throw std::runtime_error("dxmcb200: no usable CUDA device; this library has no CPU fallback");
+        dxmc::detail::ContextPtr ctx(raw);
+        dxmcb200_world dw {};
+        for (int i = 0; i < 3; ++i) {
+            dw.dim[i] = w.dimensions()[i];
+            dw.spacing[i] = w.spacing()[i];
+        }
+        for (int i = 0; i < 6; ++i)
+            dw.extent_safe[i] = w.matrixExtentSafe()[i];
+        dw.density = w.densityArray()->data();
+        dw.material = w.materialIndexArray()->data();
+        dw.measurement = w.measurementMapArray() ? w.measurementMapArray()->data() : nullptr;
+        dxmc::detail::check(ctx.get(), dxmcb200_set_world(ctx.get(), &dw), "set_world");
+        dxmc::detail::check(ctx.get(), dxmcb200_trace_indices(ctx.get(), nRays, pos, dir, nSteps, steps, outIdx, outEntry), "trace_indices");
+        return static_cast<int>(DXS_OK);
+    });
+}
+
 static const Material* materialAt(dxs_scene* s, int idx)
 {
     if (!s || idx < 0 || static_cast<std::size_t>(idx) >= s->world->materialMap().size())

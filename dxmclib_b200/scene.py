@@ -64,7 +64,7 @@ class ResultInfo(C.Structure):
 SCENE_SYMBOLS = [
     "dxs_backend", "dxs_last_error", "dxs_create", "dxs_destroy", "dxs_world_geometry", "dxs_world_add_material",
     "dxs_world_add_element", "dxs_world_arrays", "dxs_world_ctdi_phantom", "dxs_world_validate",
-    "dxs_world_dimensions", "dxs_world_get_arrays", "dxs_world_ctdi_holes", "dxs_material_attenuation",
+    "dxs_world_dimensions", "dxs_world_get_arrays", "dxs_world_ctdi_holes", "dxs_trace_indices", "dxs_material_attenuation",
     "dxs_material_form_factor_sq", "dxs_material_scatter_factor", "dxs_material_binding_energies",
     "dxs_material_shells", "dxs_material_density", "dxs_lut_generate", "dxs_lut_attenuation",
     "dxs_lut_max_inverse", "dxs_lut_scatter_factor", "dxs_lut_sample_form_factor", "dxs_lut_table",
@@ -219,6 +219,18 @@ class Scene:
         out = np.zeros(cnt.value, np.uint64)
         _chk(self.lib.dxs_world_ctdi_holes(self.h, position, out.ctypes.data_as(_u64p), C.byref(cnt)), "dxs_world_ctdi_holes")
         return out
+
+    def trace_indices(self, pos, direction, steps):
+        """Voxel-index sequences of fixed rays (see dxs_trace_indices); returns (indices [n, n_steps+1], entry [n, 3])."""
+        p = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(-1, 3)
+        s = np.ascontiguousarray(steps, np.float32)
+        idx = np.zeros((p.shape[0], s.size + 1), np.int64)
+        entry = np.zeros((p.shape[0], 3), np.float32)
+        _chk(self.lib.dxs_trace_indices(self.h, C.c_uint64(p.shape[0]), p.ctypes.data_as(_f32p), d.ctypes.data_as(_f32p), int(s.size),
+                                        s.ctypes.data_as(_f32p), idx.ctypes.data_as(C.POINTER(C.c_int64)), entry.ctypes.data_as(_f32p)),
+             "dxs_trace_indices")
+        return idx, entry
 
     # ---- material
     def material_attenuation(self, idx, energy):

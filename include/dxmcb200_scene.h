@@ -67,6 +67,13 @@ int dxs_world_get_arrays(dxs_scene*, float* density, uint8_t* material, uint8_t*
 /* CTDIPhantom::holeIndices(pos) pos: 0 centre,1 west,2 east,3 south,4 north; call with out==NULL for the count */
 int dxs_world_ctdi_holes(dxs_scene*, int position, uint64_t* out, uint64_t* count);
 
+/* Voxel-index sequence of fixed rays through the world: transportParticleToWorld, then pos += dir*step[k] with
+ * particleInsideWorld / indexFromPosition after every step (reference transport.hpp:485-521, 702-728). out_indices is
+ * [n_rays][n_steps+1] (slot 0 = voxel of the entry point, -1 = outside), out_entry [n_rays][3]. The reference harness
+ * calls the reference's own members; the product evaluates the CUDA device functions (needs a GPU). */
+int dxs_trace_indices(dxs_scene*, uint64_t n_rays, const float* pos, const float* dir, uint32_t n_steps, const float* steps,
+    int64_t* out_indices, float* out_entry);
+
 /* ---- Material (reference material.hpp:62-104) evaluated for world material `idx` ----- */
 int dxs_material_attenuation(dxs_scene*, int idx, double energy, double out_photo_compton_rayleigh_total[4]);
 int dxs_material_form_factor_sq(dxs_scene*, int idx, double q, double* out);

@@ -256,6 +256,37 @@ int dxs_world_ctdi_holes(dxs_scene* s, int position, uint64_t* out, uint64_t* co
     return DXS_OK;
 }
 
+int dxs_trace_indices(dxs_scene* s, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps, int64_t* outIdx,
+    float* outEntry)
+{
+    if (!s || !pos || !dir || !outIdx || !outEntry || (nSteps && !steps))
+        return DXS_ERR_ARG;
+    return guarded([&] {
+        s->world->makeValid();
+        const World<float>& w = *s->world;
+        if (!w.isValid())
+            return static_cast<int>(DXS_ERR_STATE);
+        Transport<float> tr; // only its geometry members are used
+        for (uint64_t r = 0; r < nRays; ++r) {
+            Particle<float> p { { pos[3 * r], pos[3 * r + 1], pos[3 * r + 2] }, { dir[3 * r], dir[3 * r + 1], dir[3 * r + 2] }, 1.0f, 1.0f };
+            bool in = tr.transportParticleToWorld(w, p);
+            for (int k = 0; k < 3; ++k)
+                outEntry[3 * r + k] = p.pos[k];
+            int64_t* out = outIdx + r * (nSteps + 1);
+            out[0] = (in && tr.particleInsideWorld(w, p)) ? static_cast<int64_t>(tr.indexFromPosition(p, w)) : -1;
+            for (uint32_t k = 0; k < nSteps; ++k) {
+                if (in) {
+                    for (std::size_t i = 0; i < 3; i++)
+                        p.pos[i] += p.dir[i] * steps[k];
+                    in = tr.particleInsideWorld(w, p);
+                }
+                out[k + 1] = in ? static_cast<int64_t>(tr.indexFromPosition(p, w)) : -1;
+            }
+        }
+        return static_cast<int>(DXS_OK);
+    });
+}
+
 static const Material* materialAt(dxs_scene* s, int idx)
 {
     if (!s || idx < 0 || static_cast<std::size_t>(idx) >= s->world->materialMap().size())

@@ -91,7 +91,7 @@ def isotropic_scene(lib, histories=20000, exposures=3, forced=False, ct=False, m
         w, e = np.array([1.0], np.float32), np.array([mono], np.float32)
     else:
         w, e = SPECTRUM_W, SPECTRUM_E
-    sc.source_isotropic((2.0, 1.0, -300.0) if not ct else (0.0, -300.0, 10.0), (1, 0, 0, 0, 1, 0) if not ct else (1, 0, 0, 0, 0, 1),
+    sc.source_isotropic((2.0, 1.0, -300.0) if not ct else (0.0, -300.0, 10.0), (1, 0, 0, 0, 1, 0) if not ct else (-1, 0, 0, 0, 0, 1),
                         (-0.12, 0.14, -0.10, 0.11), w, e, histories, exposures, ct=ct)
     return sc
 
@@ -153,7 +153,10 @@ def flatten_scene(sc: S.Scene, max_energy=None) -> dict:
                  "spline": np.ascontiguousarray(spline), "shells": np.ascontiguousarray(shells)},
         "spectra": [], "heels": [], "bowties": [],
     }
-    t = [sc.source_table(i) for i in range(7)]
+    try:
+        t = [sc.source_table(i) for i in range(7)]
+    except S.SceneError:  # scene without a source: world + LUTs only
+        t = [np.zeros(0, np.float32)] * 7
     if t[0].size:
         flat["spectra"].append((t[0], t[1].astype(np.uint32), t[2]))
     if t[3].size:

@@ -1,0 +1,45 @@
+"""BASELINE config #4 at full grid size (512x512x400, 3600 exposures) with a reduced history count: properties that do
+not need an oracle run — determinism, shard-sum identity, energy bookkeeping."""
+import numpy as np
+import pytest
+
+import support as T
+from dxmclib_b200 import cabi, phantoms
+from dxmclib_b200 import scene as S
+
+pytestmark = pytest.mark.gpu
+
+
+def test_full_size_ct_spiral_properties(gpu, product):
+    import bench
+
+    phantom = phantoms.anthropomorphic(bench.DIM, bench.SPACING)
+    hist = 3000
+    sc = bench.build_scene(product, hist, phantom=phantom)
+    assert sc.total_exposures() == 3600
+    total = 3600 * hist
+    sc.b200_prepare(device=0, model=S.MODEL_LIVERMORE, seed=bench.SEED, total_histories_all_ranks=total)
+    ctx = cabi.Context(handle=sc.b200_context())
+    ctx.n_voxels = int(np.prod(bench.DIM))
+    ctx.enable_stats(True)
+    sc.b200_run(0, 3600)
+    st = ctx.stats()
+    whole = ctx.get_raw()
+    assert st["histories"] == total
+    assert 10 < st["lookups"] / total < 40 and 0.3 < st["score_events"] / total < 3
+    # second run, split into three launches' worth of exposure blocks, must reproduce the grids bit for bit
+    ctx.clear()
+    for b, e in ((0, 1000), (1000, 1001), (1001, 3600)):
+        sc.b200_run(b, e)
+    again = ctx.get_raw()
+    for x, y in zip(whole, again):
+        assert T.bit_equal(x, y)
+    # energy bookkeeping: nothing is scored outside the body+table, and less energy is deposited than emitted
+    mat = phantom[0]
+    energy_kev = whole[0].astype(np.float64) / 2.0 ** 0  # fixed point, decode below
+    r = sc.b200_collect(output=S.OUT_EV_PER_HISTORY, histories=total)
+    assert r.dose[mat == 0].sum() < 0.02 * r.dose.sum()  # air absorbs next to nothing
+    assert 0 < r.dose.astype(np.float64).sum() < 120e3  # eV per history, below the 120 kV end point
+    assert int(r.n_events.sum()) == int(whole[2].sum()) == st["score_events"]
+    assert energy_kev.any()
+    sc.b200_release()

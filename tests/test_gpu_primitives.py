@@ -1,0 +1,123 @@
+"""CUDA device primitives through the C ABI (include/dxmcb200.h) against the restatement oracle and the committed
+reference vectors: LUT evaluation (a9/a10), voxel-index traversal (a5-a7), photon birth (a4), interaction sampling
+(a13-a16). Integer/index results must be bit-exact; floating point within the tolerance stated per test."""
+import os
+
+import numpy as np
+import pytest
+
+import support as T
+from dxmclib_b200 import cabi
+from dxmclib_b200 import scene as S
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(T.ROOT, "tests", "golden")
+
+WORLDS = {"unit": dict(dim=(64, 48, 40), spacing=(1.0, 1.0, 1.0), origin=(0.0, 0.0, 0.0)),
+          "aniso": dict(dim=(37, 51, 29), spacing=(0.7, 1.3, 2.5), origin=(12.5, -7.25, 100.0)),
+          "fine": dict(dim=(200, 10, 10), spacing=(0.1, 3.0, 3.0), origin=(-3.0, 0.5, 0.25))}
+
+
+def _ctx_and_oracle(sc, max_energy=None):
+    flat = T.flatten_scene(sc, max_energy)
+    ctx = cabi.Context(0)
+    T.load_context(ctx, flat)
+    o = pyoracle.Oracle()
+    o.load(flat)
+    return ctx, o, flat
+
+
+def test_lut_interpolation_1e6(gpu, product):
+    """north_star: LUT interpolation matches to 1e-6 relative."""
+    g = np.load(os.path.join(G, "lut.npz"))
+    sc = T.tissue_block(product)
+    ctx, o, _ = _ctx_and_oracle(sc, 140.0)
+    rng = np.random.default_rng(5)
+    e = np.concatenate([g["energy"], rng.uniform(1.0, 140.0, 20000).astype(np.float32)])
+    m = rng.integers(0, 4, e.size).astype(np.uint8)
+    att, mx = ctx.eval_attenuation(m, e)
+    ratt, rmx = o.eval_attenuation(m, e)
+    assert np.max(np.abs(att - ratt) / ratt) < 1e-6
+    assert np.max(np.abs(mx - rmx) / rmx) < 1e-6
+    for k in range(4):  # committed reference values
+        a, x = ctx.eval_attenuation(np.full(g["energy"].size, k, np.uint8), g["energy"])
+        assert np.max(np.abs(a - g["attenuation"][k]) / g["attenuation"][k]) < 1e-6
+        assert np.max(np.abs(x - g["max_inverse"]) / g["max_inverse"]) < 1e-6
+
+
+@pytest.mark.parametrize("world", list(WORLDS))
+def test_voxel_index_sequences_bit_exact(gpu, product, world):
+    """north_star: voxel-index sequences for fixed deterministic rays are bit-exact against the reference traversal."""
+    g = np.load(os.path.join(G, "traces.npz"))
+    w = WORLDS[world]
+    sc = S.Scene(product)
+    sc.world(w["dim"], w["spacing"], w["origin"])
+    sc.add_material("Water, Liquid")
+    n = int(np.prod(w["dim"]))
+    sc.arrays(np.ones(n, np.float32), np.zeros(n, np.uint8))
+    assert sc.validate()
+    idx, entry = sc.trace_indices(g[f"{world}_pos"], g[f"{world}_dir"], g[f"{world}_steps"])  # product scene API -> CUDA
+    assert np.array_equal(idx, g[f"{world}_idx"])
+    assert T.bit_equal(entry, g[f"{world}_entry"])
+
+
+def test_voxel_index_random_stress_vs_oracle(gpu, product):
+    """A million positions on and near voxel boundaries, odd spacings: the division-free index must equal
+    trunc(fl((x - x0) / s)) everywhere."""
+    rng = np.random.default_rng(17)
+    for spacing in [(1.0, 1.0, 1.0), (0.3, 0.7, 1.1), (0.9765625, 0.9765625, 5.0), (3.0, 0.1, 2.5)]:
+        dim = (61, 47, 33)
+        sc = S.Scene(product)
+        sc.world(dim, spacing, (0.37, -1.9, 11.0))
+        sc.add_material("Water, Liquid")
+        n = int(np.prod(dim))
+        sc.arrays(np.ones(n, np.float32), np.zeros(n, np.uint8))
+        assert sc.validate()
+        ctx, o, flat = _ctx_and_oracle(sc, 60.0)
+        ext = flat["extent_safe"].astype(np.float64)
+        nr = 200000
+        # positions that sit within a few ulp of voxel boundaries
+        k = rng.integers(0, np.array(dim), (nr, 3))
+        pos = np.stack([ext[0] + k[:, 0] * spacing[0], ext[2] + k[:, 1] * spacing[1], ext[4] + k[:, 2] * spacing[2]], 1).astype(np.float32)
+        pos = np.nextafter(pos, pos + rng.choice([-1.0, 1.0], pos.shape).astype(np.float32) * rng.integers(0, 3, pos.shape)).astype(np.float32)
+        d = np.tile(np.array([[0.0, 0.0, 1.0]], np.float32), (nr, 1))
+        steps = np.array([0.0], np.float32)
+        gi, ge = ctx.trace_indices(pos, d, steps)
+        oi, oe = o.trace_indices(pos, d, steps)
+        assert np.array_equal(gi, oi)
+        assert T.bit_equal(ge, oe)
+
+
+@pytest.mark.parametrize("scene", ["pencil", "isotropic", "ct"])
+def test_photon_birth(gpu, product, scene):
+    """Exposure::sampleParticle: alias-table energies and filter weights identical, directions to sincos rounding."""
+    sc = {"pencil": lambda: T.pencil_scene(product), "isotropic": lambda: T.isotropic_scene(product),
+          "ct": lambda: T.ct_scene(product)}[scene]()
+    ctx, o, _ = _ctx_and_oracle(sc)
+    exps = T.exposures_of(sc, 3)
+    for i, e in enumerate(exps):
+        a = ctx.sample_particles(e, i, T.SEED, 20000)
+        b = o.sample_particles(e, i, T.SEED, 20000)
+        assert T.bit_equal(a[:, :3], b[:, :3])  # position
+        np.testing.assert_allclose(a[:, 3:6], b[:, 3:6], atol=3e-7)  # direction
+        assert T.bit_equal(a[:, 6], b[:, 6])  # energy: same alias draws
+        np.testing.assert_allclose(a[:, 7], b[:, 7], rtol=1e-6)  # weight (bow-tie x heel interpolation)
+
+
+@pytest.mark.parametrize("model", [0, 1, 2])
+@pytest.mark.parametrize("kind", [0, 1, 2])
+@pytest.mark.parametrize("energy", [15.0, 60.0, 120.0])
+def test_interaction_sampling(gpu, product, kind, model, energy):
+    """photo / Compton / Rayleigh sampling: same random streams as the oracle, so almost every history agrees to float
+    rounding; the few that flip a rejection decision are bounded, and the moments agree."""
+    sc = T.tissue_block(product)
+    ctx, o, _ = _ctx_and_oracle(sc, 140.0)
+    n = 40000
+    for material in (1, 2, 3):
+        a = ctx.sample_interaction(kind, model, material, energy, 77, n)
+        b = o.sample_interaction(kind, model, material, energy, 77, n)
+        close = np.all(np.abs(a - b) <= 2e-4 * np.maximum(1.0, np.abs(b)), axis=1)
+        assert close.mean() > 0.995, f"only {close.mean():.4f} of histories agree"
+        np.testing.assert_allclose(a[:, 0].mean(), b[:, 0].mean(), rtol=2e-3, atol=1e-3)  # mean energy imparted
+        np.testing.assert_allclose(a[:, 4].mean(), b[:, 4].mean(), atol=5e-3)  # mean cos(theta)

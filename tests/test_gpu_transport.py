@@ -1,0 +1,198 @@
+"""Transport parity on the GPU: the product (CUDA kernels behind Transport::operator()) against the unmodified
+reference, the restatement oracle and the committed reference vectors. Criteria of BASELINE.json north_star:
+total deposited energy within 0.5 %; per-voxel dose within 3 sigma of the combined Monte Carlo uncertainty in all
+voxels with under 2 % relative error. Because both sides consume the same per-history random streams the actual
+agreement is far tighter, which the tests also assert (event grids nearly identical)."""
+import os
+
+import numpy as np
+import pytest
+
+import support as T
+from dxmclib_b200 import cabi
+from dxmclib_b200 import scene as S
+from oracle import pyoracle
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(T.ROOT, "tests", "golden")
+
+SCENES = {
+    "pencil": lambda lib: T.pencil_scene(lib, histories=40000, exposures=4),
+    "isotropic_forced": lambda lib: T.isotropic_scene(lib, histories=30000, forced=True),
+    "ct_spiral": lambda lib: T.ct_scene(lib, histories=1500),
+}
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+@pytest.mark.parametrize("model", [0, 1, 2])
+def test_against_committed_reference_streams(gpu, product, name, model):
+    g = np.load(os.path.join(G, f"streams_{name}_m{model}.npz"))
+    sc = SCENES[name](product)
+    r = sc.transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
+    assert r.histories == int(g["histories"]) and r.units == "eV/history"
+    total = float(r.dose.astype(np.float64).sum())
+    assert abs(total - float(g["total"])) / float(g["total"]) < 5e-3  # north_star bound
+    assert abs(total - float(g["total"])) / float(g["total"]) < 2e-4  # what identical streams actually give
+    assert abs(int(r.n_events.sum()) - int(g["events"])) <= max(20, 2e-4 * int(g["events"]))
+    differing = (r.n_events != g["n_events"]).mean()
+    assert differing < 5e-3, f"{differing:.4%} of voxels differ in event count"
+    nx, ny, nz = sc.dim
+    d = r.dose.astype(np.float64).reshape(nz, ny, nx)
+    np.testing.assert_allclose(d.sum(axis=(1, 2)), g["profile_z"], rtol=5e-3, atol=2e-2 * g["profile_z"].max() / 100)
+
+
+@pytest.mark.parametrize("name,builder,model", [
+    ("pencil", lambda lib: T.pencil_scene(lib, n=48, histories=250000, exposures=8), 1),
+    ("isotropic_forced", lambda lib: T.isotropic_scene(lib, histories=250000, exposures=4, forced=True), 1),
+    ("isotropic_ia", lambda lib: T.isotropic_scene(lib, histories=150000, exposures=4), 2),
+    ("ct_spiral", lambda lib: T.ct_scene(lib, histories=20000), 1),
+    ("ct_axial_none", lambda lib: T.ct_scene(lib, spiral=False, histories=20000, xcare=False, tilt=0.0), 0),
+])
+def test_live_reference_three_sigma(gpu, product, reference, name, builder, model):
+    a = builder(product).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
+    b = builder(reference).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED, workers=S.WORKERS_COUNTER_STREAMS)
+    n = a.histories
+    assert n == b.histories
+    ta, tb = float(a.dose.astype(np.float64).sum()), float(b.dose.astype(np.float64).sum())
+    assert abs(ta - tb) / tb < 5e-3
+    # reconstruct sum(e) and sum(e^2) per voxel from normalizeScoring's outputs (eV/history; variance of the mean)
+    def sums(r):
+        d = r.dose.astype(np.float64) * n / 1e3
+        v = (r.variance.astype(np.float64) * (n - 1) + (r.dose.astype(np.float64)) ** 2) * n / 1e6
+        return d, v
+    da, va = sums(a)
+    db, vb = sums(b)
+    outside, tested, worst = T.compare_dose(da, va, db, vb)
+    assert tested > 50, "scene too sparse for the per-voxel criterion"
+    assert outside <= 0.003 and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
+
+
+def test_bit_reproducible_and_shard_invariant(gpu, product):
+    """Dose is bit-reproducible regardless of thread ordering, and any partition of the exposures over contexts
+    (= GPUs) sums to the identical grids."""
+    sc = T.isotropic_scene(product, histories=60000, exposures=6, forced=True)
+    flat = T.flatten_scene(sc)
+    exps = T.exposures_of(sc)
+
+    def run(ranges):
+        acc = None
+        for b, e in ranges:
+            ctx = cabi.Context(0)
+            T.load_context(ctx, flat)
+            ctx.set_fixed_point(20, 10)
+            ctx.run(exps, b, e, model=1, seed=42)
+            raw = ctx.get_raw()
+            acc = raw if acc is None else tuple(x + y for x, y in zip(acc, raw))
+            ctx.close()
+        return acc
+
+    whole, again = run([(0, 6)]), run([(0, 6)])
+    parts = run([(0, 1), (1, 4), (4, 6)])
+    assert whole[2].sum() > 100000
+    for x, y, z in zip(whole, again, parts):
+        assert T.bit_equal(x, y)
+        assert T.bit_equal(x, z)
+
+
+def test_fixed_point_grid_against_oracle(gpu, product):
+    """The raw 64-bit fixed-point grids against the restatement with the same streams and the same scales."""
+    sc = T.isotropic_scene(product, histories=30000, exposures=3)
+    flat = T.flatten_scene(sc)
+    exps = T.exposures_of(sc)
+    ctx = cabi.Context(0)
+    T.load_context(ctx, flat)
+    ctx.set_fixed_point(22, 12)
+    ctx.run(exps, 0, 3, model=1, seed=7)
+    e, e2, ev = ctx.get_raw()
+    o = pyoracle.Oracle()
+    o.load(flat)
+    o.set_fixed_point(22, 12)
+    o.run(exps, 0, 3, model=1, seed=7, per_history_streams=True)
+    oe, oe2 = o.get_fixed()
+    _, oev, _ = o.get_raw()
+    assert (ev.astype(np.int64) != oev.astype(np.int64)).mean() < 5e-3
+    same = ev.astype(np.int64) == oev.astype(np.int64)
+    # where the same events were scored, the sums agree to the rounding of single events (a few LSB per event)
+    assert np.all(np.abs(e[same] - oe[same]) <= 64 * np.maximum(ev[same], 1) * 2 ** 6)
+    np.testing.assert_allclose(e.sum() / 2.0 ** 22, oe.sum() / 2.0 ** 22, rtol=1e-5)
+    np.testing.assert_allclose(e2.astype(np.float64).sum(), oe2.astype(np.float64).sum(), rtol=1e-4)
+
+
+def test_uneven_histories_and_empty_exposures(gpu, product):
+    """Ragged exposures (different history counts, including zero) take the prefix-search path of the kernel."""
+    sc = T.isotropic_scene(product, histories=1000, exposures=5)
+    flat = T.flatten_scene(sc)
+    exps = T.exposures_of(sc)
+    for x, h in zip(exps, (3000, 0, 17, 12001, 1)):
+        x.histories = h
+    ctx = cabi.Context(0)
+    T.load_context(ctx, flat)
+    ctx.enable_stats(True)
+    ctx.run(exps, 0, 5, model=1, seed=3)
+    assert ctx.stats()["histories"] == 3000 + 17 + 12001 + 1
+    _, _, ev = ctx.get_raw()
+    o = pyoracle.Oracle()
+    o.load(flat)
+    o.run(exps, 0, 5, model=1, seed=3, per_history_streams=True)
+    _, oev, _ = o.get_raw()
+    assert abs(int(ev.sum()) - int(oev.sum())) <= 5
+    assert (ev.astype(np.int64) != oev.astype(np.int64)).mean() < 5e-3
+    ctx.clear()
+    ctx.run(exps, 2, 2, model=1, seed=3)  # empty range is a no-op
+    assert ctx.get_raw()[2].sum() == 0
+
+
+def test_work_counters_match_oracle(gpu, product):
+    """The L (look-ups) and S (scoring events) of the roofline model, counted by the kernel, equal the oracle's."""
+    sc = T.ct_scene(product, histories=3000)
+    flat = T.flatten_scene(sc)
+    exps = T.exposures_of(sc)
+    ctx = cabi.Context(0)
+    T.load_context(ctx, flat)
+    ctx.enable_stats(True)
+    ctx.run(exps, 0, len(exps), model=1, seed=11)
+    s = ctx.stats()
+    o = pyoracle.Oracle()
+    o.load(flat)
+    o.run(exps, 0, len(exps), model=1, seed=11, per_history_streams=True)
+    t = o.stats()
+    assert s["histories"] == t["histories"]
+    for k in ("histories_in_world", "steps", "lookups", "interactions", "score_events"):
+        assert abs(s[k] - t[k]) <= 2e-4 * t[k] + 5, (k, s[k], t[k])
+
+
+def test_output_modes(gpu, product):
+    """EV_PER_HISTORY (normalizeScoring) and DOSE (energyImpartedToDose) are the documented functions of the raw sums."""
+    sc = T.isotropic_scene(product, histories=20000, exposures=2)
+    ev_mode = sc.transport(model=1, output=S.OUT_EV_PER_HISTORY, seed=5)
+    dose_mode = sc.transport(model=1, output=S.OUT_DOSE, use_calibration=False, seed=5)
+    assert dose_mode.units == "keV/kg" and ev_mode.units == "eV/history"
+    dens, _, _ = sc.get_arrays()
+    _, spacing, _ = sc.dimensions()
+    n = ev_mode.histories
+    kev = ev_mode.dose.astype(np.float64) * n / 1e3
+    mass = dens.astype(np.float64) * (np.prod(spacing.astype(np.float64)) / 1000.0) * 1e-3
+    np.testing.assert_allclose(dose_mode.dose, kev / mass, rtol=2e-5)
+    assert T.bit_equal(ev_mode.n_events, dose_mode.n_events)
+    # calibrated dose of an isotropic source uses calibration value 1 and reports mGy
+    cal = sc.transport(model=1, output=S.OUT_DOSE, use_calibration=True, seed=5)
+    assert cal.units == "mGy" and T.bit_equal(cal.dose, dose_mode.dose)
+
+
+def test_invalid_inputs_give_zero_result(gpu, product):
+    """Invalid world -> all-zero Result with numberOfHistories == 0 (reference transport.hpp:142-151)."""
+    sc = S.Scene(product)
+    sc.world((4, 4, 4), (1, 1, 1))
+    sc.add_material("Water, Liquid")
+    sc.arrays(np.ones(64, np.float32), np.ones(64, np.uint8))  # index 1 has no material
+    sc.source_pencil((0, 0, -10), (1, 0, 0, 0, 1, 0), 50.0, 100, 2)
+    r = sc.transport()
+    assert r.histories == 0 and not r.dose.any() and not r.n_events.any()
+
+
+def test_ct_dose_calibration_second_pass(gpu, product, reference):
+    """DOSE mode of a CT source: getCalibrationValue runs a second Transport on a CTDIPhantom with forced
+    interactions (reference source.hpp:925-988). The factor is a Monte Carlo estimate on both sides."""
+    a = T.ct_scene(product, histories=200, aec=False, xcare=False, tilt=0.0).calibration(S.MODEL_LIVERMORE)
+    b = T.ct_scene(reference, histories=200, aec=False, xcare=False, tilt=0.0).calibration(S.MODEL_LIVERMORE)
+    assert a > 0 and abs(a - b) / b < 0.01, (a, b)
