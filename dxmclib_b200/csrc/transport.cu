@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
                         ++cHist;
                     if (transportToWorld(P.world, p)) {
                         state = STEP;
-                        logE = log10f(p.energy);
+                        logE = log10Rounded(p.energy);
                         maxAttInv = maxAttenuationInverse(P.lut, logE);
                         if constexpr (kStats)
                             ++cWorld;
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
                 if (alive) {
                     state = STEP;
                     if (energyChanged) {
-                        logE = log10f(p.energy);
+                        logE = log10Rounded(p.energy);
                         maxAttInv = maxAttenuationInverse(P.lut, logE);
                     }
                 } else {
@@ -369,7 +369,7 @@ __global__ void evalAttenuationKernel(LutView lut, uint64_t n, const uint8_t* ma
     const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
     if (i >= n)
         return;
-    const float logE = log10f(energy[i]);
+    const float logE = log10Rounded(energy[i]);
     float a, b, c;
     attenuation(lut, material[i], logE, a, b, c);
     out3[3 * i + 0] = a;

@@ -965,4 +965,12 @@ int dxmc_oracle_sample_interaction(dxmc_oracle* h, int kind, int model, uint8_t 
 
 void dxmc_oracle_history_stream(uint64_t seed, uint64_t exposure, uint64_t history, uint64_t out[2]) { historyStream(seed, exposure, history, out); }
 
+// the host libm's float log10 — the first operation of every reference LUT look-up (attenuationinterpolator.hpp:210);
+// exposed so tests can tell where it is not correctly rounded
+void dxmc_oracle_log10f(uint64_t n, const float* x, float* out)
+{
+    for (uint64_t i = 0; i < n; ++i)
+        out[i] = std::log10(x[i]);
+}
+
 } // extern "C"

