@@ -49,6 +49,16 @@ __device__ __forceinline__ float fastExp10(float x)
     return __fmaf_rn(__fmul_rn(e, r), 0.693147180559945f, e);
 }
 
+// lg2(x) by MUFU.LG2 (absolute error ~1e-7 of a mean free path in the step length, far below the float
+// resolution of the position). x is a PCG draw: 0 or >= 2^-32, never denormal; lg2(0) = -inf sends the photon
+// out of the world exactly like the reference's -log(0).
+__device__ __forceinline__ float fastLog2(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // log10(E) correctly rounded to float (evaluated in double). It is needed once per energy change, not per step,
 // and every attenuation value of the photon inherits its rounding through the log-log slope, so it is worth being
 // exact: a 1-ulp error here is a ~1e-6 relative error in mu at photoelectric slopes.
@@ -56,12 +66,13 @@ __device__ __forceinline__ float log10Rounded(float energy) { return __double2fl
 
 // ---- tables as the kernels see them -------------------------------------------------------
 constexpr int kSplineStride = 64; // device copy: 60 coefficients, start, step, stop, 1/step
+constexpr int kCoeffStride = 8; // device copy of the log-log coefficients: one 32-byte sector per (material, segment)
 
 struct LutView {
     uint32_t nMaterials, nSegments, linearIndex;
     float linearStep, linearEnergy, invLinearStep;
     const float* knots; // [nSegments]
-    const float* coeff; // [nMaterials][nSegments][6]
+    const float* coeff; // [nMaterials][nSegments][kCoeffStride]: photo {b,a}, Compton {b,a}, Rayleigh {b,a}, pad
     const float* maxCoeff; // [nSegments][2]
     const float* rita; // [nMaterials][4][56]
     const float* spline; // [nMaterials][kSplineStride]
@@ -72,8 +83,11 @@ struct WorldView {
     uint32_t dim[3];
     float spacing[3];
     float invSpacing[3]; // __frcp_rn(spacing)
+    uint32_t exactInverse; // all three spacings are powers of two: a * invSpacing == a / spacing exactly
     float ext[6];
-    const uint2* voxels; // {density bits, material | measurement<<8}
+    const uint2* voxels; // {density bits, material | measurement<<8}; null when the grid is in palette form
+    const uint8_t* palette; // palette form: index per voxel into paletteTable (grids with <= 256 distinct records)
+    const uint2* paletteTable; // [256] records as in `voxels`
 };
 
 struct SpectrumView {
@@ -189,10 +203,17 @@ __device__ __forceinline__ bool insideWorld(const WorldView& w, float x, float y
 
 __device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, float y, float z)
 {
-    const uint32_t ix = truncDiv(__fsub_rn(x, w.ext[0]), w.spacing[0], w.invSpacing[0]);
-    const uint32_t iy = truncDiv(__fsub_rn(y, w.ext[2]), w.spacing[1], w.invSpacing[1]);
-    const uint32_t iz = truncDiv(__fsub_rn(z, w.ext[4]), w.spacing[2], w.invSpacing[2]);
-    return iz * w.dim[0] * w.dim[1] + iy * w.dim[0] + ix;
+    uint32_t ix, iy, iz;
+    if (w.exactInverse) { // uniform branch: scaling by a power of two is exact, so is the truncated quotient
+        ix = __float2uint_rz(__fmul_rn(__fsub_rn(x, w.ext[0]), w.invSpacing[0]));
+        iy = __float2uint_rz(__fmul_rn(__fsub_rn(y, w.ext[2]), w.invSpacing[1]));
+        iz = __float2uint_rz(__fmul_rn(__fsub_rn(z, w.ext[4]), w.invSpacing[2]));
+    } else {
+        ix = truncDiv(__fsub_rn(x, w.ext[0]), w.spacing[0], w.invSpacing[0]);
+        iy = truncDiv(__fsub_rn(y, w.ext[2]), w.spacing[1], w.invSpacing[1]);
+        iz = truncDiv(__fsub_rn(z, w.ext[4]), w.spacing[2], w.invSpacing[2]);
+    }
+    return (iz * w.dim[1] + iy) * w.dim[0] + ix;
 }
 
 __device__ __forceinline__ void advance(Photon& p, float step)
@@ -255,15 +276,21 @@ __device__ __forceinline__ uint32_t segmentIndex(const LutView& l, float logE, b
 }
 
 // photo, Compton, Rayleigh mass attenuation of one material at log10(E)
+// the same with the segment already known (it only changes with the photon's energy)
+__device__ __forceinline__ void attenuationAt(const LutView& l, uint32_t material, uint32_t segment, float logE, float& photo, float& compton,
+    float& rayleigh)
+{
+    const float4* c = reinterpret_cast<const float4*>(l.coeff + (material * l.nSegments + segment) * kCoeffStride);
+    const float4 pc = __ldg(c); // photo {b, a}, Compton {b, a}
+    const float2 cr = __ldg(reinterpret_cast<const float2*>(c + 1));
+    photo = fastExp10(__fadd_rn(pc.x, __fmul_rn(pc.y, logE)));
+    compton = fastExp10(__fadd_rn(pc.z, __fmul_rn(pc.w, logE)));
+    rayleigh = fastExp10(__fadd_rn(cr.x, __fmul_rn(cr.y, logE)));
+}
+
 __device__ __forceinline__ void attenuation(const LutView& l, uint32_t material, float logE, float& photo, float& compton, float& rayleigh)
 {
-    const uint32_t index = segmentIndex(l, logE, true);
-    // 6 floats per (material, segment): 24-byte records, so every {b, a} pair is 8-byte aligned
-    const float2* c = reinterpret_cast<const float2*>(l.coeff + (material * l.nSegments + index) * 6);
-    const float2 cp = __ldg(c), cc = __ldg(c + 1), cr = __ldg(c + 2);
-    photo = fastExp10(__fadd_rn(cp.x, __fmul_rn(cp.y, logE)));
-    compton = fastExp10(__fadd_rn(cc.x, __fmul_rn(cc.y, logE)));
-    rayleigh = fastExp10(__fadd_rn(cr.x, __fmul_rn(cr.y, logE)));
+    attenuationAt(l, material, segmentIndex(l, logE, true), logE, photo, compton, rayleigh);
 }
 
 // inverse of the Woodcock majorant; the linear branch is not clamped in the reference either

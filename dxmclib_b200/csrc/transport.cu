@@ -1,16 +1,20 @@
 // transport.cu — sm_100a photon-transport kernels and the C ABI runtime around them.
 //
-// Replaces the reference's worker threads (transport.hpp:729-778). One persistent launch
-// covers a range of exposures: every lane of every warp owns one photon history at a time and
-// pulls the next (exposure, history) pair from a global counter when its photon dies. Lanes are
-// regrouped inside the warp by stage so divergent work runs on batches of lanes:
-//   DEAD      waiting for a new history   (birth = Exposure::sampleParticle + AABB entry)
-//   STEP      Woodcock delta tracking      (one voxel record fetch per step)
-//   INTERACT  a real / forced interaction is pending (photo / Compton / Rayleigh sampling, scoring)
-// Births and interactions are executed only when at least kBirthBatch / kInteractBatch lanes wait
-// for them (or nothing else can run), which keeps the rejection-sampling code off the critical
-// path of the stepping lanes. Histories carry their own counter-derived PCG32 stream, and scoring
-// is 64-bit fixed-point integer atomics, so results do not depend on scheduling.
+// Replaces the reference's worker threads (transport.hpp:729-778) by two kernels per chunk of histories:
+//
+//   generateKernel   Exposure::sampleParticle + transportParticleToWorld (exposure.hpp:280-304,
+//                    transport.hpp:702-728, 733-741) for every history of the chunk, one history per thread
+//                    with all 32 lanes busy; photons that reach the voxel grid are compacted (warp ballot +
+//                    one atomic per warp) into 64-byte records in HBM, carrying their own counter-derived
+//                    PCG32 stream, log10(E), the LUT segment and the Woodcock majorant.
+//   transportKernel  persistent grid; every lane owns one photon at a time and re-fills from the record
+//                    buffer when its photon dies. Lanes are regrouped inside the warp by stage:
+//                      STEP      Woodcock delta tracking in a tight loop (one voxel record fetch per step)
+//                      INTERACT  a real / forced interaction is pending (photo / Compton / Rayleigh sampling,
+//                                scoring); executed only when at least `interactBatch` lanes wait (or nothing
+//                                else can run), so the rejection samplers stay off the stepping lanes' path
+//                      DEAD      re-filled as soon as `refillBatch` lanes are empty
+// Scoring is 64-bit fixed-point integer atomics, so results do not depend on scheduling.
 #include "physics.cuh"
 
 #include <algorithm>
@@ -29,10 +33,23 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
-enum LaneState : uint32_t { DEAD = 0, STEP = 1, INTERACT = 2 };
+enum LaneState : uint32_t { DEAD = 0, STEP = 1, INTERACT = 2, EXHAUSTED = 3 };
 
 struct Counters {
     unsigned long long histories, inWorld, steps, lookups, interactions, scores;
+};
+
+// one in-flight photon as the generation kernel hands it to the transport kernel: 4 x 16 bytes
+struct alignas(16) PhotonRecord {
+    float4 posE; // px py pz energy
+    float4 dirW; // dx dy dz weight
+    uint4 rng; // state lo/hi, increment lo/hi
+    float4 lut; // log10(E), 1/majorant, LUT segment (bits), unused
+};
+
+struct ChunkCursor {
+    unsigned int stored; // records written by generateKernel
+    unsigned int taken; // records claimed by transportKernel
 };
 
 struct KernelParams {
@@ -40,19 +57,112 @@ struct KernelParams {
     LutView lut;
     BeamView beams;
     const dxmcb200_exposure* exposures; // absolute indexing
-    const uint64_t* prefix; // [nExp+1] cumulative histories of the launched range
-    uint64_t expBegin;
+    const uint64_t* prefix; // [nExp+1] cumulative histories of the run's exposure range
+    uint64_t expBegin; // first exposure of the run's range
     uint32_t nExp;
-    uint32_t uniformHistories; // >0: every exposure of the launch has this many histories and the launch total is < 2^32
-    uint64_t totalHistories;
+    uint32_t uniformHistories; // >0: every exposure of the range has this many histories (< 2^31)
+    uint64_t chunkBegin; // first history of the chunk, counted from the start of the range
+    uint32_t chunkCount; // histories in the chunk
+    uint32_t chunkFirstExposure; // uniform case: exposure (relative to expBegin) holding chunkBegin ...
+    uint32_t chunkFirstOffset; // ... and chunkBegin's history index inside it
+    uint32_t refillBatch, interactBatch;
     uint64_t seed;
-    unsigned long long* workCounter;
+    PhotonRecord* photons;
+    ChunkCursor* cursor;
     unsigned long long* acc; // [nVoxels][4]
     Counters* counters;
     float energyScale, energySqScale;
 };
 
-// ---- scoring: 64-bit fixed point (replaces safeValueAdd, transport.hpp:208-214) ------------------
+__device__ __forceinline__ unsigned long long warpSum(uint32_t v)
+{
+    unsigned long long s = v;
+    for (int o = 16; o > 0; o >>= 1)
+        s += __shfl_xor_sync(kFull, s, o);
+    return s;
+}
+
+// everything about a photon that only changes with its energy: log10(E) correctly rounded, the LUT segment it
+// falls in, the inverse Woodcock majorant (attenuationinterpolator.hpp:207-248)
+__device__ __forceinline__ void energyDependent(const LutView& lut, float energy, float& logE, uint32_t& seg, float& maxAttInv)
+{
+    logE = log10Rounded(energy);
+    seg = segmentIndex(lut, logE, true);
+    maxAttInv = maxAttenuationInverse(lut, logE);
+}
+
+// ---- (a) exposure-to-photon generation -------------------------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant__ KernelParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+    uint32_t cHist = 0, cWorld = 0;
+    const uint32_t rounded = (P.chunkCount + 31u) & ~31u;
+    for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < rounded; i += gridDim.x * kThreads) {
+        bool keep = false;
+        Photon p {};
+        Rng rng { 0, 1 };
+        if (i < P.chunkCount) {
+            uint32_t e;
+            uint64_t history;
+            if (P.uniformHistories) {
+                const uint32_t t = i + P.chunkFirstOffset;
+                const uint32_t q = t / P.uniformHistories;
+                e = P.chunkFirstExposure + q;
+                history = t - q * P.uniformHistories;
+            } else { // exposure owning history g: last prefix entry <= g
+                const uint64_t g = P.chunkBegin + i;
+                uint32_t lo = 0, hi = P.nExp;
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (__ldg(P.prefix + mid) <= g)
+                        lo = mid;
+                    else
+                        hi = mid;
+                }
+                e = lo;
+                history = g - __ldg(P.prefix + lo);
+            }
+            const uint64_t exposure = P.expBegin + e;
+            historyStream(P.seed, exposure, history, rng.state, rng.inc);
+            p = sampleParticle(P.exposures[exposure], P.beams, rng);
+            keep = transportToWorld(P.world, p);
+            if constexpr (kStats) {
+                ++cHist;
+                cWorld += keep ? 1u : 0u;
+            }
+        }
+        const unsigned keepMask = __ballot_sync(kFull, keep);
+        if (keepMask == 0)
+            continue;
+        unsigned base = 0;
+        const int leader = __ffs(keepMask) - 1;
+        if (static_cast<int>(lane) == leader)
+            base = atomicAdd(&P.cursor->stored, static_cast<unsigned>(__popc(keepMask)));
+        base = __shfl_sync(kFull, base, leader);
+        if (keep) {
+            float logE, maxAttInv;
+            uint32_t seg;
+            energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+            PhotonRecord* r = P.photons + (base + __popc(keepMask & laneLt));
+            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
+            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                static_cast<uint32_t>(rng.inc >> 32));
+            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
+        }
+    }
+    if constexpr (kStats) {
+        const unsigned long long h = warpSum(cHist), w = warpSum(cWorld);
+        if (lane == 0) {
+            atomicAdd(&P.counters->histories, h);
+            atomicAdd(&P.counters->inWorld, w);
+        }
+    }
+}
+
+// ---- (d) scoring: 64-bit fixed point (replaces safeValueAdd, transport.hpp:208-214) ---------------
 __device__ __forceinline__ void scoreEnergy(const KernelParams& P, uint32_t voxel, float energyImparted)
 {
     const long long fe = __float2ll_rn(energyImparted * P.energyScale);
@@ -67,10 +177,10 @@ struct Pending { // what an INTERACT lane needs from the step that found the eve
     float attPhoto, attCompton, attRayleigh;
     float eventProbability;
     uint32_t voxel;
-    uint32_t material; // bits 0-7 material, bit 8 forced
+    uint32_t material; // bits 0-7 material, bits 8-15 measurement flag (forced interaction when non-zero)
 };
 
-// computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
+// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
 template <int L, bool kStats>
 __device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores)
 {
@@ -145,161 +255,232 @@ __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p,
     return true;
 }
 
-// Russian roulette (transport.hpp:684-693); false when the photon is killed
-__device__ __forceinline__ bool roulette(Photon& p, Rng& rng)
+// ---- (b) Woodcock delta tracking + (c) interactions + (d) scoring ---------------------------------
+// ---- record staging: global -> shared with cp.async (LDGSTS), so a re-fill never waits on HBM ------
+constexpr unsigned kTile = 256; // records a warp claims with one atomic
+constexpr unsigned kGroup = 16; // records per cp.async group; the ring holds two groups per warp
+
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
 {
-    if (p.energy * p.weight < kRouletteThreshold) {
-        const float r4 = rng.uniform();
-        if (r4 < kRouletteProbability)
-            return false;
-        constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
-        p.weight *= factor;
-    }
-    return true;
+    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpAsyncWait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
+// ---- (b) Woodcock delta tracking + (c) interactions + (d) scoring ---------------------------------
+template <int L, bool kStats>
 __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constant__ KernelParams P)
 {
+    __shared__ PhotonRecord ring[kThreads / 32][2 * kGroup];
+    __shared__ unsigned stage[kThreads / 32][8];
+    __shared__ uint2 sPalette[256];
+
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
+    const unsigned nRecords = P.cursor->stored; // generateKernel of this chunk has completed (stream order)
+    PhotonRecord* const myRing = ring[threadIdx.x >> 5];
+    const bool paletteForm = P.world.palette != nullptr;
+    if (paletteForm) {
+        sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
+        __syncthreads();
+    }
 
     Rng rng { 0, 1 };
     Photon p {};
     Pending pe {};
-    float maxAttInv = 0.0f, logE = 0.0f;
+    float logE = 0.0f, maxAttInv = 0.0f;
+    uint32_t seg = 0;
+    bool lowWeight = false; // E*w below the Russian-roulette threshold (transport.hpp:684)
     uint32_t state = DEAD;
-    bool exhausted = false;
-    uint32_t cHist = 0, cWorld = 0, cSteps = 0, cLookups = 0, cInter = 0, cScores = 0;
+    uint32_t cSteps = 0, cLookups = 0, cInter = 0, cScores = 0;
+
+    // -ln(r)*maxAttInv*10 (transport.hpp:655-657) is evaluated as lg2(r) * kStepScale * maxAttInv; cm -> mm is the factor 10
+    constexpr float kStepScale = -6.931471805599453f;
+
+    // warp-uniform staging state, kept in shared memory so it costs no registers in the stepping loop: the warp
+    // claims tiles of kTile records, streams them through its ring in groups of kGroup (group k lives in ring half
+    // k & 1) and hands the records of the oldest group to empty lanes. Every lane executes the same updates.
+    enum { TILE_NEXT, TILE_END, TILES_LEFT, ISSUED, CONSUMED, COUNT0, COUNT1, OFFSET };
+    volatile unsigned* const st = stage[threadIdx.x >> 5];
+    if (lane < 8)
+        st[lane] = lane == TILES_LEFT ? 1u : 0u;
+    __syncwarp();
+
+    auto issueGroup = [&]() {
+        const unsigned issued = st[ISSUED];
+        if (issued - st[CONSUMED] >= 2)
+            return;
+        unsigned tileNext = st[TILE_NEXT], tileEnd = st[TILE_END];
+        if (tileNext >= tileEnd) {
+            if (!st[TILES_LEFT])
+                return;
+            unsigned t = 0;
+            if (lane == 0)
+                t = atomicAdd(&P.cursor->taken, kTile);
+            t = __shfl_sync(kFull, t, 0);
+            if (t >= nRecords) {
+                st[TILES_LEFT] = 0;
+                return;
+            }
+            tileNext = t;
+            tileEnd = min(t + kTile, nRecords);
+            st[TILE_END] = tileEnd;
+        }
+        const unsigned half = issued & 1u;
+        const unsigned cnt = min(kGroup, tileEnd - tileNext);
+        const char* src = reinterpret_cast<const char*>(P.photons + tileNext);
+        char* dst = reinterpret_cast<char*>(myRing + half * kGroup);
+#pragma unroll
+        for (unsigned t = 0; t < (kGroup * sizeof(PhotonRecord) / 16) / 32; ++t) {
+            const unsigned piece = lane + 32 * t;
+            if (piece < cnt * (sizeof(PhotonRecord) / 16))
+                cpAsync16(dst + piece * 16, src + piece * 16);
+        }
+        cpAsyncCommit();
+        st[COUNT0 + half] = cnt;
+        st[TILE_NEXT] = tileNext + kGroup;
+        st[ISSUED] = issued + 1;
+    };
+    issueGroup();
+    issueGroup();
 
     for (;;) {
-        const unsigned deadMask = __ballot_sync(kFull, state == DEAD && !exhausted);
+        // ---- pending interactions, batched: computeInteractions[Forced] + Russian roulette (transport.hpp:667-693)
         const unsigned stepMask = __ballot_sync(kFull, state == STEP);
         const unsigned intMask = __ballot_sync(kFull, state == INTERACT);
-        if ((deadMask | stepMask | intMask) == 0)
-            break;
-
-        // ---- births: Exposure::sampleParticle + transportParticleToWorld (transport.hpp:733-741)
-        if (deadMask && (__popc(deadMask) >= kBirthBatch || stepMask == 0)) {
-            const int leader = __ffs(deadMask) - 1;
-            unsigned long long base = 0;
-            if (static_cast<int>(lane) == leader)
-                base = atomicAdd(P.workCounter, static_cast<unsigned long long>(__popc(deadMask)));
-            base = __shfl_sync(kFull, base, leader);
-            if (state == DEAD && !exhausted) {
-                const uint64_t g = base + __popc(deadMask & laneLt);
-                if (g >= P.totalHistories) {
-                    exhausted = true;
-                } else {
-                    // exposure owning history g: last prefix entry <= g
-                    uint32_t lo = 0;
-                    uint64_t history;
-                    if (P.uniformHistories) {
-                        const uint32_t g32 = static_cast<uint32_t>(g);
-                        lo = g32 / P.uniformHistories;
-                        history = g32 - lo * P.uniformHistories;
-                    } else {
-                        uint32_t hi = P.nExp;
-                        while (hi - lo > 1) {
-                            const uint32_t mid = (lo + hi) >> 1;
-                            if (__ldg(P.prefix + mid) <= g)
-                                lo = mid;
-                            else
-                                hi = mid;
-                        }
-                        history = g - __ldg(P.prefix + lo);
-                    }
-                    const uint64_t exposure = P.expBegin + lo;
-                    historyStream(P.seed, exposure, history, rng.state, rng.inc);
-                    p = sampleParticle(P.exposures[exposure], P.beams, rng);
-                    if constexpr (kStats)
-                        ++cHist;
-                    if (transportToWorld(P.world, p)) {
-                        state = STEP;
-                        logE = log10Rounded(p.energy);
-                        maxAttInv = maxAttenuationInverse(P.lut, logE);
-                        if constexpr (kStats)
-                            ++cWorld;
-                    }
-                }
-            }
-        }
-
-        // ---- interactions, batched
-        if (intMask && (__popc(intMask) >= kInteractBatch || stepMask == 0)) {
+        if (intMask && (static_cast<unsigned>(__popc(intMask)) >= P.interactBatch || stepMask == 0)) {
             if (state == INTERACT) {
                 bool energyChanged = false;
                 bool alive;
-                if (pe.material & 0x100u)
+                if (pe.material & 0xff00u)
                     alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
                 else
                     alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
                 if constexpr (kStats)
                     ++cInter;
-                if (alive)
-                    alive = roulette(p, rng);
+                if (alive && p.energy * p.weight < kRouletteThreshold) {
+                    const float r4 = rng.uniform();
+                    if (r4 < kRouletteProbability) {
+                        alive = false;
+                    } else {
+                        constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+                        p.weight *= factor;
+                    }
+                }
                 if (alive) {
                     state = STEP;
-                    if (energyChanged) {
-                        logE = log10Rounded(p.energy);
-                        maxAttInv = maxAttenuationInverse(P.lut, logE);
-                    }
+                    if (energyChanged)
+                        energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+                    lowWeight = p.energy * p.weight < kRouletteThreshold;
                 } else {
                     state = DEAD;
                 }
             }
         }
 
-        // ---- one Woodcock step (transport.hpp:655-682)
-        if (state == STEP) {
-            const float r1 = rng.uniform();
-            // MUFU.LG2-based log: absolute error ~1e-7 of a mean free path, far below the float resolution of the position
-            const float stepLength = -__logf(r1) * maxAttInv * 10.0f;
-            advance(p, stepLength);
-            if constexpr (kStats)
-                ++cSteps;
-            if (!insideWorld(P.world, p.px, p.py, p.pz)) {
-                state = DEAD;
+        // ---- re-fill empty lanes from the oldest staged group
+        const unsigned deadMask = __ballot_sync(kFull, state == DEAD);
+        if (deadMask) {
+            const unsigned issued = st[ISSUED], consumed = st[CONSUMED];
+            if (consumed == issued) { // nothing staged: only possible when the record buffer is drained
+                if (state == DEAD)
+                    state = EXHAUSTED;
             } else {
-                const uint32_t voxel = voxelIndex(P.world, p.px, p.py, p.pz);
-                const uint2 rec = __ldg(P.world.voxels + voxel);
-                const float density = __uint_as_float(rec.x);
-                const uint32_t mat = rec.y & 0xffu;
-                const uint32_t measurement = (rec.y >> 8) & 0xffu;
-                if constexpr (kStats)
-                    ++cLookups;
-                float aP, aC, aR;
-                attenuation(P.lut, mat, logE, aP, aC, aR);
-                const float attTotal = (((0.0f + aP) + aC) + aR) * density;
-                const float eventProbability = attTotal * maxAttInv;
-                if (measurement == 0) {
-                    const float r2 = rng.uniform();
-                    if (r2 < eventProbability) {
-                        pe = Pending { aP, aC, aR, eventProbability, voxel, mat };
-                        state = INTERACT;
-                    } else if (!roulette(p, rng)) {
-                        state = DEAD;
-                    }
+                if (issued - consumed == 2)
+                    cpAsyncWait<1>(); // the older of the two groups in flight has landed
+                else
+                    cpAsyncWait<0>();
+                __syncwarp();
+                const unsigned half = consumed & 1u;
+                const unsigned count = st[COUNT0 + half], offset = st[OFFSET];
+                const unsigned avail = count - offset;
+                const unsigned rank = __popc(deadMask & laneLt);
+                if (state == DEAD && rank < avail) {
+                    const PhotonRecord* r = myRing + half * kGroup + offset + rank;
+                    const float4 a = r->posE, b = r->dirW, d = r->lut;
+                    const uint4 c = r->rng;
+                    p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
+                    p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
+                    rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
+                    rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
+                    logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
+                    lowWeight = p.energy * p.weight < kRouletteThreshold;
+                    state = STEP;
+                }
+                __syncwarp(); // every lane has read its record before the half is requested again
+                const unsigned taken = min(avail, static_cast<unsigned>(__popc(deadMask)));
+                if (offset + taken == count) {
+                    st[CONSUMED] = consumed + 1;
+                    st[OFFSET] = 0;
+                    issueGroup();
                 } else {
-                    pe = Pending { aP, aC, aR, eventProbability, voxel, mat | 0x100u };
-                    state = INTERACT;
+                    st[OFFSET] = offset + taken;
                 }
             }
         }
+        if (__ballot_sync(kFull, state == STEP || state == INTERACT || state == DEAD) == 0)
+            break;
+
+        // ---- Woodcock steps (transport.hpp:655-682) until enough lanes wait for a re-fill or an interaction
+        for (;;) {
+            if (state == STEP) {
+                const float r1 = rng.uniform();
+                advance(p, (fastLog2(r1) * kStepScale) * maxAttInv);
+                if constexpr (kStats)
+                    ++cSteps;
+                if (!insideWorld(P.world, p.px, p.py, p.pz)) {
+                    state = DEAD;
+                } else {
+                    const uint32_t voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+                    uint2 rec;
+                    if (paletteForm)
+                        rec = sPalette[__ldg(P.world.palette + voxel)];
+                    else
+                        rec = __ldg(P.world.voxels + voxel);
+                    const float density = __uint_as_float(rec.x);
+                    if constexpr (kStats)
+                        ++cLookups;
+                    // a stepping lane has no interaction pending, so the pending-event registers are free to hold
+                    // this step's values; they simply stay put when the lane leaves the loop with an event
+                    pe.voxel = voxel;
+                    pe.material = rec.y;
+                    attenuationAt(P.lut, rec.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
+                    const float attTotal = (((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh) * density;
+                    pe.eventProbability = attTotal * maxAttInv;
+                    bool event = (rec.y & 0xff00u) != 0; // measurement voxel: forced interaction, no draw
+                    if (!event)
+                        event = rng.uniform() < pe.eventProbability;
+                    if (event) {
+                        state = INTERACT;
+                    } else if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
+                        const float r4 = rng.uniform();
+                        if (r4 < kRouletteProbability) {
+                            state = DEAD;
+                        } else {
+                            constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+                            p.weight *= factor;
+                            lowWeight = p.energy * p.weight < kRouletteThreshold;
+                        }
+                    }
+                }
+            }
+            const unsigned dead = __ballot_sync(kFull, state == DEAD);
+            const unsigned pend = __ballot_sync(kFull, state == INTERACT);
+            const unsigned stepping = __ballot_sync(kFull, state == STEP);
+            if (static_cast<unsigned>(__popc(dead)) >= P.refillBatch || static_cast<unsigned>(__popc(pend)) >= P.interactBatch || stepping == 0)
+                break;
+        }
     }
+    cpAsyncWait<0>();
 
     if constexpr (kStats) {
-        auto warpSum = [](uint32_t v) {
-            unsigned long long s = v;
-            for (int o = 16; o > 0; o >>= 1)
-                s += __shfl_xor_sync(kFull, s, o);
-            return s;
-        };
-        const unsigned long long h = warpSum(cHist), w = warpSum(cWorld), s = warpSum(cSteps), l = warpSum(cLookups),
-                                 i = warpSum(cInter), sc = warpSum(cScores);
+        const unsigned long long s = warpSum(cSteps), l = warpSum(cLookups), i = warpSum(cInter), sc = warpSum(cScores);
         if (lane == 0) {
-            atomicAdd(&P.counters->histories, h);
-            atomicAdd(&P.counters->inWorld, w);
             atomicAdd(&P.counters->steps, s);
             atomicAdd(&P.counters->lookups, l);
             atomicAdd(&P.counters->interactions, i);
@@ -318,8 +499,92 @@ __global__ void packVoxelsKernel(const float* __restrict__ density, const uint8_
     }
 }
 
+// ---- palette form of the voxel grid ---------------------------------------------------------------
+// Segmentation phantoms hold a handful of distinct {density, material, measurement} records. When there are at
+// most 256 of them the grid is stored as one byte per voxel plus a 256-entry record table: lossless, 8x less
+// look-up traffic, and at 512x512x400 small enough to stay resident in the 126 MB L2.
+constexpr unsigned kPaletteSlots = 4096; // open-addressing hash table of 64-bit record keys
+constexpr unsigned long long kEmptyKey = ~0ULL;
+
+__device__ __forceinline__ unsigned long long voxelKey(const float* density, const uint8_t* material, const uint8_t* measurement, uint64_t i)
+{
+    const uint32_t m = material[i] | (measurement ? (static_cast<uint32_t>(measurement[i]) << 8) : 0u);
+    return (static_cast<unsigned long long>(m) << 32) | __float_as_uint(density[i]);
+}
+
+__device__ __forceinline__ unsigned paletteHash(unsigned long long key)
+{
+    return static_cast<unsigned>((key * 0x9E3779B97F4A7C15ULL) >> 40) & (kPaletteSlots - 1);
+}
+
+// pass 1: collect the distinct records; *distinct > 256 (or a full table) means "no palette"
+__global__ void paletteCollectKernel(const float* __restrict__ density, const uint8_t* __restrict__ material,
+    const uint8_t* __restrict__ measurement, uint64_t n, unsigned long long* table, unsigned* distinct)
+{
+    const uint64_t threads = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t per = (n + threads - 1) / threads;
+    const uint64_t begin = (blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x) * per;
+    const uint64_t end = begin + per < n ? begin + per : n;
+    unsigned long long last = kEmptyKey;
+    for (uint64_t i = begin; i < end; ++i) { // a thread walks a contiguous run, so repeated records cost nothing
+        const unsigned long long key = voxelKey(density, material, measurement, i);
+        if (key == last)
+            continue;
+        last = key;
+        if (*reinterpret_cast<volatile unsigned*>(distinct) > 256u)
+            return;
+        unsigned h = paletteHash(key);
+        bool placed = false;
+        for (unsigned probe = 0; probe < kPaletteSlots && !placed; ++probe) {
+            const unsigned long long old = atomicCAS(table + h, kEmptyKey, key);
+            if (old == kEmptyKey) {
+                atomicAdd(distinct, 1u);
+                placed = true;
+            } else if (old == key) {
+                placed = true;
+            }
+            h = (h + 1) & (kPaletteSlots - 1);
+        }
+        if (!placed)
+            atomicAdd(distinct, 1000u);
+    }
+}
+
+// pass 2 (one block): number the occupied slots
+__global__ void paletteNumberKernel(const unsigned long long* table, unsigned* slotIndex, uint2* paletteTable)
+{
+    __shared__ unsigned next;
+    if (threadIdx.x == 0)
+        next = 0;
+    __syncthreads();
+    for (unsigned s = threadIdx.x; s < kPaletteSlots; s += blockDim.x) {
+        const unsigned long long key = table[s];
+        if (key != kEmptyKey) {
+            const unsigned idx = atomicAdd(&next, 1u);
+            slotIndex[s] = idx;
+            if (idx < 256u)
+                paletteTable[idx] = make_uint2(static_cast<uint32_t>(key), static_cast<uint32_t>(key >> 32));
+        }
+    }
+}
+
+// pass 3: one byte per voxel
+__global__ void paletteIndexKernel(const float* __restrict__ density, const uint8_t* __restrict__ material,
+    const uint8_t* __restrict__ measurement, uint64_t n, const unsigned long long* __restrict__ table, const unsigned* __restrict__ slotIndex,
+    uint8_t* __restrict__ out)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const unsigned long long key = voxelKey(density, material, measurement, i);
+        unsigned h = paletteHash(key);
+        while (table[h] != key)
+            h = (h + 1) & (kPaletteSlots - 1);
+        out[i] = static_cast<uint8_t>(slotIndex[h]);
+    }
+}
+
 // normalizeScoring / energyImpartedToDose (transport.hpp:780-816) fused with the fixed-point decode
-__global__ void resultKernel(const unsigned long long* __restrict__ acc, const uint2* __restrict__ voxels, uint64_t n, int mode,
+__global__ void resultKernel(const unsigned long long* __restrict__ acc, const uint2* __restrict__ voxels, const uint8_t* __restrict__ palette,
+    const uint2* __restrict__ paletteTable, uint64_t n, int mode,
     float energyLsb, float energySqLsb, uint64_t histories, float calibration, float voxelVolume, float* __restrict__ dose,
     uint32_t* __restrict__ nEvents, float* __restrict__ variance)
 {
@@ -335,7 +600,7 @@ __global__ void resultKernel(const unsigned long long* __restrict__ acc, const u
             d = e * hdInv;
             v = (e2 * hvInv - d * d) * hInv;
         } else if (mode == 1) {
-            const float de = __uint_as_float(voxels[i].x);
+            const float de = __uint_as_float(palette ? paletteTable[palette[i]].x : voxels[i].x);
             const float voxelMass = de * voxelVolume * 0.001f;
             const float factor = calibration / voxelMass;
             d = de > 0.0f ? e * factor : 0.0f;
@@ -468,7 +733,10 @@ struct dxmcb200_ctx {
     // world
     WorldView world {};
     uint64_t nVoxels = 0;
-    uint2* dVoxels = nullptr;
+    uint2* dVoxels = nullptr; // 8-byte records, or null when the grid is in palette form
+    uint8_t* dPalette = nullptr; // palette form: one byte per voxel ...
+    uint2* dPaletteTable = nullptr; // ... into this 256-entry record table
+    bool allowPalette = true;
     unsigned long long* dAcc = nullptr;
 
     // luts
@@ -486,12 +754,16 @@ struct dxmcb200_ctx {
     uint64_t* dPrefix = nullptr;
     uint64_t prefixCapacity = 0;
 
-    unsigned long long* dWorkCounter = nullptr;
+    // photon record buffer between generateKernel and transportKernel, one chunk of histories at a time
+    PhotonRecord* dPhotons = nullptr;
+    uint64_t photonCapacity = 0;
+    ChunkCursor* dCursor = nullptr;
     Counters* dCounters = nullptr;
 
     int energyBits = 20, energySqBits = 10;
     bool collectStats = false;
-    uint64_t maxHistoriesPerLaunch = 2000000000ULL;
+    uint32_t chunkHistories = 1u << 25; // histories per generate/transport launch pair (2 GiB of records)
+    uint32_t refillBatch = 4, interactBatch = 8; // lanes that must wait before a re-fill / interaction stage runs
 
     double lastRunMs = 0, totalMs = 0;
     uint64_t launches = 0;
@@ -525,131 +797,135 @@ T* advancePtr(char*& cursor, size_t count)
     return p;
 }
 
-template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
-cudaError_t launchTransportBatched(const dxmcb200_ctx* c, const KernelParams& P);
-
-// lanes that must wait before a birth / interaction stage runs; tunable for experiments with
-// DXMCB200_BATCH=<birth>,<interact> out of the compiled set
-template <int L, bool kStats>
-cudaError_t launchTransport(const dxmcb200_ctx* c, const KernelParams& P)
+// persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
+template <typename K>
+cudaError_t launchPersistent(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items)
 {
-    static const int choice = [] {
-        const char* env = std::getenv("DXMCB200_BATCH");
-        int b = 8, i = 8;
-        if (env)
-            std::sscanf(env, "%d,%d", &b, &i);
-        return b * 100 + i;
-    }();
-    if constexpr (!kStats) {
-        switch (choice) {
-        case 408:
-            return launchTransportBatched<L, kStats, 4, 8>(c, P);
-        case 812:
-            return launchTransportBatched<L, kStats, 8, 12>(c, P);
-        case 816:
-            return launchTransportBatched<L, kStats, 8, 16>(c, P);
-        case 1216:
-            return launchTransportBatched<L, kStats, 12, 16>(c, P);
-        case 1616:
-            return launchTransportBatched<L, kStats, 16, 16>(c, P);
-        case 1624:
-            return launchTransportBatched<L, kStats, 16, 24>(c, P);
-        default:
-            break;
-        }
-    }
-    return launchTransportBatched<L, kStats, 8, 8>(c, P);
-}
-
-template <int L, bool kStats, int kBirthBatch, int kInteractBatch>
-cudaError_t launchTransportBatched(const dxmcb200_ctx* c, const KernelParams& P)
-{
-    auto kernel = transportKernel<L, kStats, kBirthBatch, kInteractBatch>;
     int blocksPerSm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
     if (e != cudaSuccess)
         return e;
-    blocksPerSm = std::max(blocksPerSm, 1);
-    // persistent grid: a whole number of resident CTAs per SM, never more lanes than histories
-    uint64_t blocks = static_cast<uint64_t>(c->smCount) * blocksPerSm;
-    const uint64_t needed = (P.totalHistories + kThreads - 1) / kThreads;
-    blocks = std::max<uint64_t>(1, std::min(blocks, needed));
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * std::max(blocksPerSm, 1);
+    blocks = std::max<uint64_t>(1, std::min(blocks, (items + kThreads - 1) / kThreads));
     kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
     return cudaGetLastError();
+}
+
+template <int L>
+cudaError_t launchChunk(const dxmcb200_ctx* c, const KernelParams& P)
+{
+    cudaError_t e = c->collectStats ? launchPersistent(c, generateKernel<true>, P, P.chunkCount) : launchPersistent(c, generateKernel<false>, P, P.chunkCount);
+    if (e != cudaSuccess)
+        return e;
+    return c->collectStats ? launchPersistent(c, transportKernel<L, true>, P, P.chunkCount) : launchPersistent(c, transportKernel<L, false>, P, P.chunkCount);
 }
 
 int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmcb200_exposure* devExposures, uint64_t expBegin,
     uint64_t expEnd, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
 {
-    if (!c->dVoxels || !c->dLutBlob)
+    if ((!c->dVoxels && !c->dPalette) || !c->dLutBlob)
         return DXMCB200_ERR_STATE;
     if (model < 0 || model > 2 || expEnd < expBegin)
         return DXMCB200_ERR_ARG;
     CU_CHECK(c, cudaSetDevice(c->device));
     c->lastRunMs = 0;
-    uint64_t e0 = expBegin;
-    while (e0 < expEnd) {
-        if (cancel && *cancel)
-            return DXMCB200_ERR_CANCELLED;
-        // chunk of exposures bounded by histories per launch
-        std::vector<uint64_t> prefix;
-        prefix.push_back(0);
-        uint64_t e1 = e0;
-        while (e1 < expEnd && (prefix.back() == 0 || prefix.back() + hostExposures[e1].histories <= c->maxHistoriesPerLaunch)) {
-            prefix.push_back(prefix.back() + hostExposures[e1].histories);
-            ++e1;
-        }
-        const uint64_t total = prefix.back();
-        if (total > 0) {
-            if (prefix.size() > c->prefixCapacity) {
-                if (c->dPrefix)
-                    cudaFree(c->dPrefix);
-                c->prefixCapacity = std::max<uint64_t>(prefix.size(), 4096);
-                CU_CHECK(c, cudaMalloc(&c->dPrefix, c->prefixCapacity * sizeof(uint64_t)));
-            }
-            CU_CHECK(c, cudaMemcpyAsync(c->dPrefix, prefix.data(), prefix.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
-            CU_CHECK(c, cudaMemsetAsync(c->dWorkCounter, 0, sizeof(unsigned long long), c->stream));
-
-            KernelParams P {};
-            P.world = c->world;
-            P.lut = c->lut;
-            P.beams = c->beams;
-            P.exposures = devExposures;
-            P.prefix = c->dPrefix;
-            P.expBegin = e0;
-            P.nExp = static_cast<uint32_t>(e1 - e0);
-            P.totalHistories = total;
-            bool uniform = total < (1ULL << 32);
-            for (uint64_t e = e0; e < e1 && uniform; ++e)
-                uniform = hostExposures[e].histories == hostExposures[e0].histories;
-            P.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[e0].histories) : 0u;
-            P.seed = seed;
-            P.workCounter = c->dWorkCounter;
-            P.acc = c->dAcc;
-            P.counters = c->dCounters;
-            P.energyScale = std::ldexp(1.0f, c->energyBits);
-            P.energySqScale = std::ldexp(1.0f, c->energySqBits);
-
-            CU_CHECK(c, cudaEventRecord(c->evStart, c->stream));
-            cudaError_t le;
-            if (c->collectStats) {
-                le = model == 0 ? launchTransport<0, true>(c, P) : model == 1 ? launchTransport<1, true>(c, P) : launchTransport<2, true>(c, P);
-            } else {
-                le = model == 0 ? launchTransport<0, false>(c, P) : model == 1 ? launchTransport<1, false>(c, P) : launchTransport<2, false>(c, P);
-            }
-            CU_CHECK(c, le);
-            CU_CHECK(c, cudaEventRecord(c->evStop, c->stream));
-            CU_CHECK(c, cudaStreamSynchronize(c->stream)); // also keeps `prefix` alive until the copy is done
-            float ms = 0;
-            CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
-            c->lastRunMs += ms;
-            c->totalMs += ms;
-            ++c->launches;
-        }
-        e0 = e1;
-        if (cb)
-            cb(e0 - expBegin, user);
+    const uint64_t nExp = expEnd - expBegin;
+    if (nExp == 0)
+        return DXMCB200_OK;
+    if (nExp >= (1ULL << 32)) {
+        c->error = "more than 2^32 exposures in one run";
+        return DXMCB200_ERR_ARG;
     }
+
+    // cumulative histories of the range; histories are numbered 0..total-1 across it
+    std::vector<uint64_t> prefix(nExp + 1, 0);
+    bool uniform = hostExposures[expBegin].histories > 0 && hostExposures[expBegin].histories < (1ULL << 31);
+    for (uint64_t e = 0; e < nExp; ++e) {
+        prefix[e + 1] = prefix[e] + hostExposures[expBegin + e].histories;
+        uniform = uniform && hostExposures[expBegin + e].histories == hostExposures[expBegin].histories;
+    }
+    const uint64_t total = prefix.back();
+    if (total == 0) {
+        if (cb)
+            cb(nExp, user);
+        return DXMCB200_OK;
+    }
+    if (prefix.size() > c->prefixCapacity) {
+        if (c->dPrefix)
+            cudaFree(c->dPrefix);
+        c->dPrefix = nullptr;
+        c->prefixCapacity = std::max<uint64_t>(prefix.size(), 4096);
+        CU_CHECK(c, cudaMalloc(&c->dPrefix, c->prefixCapacity * sizeof(uint64_t)));
+    }
+    CU_CHECK(c, cudaMemcpyAsync(c->dPrefix, prefix.data(), prefix.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
+
+    const uint64_t chunk = std::min<uint64_t>(c->chunkHistories, total);
+    if (chunk > c->photonCapacity) {
+        cudaFree(c->dPhotons);
+        c->dPhotons = nullptr;
+        c->photonCapacity = 0;
+        CU_CHECK(c, cudaMalloc(&c->dPhotons, chunk * sizeof(PhotonRecord)));
+        c->photonCapacity = chunk;
+    }
+
+    KernelParams P {};
+    P.world = c->world;
+    P.lut = c->lut;
+    P.beams = c->beams;
+    P.exposures = devExposures;
+    P.prefix = c->dPrefix;
+    P.expBegin = expBegin;
+    P.nExp = static_cast<uint32_t>(nExp);
+    P.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
+    P.refillBatch = c->refillBatch;
+    P.interactBatch = c->interactBatch;
+    P.seed = seed;
+    P.photons = c->dPhotons;
+    P.cursor = c->dCursor;
+    P.acc = c->dAcc;
+    P.counters = c->dCounters;
+    P.energyScale = std::ldexp(1.0f, c->energyBits);
+    P.energySqScale = std::ldexp(1.0f, c->energySqBits);
+
+    uint64_t expDone = 0; // exposures of the range completely transported, for the progress callback
+    CU_CHECK(c, cudaEventRecord(c->evStart, c->stream));
+    uint64_t sinceSync = 0;
+    for (uint64_t h0 = 0; h0 < total; h0 += chunk) {
+        if (cancel && *cancel) {
+            cudaStreamSynchronize(c->stream);
+            return DXMCB200_ERR_CANCELLED;
+        }
+        P.chunkBegin = h0;
+        P.chunkCount = static_cast<uint32_t>(std::min<uint64_t>(chunk, total - h0));
+        if (uniform) {
+            P.chunkFirstExposure = static_cast<uint32_t>(h0 / P.uniformHistories);
+            P.chunkFirstOffset = static_cast<uint32_t>(h0 % P.uniformHistories);
+        }
+        CU_CHECK(c, cudaMemsetAsync(c->dCursor, 0, sizeof(ChunkCursor), c->stream));
+        const cudaError_t le = model == 0 ? launchChunk<0>(c, P) : model == 1 ? launchChunk<1>(c, P) : launchChunk<2>(c, P);
+        CU_CHECK(c, le);
+        c->launches += 2;
+        sinceSync += P.chunkCount;
+        // progress / cancellation need the host in the loop now and then; otherwise chunks are queued back to back
+        if ((cb || cancel) && sinceSync >= (1ULL << 28)) {
+            CU_CHECK(c, cudaStreamSynchronize(c->stream));
+            sinceSync = 0;
+            if (cb) {
+                const uint64_t done = h0 + P.chunkCount;
+                while (expDone < nExp && prefix[expDone + 1] <= done)
+                    ++expDone;
+                cb(expDone, user);
+            }
+        }
+    }
+    CU_CHECK(c, cudaEventRecord(c->evStop, c->stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->stream)); // also keeps `prefix` alive until the copy is done
+    float ms = 0;
+    CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+    c->lastRunMs = ms;
+    c->totalMs += ms;
+    if (cb && expDone < nExp)
+        cb(nExp, user);
     return DXMCB200_OK;
 }
 
@@ -684,13 +960,22 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->evStart) != cudaSuccess
-        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dWorkCounter, sizeof(unsigned long long)) != cudaSuccess
+        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dCursor, sizeof(ChunkCursor)) != cudaSuccess
         || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemset(c->dCounters, 0, sizeof(Counters)) != cudaSuccess) {
         dxmcb200_destroy(c);
         return DXMCB200_ERR_CUDA;
     }
     const char* stats = std::getenv("DXMCB200_STATS");
     c->collectStats = stats && stats[0] == '1';
+    if (const char* env = std::getenv("DXMCB200_PALETTE"))
+        c->allowPalette = env[0] != '0';
+    if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill>,<interact>[,<log2 chunk>]
+        int r = 4, i = 8, lg = 25;
+        std::sscanf(env, "%d,%d,%d", &r, &i, &lg);
+        c->refillBatch = static_cast<uint32_t>(std::clamp(r, 1, 32));
+        c->interactBatch = static_cast<uint32_t>(std::clamp(i, 1, 32));
+        c->chunkHistories = 1u << std::clamp(lg, 10, 28);
+    }
     *out = c;
     return DXMCB200_OK;
 }
@@ -701,12 +986,15 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
         return;
     cudaSetDevice(c->device);
     cudaFree(c->dVoxels);
+    cudaFree(c->dPalette);
+    cudaFree(c->dPaletteTable);
     cudaFree(c->dAcc);
     cudaFree(c->dLutBlob);
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
-    cudaFree(c->dWorkCounter);
+    cudaFree(c->dCursor);
+    cudaFree(c->dPhotons);
     cudaFree(c->dCounters);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
@@ -730,15 +1018,18 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     }
     CU_CHECK(c, cudaSetDevice(c->device));
     if (n != c->nVoxels) {
-        cudaFree(c->dVoxels);
         cudaFree(c->dAcc);
-        c->dVoxels = nullptr;
         c->dAcc = nullptr;
         c->nVoxels = 0;
-        CU_CHECK(c, cudaMalloc(&c->dVoxels, n * sizeof(uint2)));
         CU_CHECK(c, cudaMalloc(&c->dAcc, n * 4 * sizeof(unsigned long long)));
         c->nVoxels = n;
     }
+    cudaFree(c->dVoxels);
+    cudaFree(c->dPalette);
+    cudaFree(c->dPaletteTable);
+    c->dVoxels = nullptr;
+    c->dPalette = nullptr;
+    c->dPaletteTable = nullptr;
     float* dDensity = nullptr;
     uint8_t* dMat = nullptr;
     uint8_t* dMeas = nullptr;
@@ -750,9 +1041,41 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     CU_CHECK(c, cudaMemcpyAsync(dMat, w->material, n, cudaMemcpyHostToDevice, c->stream));
     if (w->measurement)
         CU_CHECK(c, cudaMemcpyAsync(dMeas, w->measurement, n, cudaMemcpyHostToDevice, c->stream));
-    packVoxelsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, c->dVoxels, n);
-    CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, n * 4 * sizeof(unsigned long long), c->stream));
+
+    // palette form when the grid holds at most 256 distinct records, 8-byte records otherwise
+    bool palette = false;
+    if (c->allowPalette) {
+        unsigned long long* dTable = nullptr;
+        unsigned* dSlotIndex = nullptr; // [kPaletteSlots] + the distinct-record counter
+        CU_CHECK(c, cudaMalloc(&dTable, kPaletteSlots * sizeof(unsigned long long)));
+        CU_CHECK(c, cudaMalloc(&dSlotIndex, (kPaletteSlots + 1) * sizeof(unsigned)));
+        CU_CHECK(c, cudaMemsetAsync(dTable, 0xff, kPaletteSlots * sizeof(unsigned long long), c->stream));
+        CU_CHECK(c, cudaMemsetAsync(dSlotIndex, 0, (kPaletteSlots + 1) * sizeof(unsigned), c->stream));
+        unsigned* dDistinct = dSlotIndex + kPaletteSlots;
+        paletteCollectKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, n, dTable, dDistinct);
+        CU_CHECK(c, cudaGetLastError());
+        unsigned distinct = 0;
+        CU_CHECK(c, cudaMemcpyAsync(&distinct, dDistinct, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        if (distinct <= 256u) {
+            CU_CHECK(c, cudaMalloc(&c->dPalette, n));
+            CU_CHECK(c, cudaMalloc(&c->dPaletteTable, 256 * sizeof(uint2)));
+            CU_CHECK(c, cudaMemsetAsync(c->dPaletteTable, 0, 256 * sizeof(uint2), c->stream));
+            paletteNumberKernel<<<1, 256, 0, c->stream>>>(dTable, dSlotIndex, c->dPaletteTable);
+            paletteIndexKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, n, dTable, dSlotIndex, c->dPalette);
+            CU_CHECK(c, cudaGetLastError());
+            CU_CHECK(c, cudaStreamSynchronize(c->stream));
+            palette = true;
+        }
+        cudaFree(dTable);
+        cudaFree(dSlotIndex);
+    }
+    if (!palette) {
+        CU_CHECK(c, cudaMalloc(&c->dVoxels, n * sizeof(uint2)));
+        packVoxelsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, c->dVoxels, n);
+        CU_CHECK(c, cudaGetLastError());
+    }
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     cudaFree(dDensity);
     cudaFree(dMat);
@@ -762,9 +1085,17 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         c->world.spacing[i] = w->spacing[i];
         c->world.invSpacing[i] = 1.0f / w->spacing[i]; // IEEE single division on the host == __frcp_rn
     }
+    c->world.exactInverse = 1;
+    for (int i = 0; i < 3; ++i) {
+        int exponent = 0;
+        if (std::frexp(w->spacing[i], &exponent) != 0.5f || exponent < -60 || exponent > 60)
+            c->world.exactInverse = 0;
+    }
     for (int i = 0; i < 6; ++i)
         c->world.ext[i] = w->extent_safe[i];
     c->world.voxels = c->dVoxels;
+    c->world.palette = c->dPalette;
+    c->world.paletteTable = c->dPaletteTable;
     return DXMCB200_OK;
 }
 
@@ -775,13 +1106,14 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
         return DXMCB200_ERR_ARG;
     CU_CHECK(c, cudaSetDevice(c->device));
     const size_t nKnots = l->n_segments;
-    const size_t nCoeff = static_cast<size_t>(l->n_materials) * l->n_segments * 6;
+    const size_t nCoeffIn = static_cast<size_t>(l->n_materials) * l->n_segments * 6;
+    const size_t nCoeff = static_cast<size_t>(l->n_materials) * l->n_segments * kCoeffStride;
     const size_t nMax = static_cast<size_t>(l->n_segments) * 2;
     const size_t nRita = static_cast<size_t>(l->n_materials) * 4 * DXMCB200_RITA_N;
     const size_t nSpline = static_cast<size_t>(l->n_materials) * kSplineStride;
     const size_t nShell = static_cast<size_t>(l->n_materials) * DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS;
-    // one blob, every table 16-byte aligned
-    auto pad = [](size_t n) { return (n + 3) & ~static_cast<size_t>(3); };
+    // one blob, every table 32-byte (sector) aligned
+    auto pad = [](size_t n) { return (n + 7) & ~static_cast<size_t>(7); };
     const size_t total = pad(nKnots) + pad(nCoeff) + pad(nMax) + pad(nRita) + pad(nSpline) + pad(nShell);
     std::vector<float> blob(total, 0.0f);
     size_t off = 0;
@@ -798,7 +1130,11 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
             DXMCB200_SPLINE_FLOATS * sizeof(float));
         spline[static_cast<size_t>(m) * kSplineStride + 63] = 1.0f / l->spline[static_cast<size_t>(m) * DXMCB200_SPLINE_FLOATS + 61];
     }
-    const size_t oKnots = put(l->knots, nKnots), oCoeff = put(l->coefficients, nCoeff), oMax = put(l->max_coefficients, nMax),
+    // device coefficient records are padded from 6 to kCoeffStride floats: one aligned 32-byte sector each
+    std::vector<float> coeff(nCoeff, 0.0f);
+    for (size_t r = 0; r < nCoeffIn / 6; ++r)
+        std::memcpy(coeff.data() + r * kCoeffStride, l->coefficients + r * 6, 6 * sizeof(float));
+    const size_t oKnots = put(l->knots, nKnots), oCoeff = put(coeff.data(), nCoeff), oMax = put(l->max_coefficients, nMax),
                  oRita = put(l->rita, nRita), oSpline = put(spline.data(), nSpline), oShell = put(l->shells, nShell);
     cudaFree(c->dLutBlob);
     c->dLutBlob = nullptr;
@@ -1005,7 +1341,7 @@ int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, floa
     if (nEvents)
         CU_CHECK(c, cudaMalloc(&dEv, n * sizeof(uint32_t)));
     const float voxelVolume = c->world.spacing[0] * c->world.spacing[1] * c->world.spacing[2] / 1000.0f;
-    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, n, mode, std::ldexp(1.0f, -c->energyBits),
+    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, n, mode, std::ldexp(1.0f, -c->energyBits),
         std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, dDose, dEv, dVar);
     CU_CHECK(c, cudaGetLastError());
     if (dose)
@@ -1141,7 +1477,7 @@ int dxmcb200_eval_attenuation(dxmcb200_ctx* c, uint64_t n, const uint8_t* materi
 int dxmcb200_trace_indices(dxmcb200_ctx* c, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps,
     int64_t* outIdx, float* outEntry)
 {
-    if (!c || !c->dVoxels || !pos || !dir || !steps || !outIdx || !outEntry || nRays == 0)
+    if (!c || (!c->dVoxels && !c->dPalette) || !pos || !dir || !steps || !outIdx || !outEntry || nRays == 0)
         return DXMCB200_ERR_STATE;
     CU_CHECK(c, cudaSetDevice(c->device));
     float *dP = nullptr, *dD = nullptr, *dS = nullptr, *dEn = nullptr;
