@@ -265,7 +265,7 @@ def main():
     achieved = EXPOSURES * hist * b_alg / kernel_s_per_step / 1e9
     peak, peak_src = measured_peak()
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "generateKernel + transportKernel<1,false>", "bytes_per_history": b_alg, "lookups_per_history": L,
+                "kernel": "generateKernel + transportKernel + interactKernel<1> (whole wave pipeline)", "bytes_per_history": b_alg, "lookups_per_history": L,
                 "score_events_per_history": Sev, "steps_per_history": st["steps"] / max(st["histories"], 1),
                 "interactions_per_history": st["interactions"] / max(st["histories"], 1),
                 "kernel_ms_per_step": kernel_total_ms / args.steps, "peak_source": peak_src}

@@ -1,20 +1,24 @@
 // transport.cu — sm_100a photon-transport kernels and the C ABI runtime around them.
 //
-// Replaces the reference's worker threads (transport.hpp:729-778) by two kernels per chunk of histories:
+// Replaces the reference's worker threads (transport.hpp:729-778) by a wavefront of three kernels that hand
+// photons to each other through record buffers in HBM. Every kernel keeps all 32 lanes of a warp on ONE kind of
+// work; the divergent stages of a history (birth, stepping, interaction) never share a warp:
 //
-//   generateKernel   Exposure::sampleParticle + transportParticleToWorld (exposure.hpp:280-304,
-//                    transport.hpp:702-728, 733-741) for every history of the chunk, one history per thread
-//                    with all 32 lanes busy; photons that reach the voxel grid are compacted (warp ballot +
-//                    one atomic per warp) into 64-byte records in HBM, carrying their own counter-derived
-//                    PCG32 stream, log10(E), the LUT segment and the Woodcock majorant.
-//   transportKernel  persistent grid; every lane owns one photon at a time and re-fills from the record
-//                    buffer when its photon dies. Lanes are regrouped inside the warp by stage:
-//                      STEP      Woodcock delta tracking in a tight loop (one voxel record fetch per step)
-//                      INTERACT  a real / forced interaction is pending (photo / Compton / Rayleigh sampling,
-//                                scoring); executed only when at least `interactBatch` lanes wait (or nothing
-//                                else can run), so the rejection samplers stay off the stepping lanes' path
-//                      DEAD      re-filled as soon as `refillBatch` lanes are empty
-// Scoring is 64-bit fixed-point integer atomics, so results do not depend on scheduling.
+//   generateKernel   (a) Exposure::sampleParticle + transportParticleToWorld (exposure.hpp:280-304,
+//                    transport.hpp:702-728, 733-741), one history per thread; photons that reach the voxel grid
+//                    are compacted (warp ballot + one atomic per warp) into 64-byte photon records carrying their
+//                    own counter-derived PCG32 stream, log10(E), the LUT segment and the Woodcock majorant.
+//   transportKernel  (b) Woodcock delta tracking (transport.hpp:640-700), persistent grid. A lane steps one photon
+//                    until it leaves the world, is killed by Russian roulette, or a real / forced interaction is
+//                    due; events are appended to the event buffer as 80-byte records, and the lane re-fills from
+//                    the photon buffer through a per-warp cp.async ring in shared memory.
+//   interactKernel   (c)+(d) computeInteractions[Forced] (transport.hpp:523-638): photoelectric / Compton /
+//                    Rayleigh sampling against the LUTs, 64-bit fixed-point scoring, Russian roulette; surviving
+//                    photons are compacted into the NEXT wave's photon buffer.
+//
+// One wave = births + survivors of the previous wave, at most `waveRecords` photons; the host tops every wave up
+// with new births until all histories are issued and then drains. Scoring is integer atomics and every history
+// carries its own random stream, so results do not depend on the wave size, scheduling or GPU partition.
 #include "physics.cuh"
 
 #include <algorithm>
@@ -33,23 +37,40 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
-enum LaneState : uint32_t { DEAD = 0, STEP = 1, INTERACT = 2, EXHAUSTED = 3 };
+enum LaneState : uint32_t { DEAD = 0, STEP = 1, EVENT = 2, EXHAUSTED = 3 };
 
 struct Counters {
     unsigned long long histories, inWorld, steps, lookups, interactions, scores;
 };
 
-// one in-flight photon as the generation kernel hands it to the transport kernel: 4 x 16 bytes
+// one in-flight photon between kernels: 4 x 16 bytes
 struct alignas(16) PhotonRecord {
     float4 posE; // px py pz energy
     float4 dirW; // dx dy dz weight
     uint4 rng; // state lo/hi, increment lo/hi
-    float4 lut; // log10(E), 1/majorant, LUT segment (bits), unused
+    float4 lut; // log10(E), 1/majorant, LUT segment (bits), event probability (event records only)
 };
 
-struct ChunkCursor {
-    unsigned int stored; // records written by generateKernel
-    unsigned int taken; // records claimed by transportKernel
+// a photon with an interaction due: 5 x 16 bytes
+struct alignas(16) EventRecord {
+    PhotonRecord photon;
+    uint4 where; // voxel index, material | measurement << 8 (kNoEvent marks an unused slot), 0, 0
+};
+constexpr uint32_t kNoEvent = 0xffffffffu;
+
+// Every buffer is split into kShards regions with their own append / claim cursors on separate 128-byte lines:
+// tens of thousands of warps appending through ONE counter serialise in a single L2 atomic unit (measured: the
+// interaction kernel spent 4 of its 4.4 ms queueing on it); spread over 64 addresses the cost disappears.
+constexpr unsigned kShards = 64;
+struct alignas(128) ShardCursor {
+    unsigned int stored; // slots appended to the region
+    unsigned int taken; // slots of the region claimed by the consumer
+    unsigned int pad[30];
+};
+struct WaveCursors {
+    ShardCursor photons[2][kShards];
+    ShardCursor events[kShards];
+    ShardCursor overflow; // .stored != 0: a region was too small, the run is invalid
 };
 
 struct KernelParams {
@@ -61,14 +82,20 @@ struct KernelParams {
     uint64_t expBegin; // first exposure of the run's range
     uint32_t nExp;
     uint32_t uniformHistories; // >0: every exposure of the range has this many histories (< 2^31)
-    uint64_t chunkBegin; // first history of the chunk, counted from the start of the range
-    uint32_t chunkCount; // histories in the chunk
+    uint64_t chunkBegin; // first history generateKernel makes, counted from the start of the range
+    uint32_t chunkCount; // histories generateKernel makes
     uint32_t chunkFirstExposure; // uniform case: exposure (relative to expBegin) holding chunkBegin ...
     uint32_t chunkFirstOffset; // ... and chunkBegin's history index inside it
-    uint32_t refillBatch, interactBatch;
+    uint32_t refillBatch; // lanes that must be empty before a warp stops stepping to re-fill
     uint64_t seed;
-    PhotonRecord* photons;
-    ChunkCursor* cursor;
+    PhotonRecord* photonsIn; // wave being transported: kShards regions of photonRegion records
+    ShardCursor* inCursors;
+    PhotonRecord* photonsOut; // next wave: generateKernel and interactKernel append here
+    ShardCursor* outCursors;
+    EventRecord* events; // kShards regions of eventRegion slots, claimed in tiles of kEventTile
+    ShardCursor* eventCursors;
+    unsigned int* overflow;
+    uint32_t photonRegion, eventRegion;
     unsigned long long* acc; // [nVoxels][4]
     Counters* counters;
     float energyScale, energySqScale;
@@ -80,6 +107,27 @@ __device__ __forceinline__ unsigned long long warpSum(uint32_t v)
     for (int o = 16; o > 0; o >>= 1)
         s += __shfl_xor_sync(kFull, s, o);
     return s;
+}
+
+// Append the photons of the lanes in `mask` to the warp's shard of the output wave; returns the record to write
+// (nullptr for lanes outside the mask, or when the region is full, which invalidates the run).
+__device__ __forceinline__ PhotonRecord* appendPhotons(const KernelParams& P, unsigned mask, unsigned lane)
+{
+    const unsigned shard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
+    unsigned base = 0;
+    const int leader = __ffs(mask) - 1;
+    const unsigned n = __popc(mask);
+    if (static_cast<int>(lane) == leader)
+        base = atomicAdd(&P.outCursors[shard].stored, n);
+    base = __shfl_sync(kFull, base, leader);
+    if (base + n > P.photonRegion) {
+        if (static_cast<int>(lane) == leader)
+            atomicExch(P.overflow, 1u);
+        return nullptr;
+    }
+    if (!((mask >> lane) & 1u))
+        return nullptr;
+    return P.photonsOut + (static_cast<size_t>(shard) * P.photonRegion + base + __popc(mask & ((1u << lane) - 1u)));
 }
 
 // everything about a photon that only changes with its energy: log10(E) correctly rounded, the LUT segment it
@@ -136,16 +184,11 @@ __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant
         const unsigned keepMask = __ballot_sync(kFull, keep);
         if (keepMask == 0)
             continue;
-        unsigned base = 0;
-        const int leader = __ffs(keepMask) - 1;
-        if (static_cast<int>(lane) == leader)
-            base = atomicAdd(&P.cursor->stored, static_cast<unsigned>(__popc(keepMask)));
-        base = __shfl_sync(kFull, base, leader);
-        if (keep) {
+        PhotonRecord* r = appendPhotons(P, keepMask, lane);
+        if (r) {
             float logE, maxAttInv;
             uint32_t seg;
             energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
-            PhotonRecord* r = P.photons + (base + __popc(keepMask & laneLt));
             r->posE = make_float4(p.px, p.py, p.pz, p.energy);
             r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
             r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
@@ -257,8 +300,9 @@ __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p,
 
 // ---- (b) Woodcock delta tracking + (c) interactions + (d) scoring ---------------------------------
 // ---- record staging: global -> shared with cp.async (LDGSTS), so a re-fill never waits on HBM ------
-constexpr unsigned kTile = 256; // records a warp claims with one atomic
+constexpr unsigned kTile = 256; // photon records a warp claims with one atomic
 constexpr unsigned kGroup = 16; // records per cp.async group; the ring holds two groups per warp
+constexpr unsigned kEventTile = 64; // event slots a warp claims with one atomic
 
 __device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
 {
@@ -272,9 +316,9 @@ __device__ __forceinline__ void cpAsyncWait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// ---- (b) Woodcock delta tracking + (c) interactions + (d) scoring ---------------------------------
-template <int L, bool kStats>
-__global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constant__ KernelParams P)
+// ---- (b) Woodcock delta tracking (transport.hpp:640-700) -------------------------------------------
+template <bool kStats>
+__global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_constant__ KernelParams P)
 {
     __shared__ PhotonRecord ring[kThreads / 32][2 * kGroup];
     __shared__ unsigned stage[kThreads / 32][8];
@@ -282,7 +326,7 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
-    const unsigned nRecords = P.cursor->stored; // generateKernel of this chunk has completed (stream order)
+    const unsigned myShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
     PhotonRecord* const myRing = ring[threadIdx.x >> 5];
     const bool paletteForm = P.world.palette != nullptr;
     if (paletteForm) {
@@ -292,48 +336,59 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
 
     Rng rng { 0, 1 };
     Photon p {};
-    Pending pe {};
-    float logE = 0.0f, maxAttInv = 0.0f;
-    uint32_t seg = 0;
+    float logE = 0.0f, maxAttInv = 0.0f, eventProbability = 0.0f;
+    uint32_t seg = 0, voxel = 0, material = 0;
     bool lowWeight = false; // E*w below the Russian-roulette threshold (transport.hpp:684)
     uint32_t state = DEAD;
-    uint32_t cSteps = 0, cLookups = 0, cInter = 0, cScores = 0;
+    uint32_t cSteps = 0, cLookups = 0;
 
     // -ln(r)*maxAttInv*10 (transport.hpp:655-657) is evaluated as lg2(r) * kStepScale * maxAttInv; cm -> mm is the factor 10
     constexpr float kStepScale = -6.931471805599453f;
 
-    // warp-uniform staging state, kept in shared memory so it costs no registers in the stepping loop: the warp
-    // claims tiles of kTile records, streams them through its ring in groups of kGroup (group k lives in ring half
-    // k & 1) and hands the records of the oldest group to empty lanes. Every lane executes the same updates.
-    enum { TILE_NEXT, TILE_END, TILES_LEFT, ISSUED, CONSUMED, COUNT0, COUNT1, OFFSET };
+    // ---- staging, all warp-uniform. Input: the warp claims tiles of kTile records from the shards of the wave and
+    // streams them through its ring in groups of kGroup records (group k lives in ring half k & 1); empty lanes take
+    // records from the current group. Output: event slots are claimed in tiles of kEventTile. The four values every
+    // service needs live in registers, the rest of the bookkeeping (touched once per group / tile) in shared memory.
+    unsigned ringPos = 0, ringEnd = 0; // ring slots of the current group not yet handed out: [ringPos, ringEnd)
+    unsigned outPos = 0, outEnd = 0; // event slots of the current tile not yet written
+    unsigned exhaustedMask = 0;
+    enum { TILE_NEXT, TILE_END, SHARDS_TRIED, ISSUED, CONSUMED, COUNT0, COUNT1, IN_SHARD };
     volatile unsigned* const st = stage[threadIdx.x >> 5];
     if (lane < 8)
-        st[lane] = lane == TILES_LEFT ? 1u : 0u;
+        st[lane] = lane == IN_SHARD ? myShard : 0u;
     __syncwarp();
 
+    // request the next group of records into the free half of the ring (no-op when both halves are in flight)
     auto issueGroup = [&]() {
         const unsigned issued = st[ISSUED];
         if (issued - st[CONSUMED] >= 2)
             return;
         unsigned tileNext = st[TILE_NEXT], tileEnd = st[TILE_END];
-        if (tileNext >= tileEnd) {
-            if (!st[TILES_LEFT])
-                return;
-            unsigned t = 0;
-            if (lane == 0)
-                t = atomicAdd(&P.cursor->taken, kTile);
-            t = __shfl_sync(kFull, t, 0);
-            if (t >= nRecords) {
-                st[TILES_LEFT] = 0;
-                return;
+        if (tileNext >= tileEnd) { // claim the next tile: from the warp's own shard first, then round the others
+            unsigned tried = st[SHARDS_TRIED], shard = st[IN_SHARD];
+            for (;;) {
+                if (tried >= kShards)
+                    return;
+                const unsigned n = min(P.inCursors[shard].stored, P.photonRegion); // filled by completed kernels
+                unsigned t = n;
+                if (lane == 0 && n)
+                    t = atomicAdd(&P.inCursors[shard].taken, kTile);
+                t = __shfl_sync(kFull, t, 0);
+                if (t < n) {
+                    tileNext = shard * P.photonRegion + t;
+                    tileEnd = shard * P.photonRegion + min(t + kTile, n);
+                    break;
+                }
+                shard = (shard + 1) % kShards;
+                ++tried;
+                st[IN_SHARD] = shard;
+                st[SHARDS_TRIED] = tried;
             }
-            tileNext = t;
-            tileEnd = min(t + kTile, nRecords);
             st[TILE_END] = tileEnd;
         }
         const unsigned half = issued & 1u;
         const unsigned cnt = min(kGroup, tileEnd - tileNext);
-        const char* src = reinterpret_cast<const char*>(P.photons + tileNext);
+        const char* src = reinterpret_cast<const char*>(P.photonsIn + tileNext);
         char* dst = reinterpret_cast<char*>(myRing + half * kGroup);
 #pragma unroll
         for (unsigned t = 0; t < (kGroup * sizeof(PhotonRecord) / 16) / 32; ++t) {
@@ -346,146 +401,240 @@ __global__ void __launch_bounds__(kThreads) transportKernel(const __grid_constan
         st[TILE_NEXT] = tileNext + kGroup;
         st[ISSUED] = issued + 1;
     };
+    // make the oldest requested group the current one; false when the wave is drained
+    auto openGroup = [&]() {
+        const unsigned issued = st[ISSUED], consumed = st[CONSUMED];
+        if (issued == consumed)
+            return false;
+        if (issued - consumed == 2)
+            cpAsyncWait<1>(); // the older of the two groups in flight has landed
+        else
+            cpAsyncWait<0>();
+        __syncwarp();
+        const unsigned half = consumed & 1u;
+        ringPos = half * kGroup;
+        ringEnd = ringPos + st[COUNT0 + half];
+        return true;
+    };
     issueGroup();
     issueGroup();
+    openGroup();
 
     for (;;) {
-        // ---- pending interactions, batched: computeInteractions[Forced] + Russian roulette (transport.hpp:667-693)
-        const unsigned stepMask = __ballot_sync(kFull, state == STEP);
-        const unsigned intMask = __ballot_sync(kFull, state == INTERACT);
-        if (intMask && (static_cast<unsigned>(__popc(intMask)) >= P.interactBatch || stepMask == 0)) {
-            if (state == INTERACT) {
-                bool energyChanged = false;
-                bool alive;
-                if (pe.material & 0xff00u)
-                    alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+        // ---- one Woodcock step (transport.hpp:655-682)
+        if (state == STEP) {
+            const float r1 = rng.uniform();
+            advance(p, (fastLog2(r1) * kStepScale) * maxAttInv);
+            if constexpr (kStats)
+                ++cSteps;
+            if (!insideWorld(P.world, p.px, p.py, p.pz)) {
+                state = DEAD;
+            } else {
+                voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+                uint2 rec;
+                // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
+                if (paletteForm)
+                    rec = sPalette[__ldcg(P.world.palette + voxel)];
                 else
-                    alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+                    rec = __ldcg(P.world.voxels + voxel);
+                const float density = __uint_as_float(rec.x);
+                material = rec.y;
                 if constexpr (kStats)
-                    ++cInter;
-                if (alive && p.energy * p.weight < kRouletteThreshold) {
+                    ++cLookups;
+                float aP, aC, aR;
+                attenuationAt(P.lut, material & 0xffu, seg, logE, aP, aC, aR);
+                const float attTotal = (((0.0f + aP) + aC) + aR) * density;
+                eventProbability = attTotal * maxAttInv;
+                bool event = (material & 0xff00u) != 0; // measurement voxel: forced interaction, no draw
+                if (!event)
+                    event = rng.uniform() < eventProbability;
+                if (event) {
+                    state = EVENT;
+                } else if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
                     const float r4 = rng.uniform();
                     if (r4 < kRouletteProbability) {
-                        alive = false;
+                        state = DEAD;
                     } else {
                         constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
                         p.weight *= factor;
+                        lowWeight = p.energy * p.weight < kRouletteThreshold;
                     }
-                }
-                if (alive) {
-                    state = STEP;
-                    if (energyChanged)
-                        energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
-                    lowWeight = p.energy * p.weight < kRouletteThreshold;
-                } else {
-                    state = DEAD;
                 }
             }
         }
+        const unsigned eventMask = __ballot_sync(kFull, state == EVENT);
+        unsigned deadMask = __ballot_sync(kFull, state == DEAD);
+        const unsigned idle = eventMask | deadMask;
+        if (static_cast<unsigned>(__popc(idle)) < P.refillBatch && (idle | exhaustedMask) != kFull)
+            continue; // keep stepping until enough lanes are empty
 
-        // ---- re-fill empty lanes from the oldest staged group
-        const unsigned deadMask = __ballot_sync(kFull, state == DEAD);
-        if (deadMask) {
-            const unsigned issued = st[ISSUED], consumed = st[CONSUMED];
-            if (consumed == issued) { // nothing staged: only possible when the record buffer is drained
+        // ---- lanes with an interaction due append their photon to the event buffer and become empty
+        if (eventMask) {
+            const unsigned n = __popc(eventMask);
+            const unsigned room = outEnd - outPos;
+            const unsigned first = outPos;
+            unsigned fresh = 0; // first slot of a newly claimed tile, when the current one cannot take all n
+            bool full = false;
+            if (n > room) {
+                if (lane == 0)
+                    fresh = atomicAdd(&P.eventCursors[myShard].stored, kEventTile);
+                fresh = __shfl_sync(kFull, fresh, 0);
+                full = fresh + kEventTile > P.eventRegion;
+                if (full && lane == 0)
+                    atomicExch(P.overflow, 1u);
+                fresh += myShard * P.eventRegion;
+                if (!full) {
+                    outPos = fresh + (n - room);
+                    outEnd = fresh + kEventTile;
+                }
+            } else {
+                outPos += n;
+            }
+            if (state == EVENT) {
+                const unsigned rank = __popc(eventMask & laneLt);
+                EventRecord* e = P.events + (rank < room ? first + rank : fresh + (rank - room));
+                if (full && rank >= room)
+                    e = P.events; // region overflow: the run is flagged invalid, keep the store in bounds
+                e->photon.posE = make_float4(p.px, p.py, p.pz, p.energy);
+                e->photon.dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+                e->photon.rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32),
+                    static_cast<uint32_t>(rng.inc), static_cast<uint32_t>(rng.inc >> 32));
+                e->photon.lut = make_float4(logE, maxAttInv, __uint_as_float(seg), eventProbability);
+                e->where = make_uint4(voxel, material, 0u, 0u);
+                state = DEAD;
+            }
+            deadMask |= eventMask;
+        }
+
+        // ---- re-fill empty lanes from the ring (a second pass when the current group runs out half-way)
+#pragma unroll 1
+        for (int pass = 0; pass < 3 && deadMask; ++pass) {
+            if (ringPos == ringEnd) { // drained: nothing left to hand out in this wave
                 if (state == DEAD)
                     state = EXHAUSTED;
-            } else {
-                if (issued - consumed == 2)
-                    cpAsyncWait<1>(); // the older of the two groups in flight has landed
-                else
-                    cpAsyncWait<0>();
-                __syncwarp();
-                const unsigned half = consumed & 1u;
-                const unsigned count = st[COUNT0 + half], offset = st[OFFSET];
-                const unsigned avail = count - offset;
-                const unsigned rank = __popc(deadMask & laneLt);
-                if (state == DEAD && rank < avail) {
-                    const PhotonRecord* r = myRing + half * kGroup + offset + rank;
-                    const float4 a = r->posE, b = r->dirW, d = r->lut;
-                    const uint4 c = r->rng;
-                    p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
-                    p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
-                    rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
-                    rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
-                    logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
-                    lowWeight = p.energy * p.weight < kRouletteThreshold;
-                    state = STEP;
-                }
-                __syncwarp(); // every lane has read its record before the half is requested again
-                const unsigned taken = min(avail, static_cast<unsigned>(__popc(deadMask)));
-                if (offset + taken == count) {
-                    st[CONSUMED] = consumed + 1;
-                    st[OFFSET] = 0;
-                    issueGroup();
-                } else {
-                    st[OFFSET] = offset + taken;
-                }
-            }
-        }
-        if (__ballot_sync(kFull, state == STEP || state == INTERACT || state == DEAD) == 0)
-            break;
-
-        // ---- Woodcock steps (transport.hpp:655-682) until enough lanes wait for a re-fill or an interaction
-        for (;;) {
-            if (state == STEP) {
-                const float r1 = rng.uniform();
-                advance(p, (fastLog2(r1) * kStepScale) * maxAttInv);
-                if constexpr (kStats)
-                    ++cSteps;
-                if (!insideWorld(P.world, p.px, p.py, p.pz)) {
-                    state = DEAD;
-                } else {
-                    const uint32_t voxel = voxelIndex(P.world, p.px, p.py, p.pz);
-                    uint2 rec;
-                    if (paletteForm)
-                        rec = sPalette[__ldg(P.world.palette + voxel)];
-                    else
-                        rec = __ldg(P.world.voxels + voxel);
-                    const float density = __uint_as_float(rec.x);
-                    if constexpr (kStats)
-                        ++cLookups;
-                    // a stepping lane has no interaction pending, so the pending-event registers are free to hold
-                    // this step's values; they simply stay put when the lane leaves the loop with an event
-                    pe.voxel = voxel;
-                    pe.material = rec.y;
-                    attenuationAt(P.lut, rec.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
-                    const float attTotal = (((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh) * density;
-                    pe.eventProbability = attTotal * maxAttInv;
-                    bool event = (rec.y & 0xff00u) != 0; // measurement voxel: forced interaction, no draw
-                    if (!event)
-                        event = rng.uniform() < pe.eventProbability;
-                    if (event) {
-                        state = INTERACT;
-                    } else if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
-                        const float r4 = rng.uniform();
-                        if (r4 < kRouletteProbability) {
-                            state = DEAD;
-                        } else {
-                            constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
-                            p.weight *= factor;
-                            lowWeight = p.energy * p.weight < kRouletteThreshold;
-                        }
-                    }
-                }
-            }
-            const unsigned dead = __ballot_sync(kFull, state == DEAD);
-            const unsigned pend = __ballot_sync(kFull, state == INTERACT);
-            const unsigned stepping = __ballot_sync(kFull, state == STEP);
-            if (static_cast<unsigned>(__popc(dead)) >= P.refillBatch || static_cast<unsigned>(__popc(pend)) >= P.interactBatch || stepping == 0)
+                exhaustedMask |= deadMask;
                 break;
+            }
+            const unsigned rank = __popc(deadMask & laneLt);
+            if (state == DEAD && rank < ringEnd - ringPos) {
+                const PhotonRecord* r = myRing + ringPos + rank;
+                const float4 a = r->posE, b = r->dirW, d = r->lut;
+                const uint4 c = r->rng;
+                p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
+                p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
+                rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
+                rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
+                logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
+                lowWeight = p.energy * p.weight < kRouletteThreshold;
+                state = STEP;
+            }
+            ringPos = min(ringEnd, ringPos + static_cast<unsigned>(__popc(deadMask)));
+            deadMask = __ballot_sync(kFull, state == DEAD);
+            if (ringPos == ringEnd) { // group handed out completely: recycle its half, move on to the next group
+                __syncwarp(); // every lane has read its record before the half is requested again
+                st[CONSUMED] = st[CONSUMED] + 1;
+                issueGroup();
+                openGroup(); // leaves ringPos == ringEnd when the wave is drained
+            }
         }
+        if (exhaustedMask == kFull)
+            break;
     }
     cpAsyncWait<0>();
+    // mark the unused slots of the warp's last event tile
+    for (unsigned slot = outPos + lane; slot < outEnd; slot += 32)
+        P.events[slot].where = make_uint4(0u, kNoEvent, 0u, 0u);
 
     if constexpr (kStats) {
-        const unsigned long long s = warpSum(cSteps), l = warpSum(cLookups), i = warpSum(cInter), sc = warpSum(cScores);
+        const unsigned long long s = warpSum(cSteps), l = warpSum(cLookups);
         if (lane == 0) {
             atomicAdd(&P.counters->steps, s);
             atomicAdd(&P.counters->lookups, l);
+        }
+    }
+}
+
+// ---- (c) interactions + (d) scoring: one event per thread ------------------------------------------
+template <int L, bool kStats>
+__global__ void __launch_bounds__(kThreads) interactKernel(const __grid_constant__ KernelParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const unsigned laneLt = (1u << lane) - 1u;
+    uint32_t cInter = 0, cScores = 0;
+    // block b works on event shard b % kShards together with the other blocks of the same residue
+    const unsigned blocksPerShard = gridDim.x / kShards; // the grid is a multiple of kShards
+    const unsigned shard = blockIdx.x % kShards;
+    const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion); // a multiple of kEventTile
+    const EventRecord* const region = P.events + static_cast<size_t>(shard) * P.eventRegion;
+    for (unsigned i = (blockIdx.x / kShards) * kThreads + threadIdx.x; i < nSlots; i += blocksPerShard * kThreads) {
+        const EventRecord* e = region + i;
+        const uint4 where = e->where;
+        bool alive = false;
+        Photon p {};
+        Rng rng { 0, 1 };
+        float logE = 0.0f, maxAttInv = 0.0f;
+        uint32_t seg = 0;
+        if (where.y != kNoEvent) {
+            const float4 a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
+            const uint4 c = e->photon.rng;
+            p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
+            p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
+            rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
+            rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
+            logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
+            Pending pe;
+            pe.eventProbability = d.w;
+            pe.voxel = where.x;
+            pe.material = where.y;
+            attenuationAt(P.lut, where.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
+            bool energyChanged = false;
+            if (where.y & 0xff00u)
+                alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+            else
+                alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+            if constexpr (kStats)
+                ++cInter;
+            // Russian roulette (transport.hpp:684-693)
+            if (alive && p.energy * p.weight < kRouletteThreshold) {
+                const float r4 = rng.uniform();
+                if (r4 < kRouletteProbability) {
+                    alive = false;
+                } else {
+                    constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+                    p.weight *= factor;
+                }
+            }
+            if (alive && energyChanged)
+                energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+        }
+        const unsigned aliveMask = __ballot_sync(kFull, alive);
+        if (aliveMask == 0)
+            continue;
+        PhotonRecord* r = appendPhotons(P, aliveMask, lane);
+        if (r) {
+            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
+            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                static_cast<uint32_t>(rng.inc >> 32));
+            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
+        }
+    }
+    if constexpr (kStats) {
+        const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
+        if (lane == 0) {
             atomicAdd(&P.counters->interactions, i);
             atomicAdd(&P.counters->scores, sc);
         }
+    }
+}
+
+// reset the cursors of one buffer between waves
+__global__ void resetCursorsKernel(ShardCursor* cursors, int storedToo)
+{
+    if (threadIdx.x < kShards) {
+        cursors[threadIdx.x].taken = 0;
+        if (storedToo)
+            cursors[threadIdx.x].stored = 0;
     }
 }
 
@@ -754,16 +903,18 @@ struct dxmcb200_ctx {
     uint64_t* dPrefix = nullptr;
     uint64_t prefixCapacity = 0;
 
-    // photon record buffer between generateKernel and transportKernel, one chunk of histories at a time
-    PhotonRecord* dPhotons = nullptr;
-    uint64_t photonCapacity = 0;
-    ChunkCursor* dCursor = nullptr;
+    // wave buffers: two photon buffers (ping-pong) and the event buffer between transportKernel and interactKernel
+    PhotonRecord* dPhotons[2] = { nullptr, nullptr };
+    EventRecord* dEvents = nullptr;
+    uint64_t photonRegion = 0, eventRegion = 0; // slots per shard region of the photon / event buffers
+    WaveCursors* hCursors = nullptr; // pinned host copy for the per-wave read-back
+    WaveCursors* dCursors = nullptr;
     Counters* dCounters = nullptr;
 
     int energyBits = 20, energySqBits = 10;
     bool collectStats = false;
-    uint32_t chunkHistories = 1u << 25; // histories per generate/transport launch pair (2 GiB of records)
-    uint32_t refillBatch = 4, interactBatch = 8; // lanes that must wait before a re-fill / interaction stage runs
+    uint32_t waveRecords = 1u << 25; // photons per wave (2 GiB per photon buffer, 2.5 GiB of event records)
+    uint32_t refillBatch = 4; // empty lanes that make a warp stop stepping and re-fill
 
     double lastRunMs = 0, totalMs = 0;
     uint64_t launches = 0;
@@ -799,7 +950,7 @@ T* advancePtr(char*& cursor, size_t count)
 
 // persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
 template <typename K>
-cudaError_t launchPersistent(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items)
+cudaError_t launchPersistent(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items, unsigned* blocksOut = nullptr)
 {
     int blocksPerSm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
@@ -807,17 +958,39 @@ cudaError_t launchPersistent(const dxmcb200_ctx* c, K kernel, const KernelParams
         return e;
     uint64_t blocks = static_cast<uint64_t>(c->smCount) * std::max(blocksPerSm, 1);
     blocks = std::max<uint64_t>(1, std::min(blocks, (items + kThreads - 1) / kThreads));
+    if (blocksOut)
+        *blocksOut = static_cast<unsigned>(blocks);
+    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
+    return cudaGetLastError();
+}
+
+// interactKernel assigns block b to event shard b % kShards, so its grid is a multiple of kShards
+template <typename K>
+cudaError_t launchSharded(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items)
+{
+    int blocksPerSm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
+    if (e != cudaSuccess)
+        return e;
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * std::max(blocksPerSm, 1);
+    blocks = std::min(blocks, (items + kThreads - 1) / kThreads);
+    blocks = std::max<uint64_t>(1, (blocks + kShards - 1) / kShards) * kShards;
     kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
     return cudaGetLastError();
 }
 
 template <int L>
-cudaError_t launchChunk(const dxmcb200_ctx* c, const KernelParams& P)
+cudaError_t launchInteract(const dxmcb200_ctx* c, const KernelParams& P, uint64_t items)
 {
-    cudaError_t e = c->collectStats ? launchPersistent(c, generateKernel<true>, P, P.chunkCount) : launchPersistent(c, generateKernel<false>, P, P.chunkCount);
-    if (e != cudaSuccess)
-        return e;
-    return c->collectStats ? launchPersistent(c, transportKernel<L, true>, P, P.chunkCount) : launchPersistent(c, transportKernel<L, false>, P, P.chunkCount);
+    return c->collectStats ? launchSharded(c, interactKernel<L, true>, P, items) : launchSharded(c, interactKernel<L, false>, P, items);
+}
+
+unsigned maxTransportBlocks(const dxmcb200_ctx* c)
+{
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, transportKernel<false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, transportKernel<true>, kThreads, 0);
+    return static_cast<unsigned>(c->smCount) * static_cast<unsigned>(std::max({ a, b, 1 }));
 }
 
 int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmcb200_exposure* devExposures, uint64_t expBegin,
@@ -859,13 +1032,24 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     }
     CU_CHECK(c, cudaMemcpyAsync(c->dPrefix, prefix.data(), prefix.size() * sizeof(uint64_t), cudaMemcpyHostToDevice, c->stream));
 
-    const uint64_t chunk = std::min<uint64_t>(c->chunkHistories, total);
-    if (chunk > c->photonCapacity) {
-        cudaFree(c->dPhotons);
-        c->dPhotons = nullptr;
-        c->photonCapacity = 0;
-        CU_CHECK(c, cudaMalloc(&c->dPhotons, chunk * sizeof(PhotonRecord)));
-        c->photonCapacity = chunk;
+    // wave buffers sized for this run (kept for the next one when large enough): kShards regions each, with 50 %
+    // head-room over an even split (shards fill evenly: every warp appends to shard `global warp index % kShards`)
+    const uint64_t wave = std::max<uint64_t>(std::min<uint64_t>(c->waveRecords, total), 1024);
+    const uint64_t warpsPerShard = (static_cast<uint64_t>(maxTransportBlocks(c)) * (kThreads / 32) + kShards - 1) / kShards;
+    const uint64_t photonRegion = ((wave + wave / 2) / kShards + 1024 + 15) & ~15ULL;
+    const uint64_t eventRegion = (photonRegion + warpsPerShard * kEventTile + kEventTile - 1) / kEventTile * kEventTile;
+    if (photonRegion > c->photonRegion || eventRegion > c->eventRegion) {
+        cudaFree(c->dPhotons[0]);
+        cudaFree(c->dPhotons[1]);
+        cudaFree(c->dEvents);
+        c->dPhotons[0] = c->dPhotons[1] = nullptr;
+        c->dEvents = nullptr;
+        c->photonRegion = c->eventRegion = 0;
+        CU_CHECK(c, cudaMalloc(&c->dPhotons[0], photonRegion * kShards * sizeof(PhotonRecord)));
+        CU_CHECK(c, cudaMalloc(&c->dPhotons[1], photonRegion * kShards * sizeof(PhotonRecord)));
+        CU_CHECK(c, cudaMalloc(&c->dEvents, eventRegion * kShards * sizeof(EventRecord)));
+        c->photonRegion = photonRegion;
+        c->eventRegion = eventRegion;
     }
 
     KernelParams P {};
@@ -878,53 +1062,90 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     P.nExp = static_cast<uint32_t>(nExp);
     P.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
     P.refillBatch = c->refillBatch;
-    P.interactBatch = c->interactBatch;
     P.seed = seed;
-    P.photons = c->dPhotons;
-    P.cursor = c->dCursor;
+    P.events = c->dEvents;
+    P.eventCursors = c->dCursors->events;
+    P.overflow = &c->dCursors->overflow.stored;
+    P.photonRegion = static_cast<uint32_t>(c->photonRegion);
+    P.eventRegion = static_cast<uint32_t>(c->eventRegion);
     P.acc = c->dAcc;
     P.counters = c->dCounters;
     P.energyScale = std::ldexp(1.0f, c->energyBits);
     P.energySqScale = std::ldexp(1.0f, c->energySqBits);
 
-    uint64_t expDone = 0; // exposures of the range completely transported, for the progress callback
+    uint64_t issuedHistories = 0; // births generated so far
+    uint64_t expDone = 0; // exposures of the range whose histories have all been issued, for the progress callback
+    unsigned survivors = 0; // photons waiting in the current buffer
+    int cur = 0;
+    CU_CHECK(c, cudaMemsetAsync(c->dCursors, 0, sizeof(WaveCursors), c->stream));
+    if (!c->hCursors)
+        CU_CHECK(c, cudaMallocHost(&c->hCursors, sizeof(WaveCursors)));
     CU_CHECK(c, cudaEventRecord(c->evStart, c->stream));
-    uint64_t sinceSync = 0;
-    for (uint64_t h0 = 0; h0 < total; h0 += chunk) {
+    while (issuedHistories < total || survivors > 0) {
         if (cancel && *cancel) {
             cudaStreamSynchronize(c->stream);
             return DXMCB200_ERR_CANCELLED;
         }
-        P.chunkBegin = h0;
-        P.chunkCount = static_cast<uint32_t>(std::min<uint64_t>(chunk, total - h0));
-        if (uniform) {
-            P.chunkFirstExposure = static_cast<uint32_t>(h0 / P.uniformHistories);
-            P.chunkFirstOffset = static_cast<uint32_t>(h0 % P.uniformHistories);
-        }
-        CU_CHECK(c, cudaMemsetAsync(c->dCursor, 0, sizeof(ChunkCursor), c->stream));
-        const cudaError_t le = model == 0 ? launchChunk<0>(c, P) : model == 1 ? launchChunk<1>(c, P) : launchChunk<2>(c, P);
-        CU_CHECK(c, le);
-        c->launches += 2;
-        sinceSync += P.chunkCount;
-        // progress / cancellation need the host in the loop now and then; otherwise chunks are queued back to back
-        if ((cb || cancel) && sinceSync >= (1ULL << 28)) {
-            CU_CHECK(c, cudaStreamSynchronize(c->stream));
-            sinceSync = 0;
-            if (cb) {
-                const uint64_t done = h0 + P.chunkCount;
-                while (expDone < nExp && prefix[expDone + 1] <= done)
-                    ++expDone;
-                cb(expDone, user);
+        const int nxt = cur ^ 1;
+        // (a) top the wave up with births
+        const uint64_t births = std::min<uint64_t>(wave - survivors, total - issuedHistories);
+        P.photonsOut = c->dPhotons[cur];
+        P.outCursors = c->dCursors->photons[cur];
+        if (births > 0) {
+            P.chunkBegin = issuedHistories;
+            P.chunkCount = static_cast<uint32_t>(births);
+            if (uniform) {
+                P.chunkFirstExposure = static_cast<uint32_t>(issuedHistories / P.uniformHistories);
+                P.chunkFirstOffset = static_cast<uint32_t>(issuedHistories % P.uniformHistories);
             }
+            CU_CHECK(c, c->collectStats ? launchPersistent(c, generateKernel<true>, P, births) : launchPersistent(c, generateKernel<false>, P, births));
+            issuedHistories += births;
+            ++c->launches;
+        }
+        // (b) step every photon of the wave to its next event
+        const uint64_t records = survivors + births; // upper bound: births that miss the world store nothing
+        P.photonsIn = c->dPhotons[cur];
+        P.inCursors = c->dCursors->photons[cur];
+        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->photons[cur], 0);
+        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->events, 1);
+        CU_CHECK(c, c->collectStats ? launchPersistent(c, transportKernel<true>, P, records) : launchPersistent(c, transportKernel<false>, P, records));
+        // (c)+(d) interactions and scoring; survivors open the next wave
+        P.photonsOut = c->dPhotons[nxt];
+        P.outCursors = c->dCursors->photons[nxt];
+        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->photons[nxt], 1);
+        CU_CHECK(c, model == 0 ? launchInteract<0>(c, P, records) : model == 1 ? launchInteract<1>(c, P, records) : launchInteract<2>(c, P, records));
+        c->launches += 2;
+        CU_CHECK(c, cudaMemcpyAsync(c->hCursors->photons[nxt], c->dCursors->photons[nxt], sizeof(ShardCursor) * kShards, cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaMemcpyAsync(&c->hCursors->overflow, &c->dCursors->overflow, sizeof(ShardCursor), cudaMemcpyDeviceToHost, c->stream));
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        if (c->hCursors->overflow.stored) {
+            c->error = "wave buffer region overflow";
+            return DXMCB200_ERR_STATE;
+        }
+        uint64_t alive = 0;
+        for (unsigned k = 0; k < kShards; ++k)
+            alive += c->hCursors->photons[nxt][k].stored;
+        survivors = static_cast<unsigned>(alive);
+        if (survivors > wave) {
+            c->error = "wave buffer overflow";
+            return DXMCB200_ERR_STATE;
+        }
+        cur = nxt;
+        if (cb) {
+            const uint64_t before = expDone;
+            while (expDone < nExp && prefix[expDone + 1] <= issuedHistories)
+                ++expDone;
+            if (expDone != before && !(expDone == nExp && survivors > 0))
+                cb(expDone, user);
         }
     }
     CU_CHECK(c, cudaEventRecord(c->evStop, c->stream));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream)); // also keeps `prefix` alive until the copy is done
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
     CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
     c->lastRunMs = ms;
     c->totalMs += ms;
-    if (cb && expDone < nExp)
+    if (cb)
         cb(nExp, user);
     return DXMCB200_OK;
 }
@@ -960,7 +1181,7 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->evStart) != cudaSuccess
-        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dCursor, sizeof(ChunkCursor)) != cudaSuccess
+        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dCursors, sizeof(WaveCursors)) != cudaSuccess
         || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemset(c->dCounters, 0, sizeof(Counters)) != cudaSuccess) {
         dxmcb200_destroy(c);
         return DXMCB200_ERR_CUDA;
@@ -969,12 +1190,11 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     c->collectStats = stats && stats[0] == '1';
     if (const char* env = std::getenv("DXMCB200_PALETTE"))
         c->allowPalette = env[0] != '0';
-    if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill>,<interact>[,<log2 chunk>]
-        int r = 4, i = 8, lg = 25;
-        std::sscanf(env, "%d,%d,%d", &r, &i, &lg);
+    if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill batch>[,<log2 wave records>]
+        int r = 4, lg = 25;
+        std::sscanf(env, "%d,%d", &r, &lg);
         c->refillBatch = static_cast<uint32_t>(std::clamp(r, 1, 32));
-        c->interactBatch = static_cast<uint32_t>(std::clamp(i, 1, 32));
-        c->chunkHistories = 1u << std::clamp(lg, 10, 28);
+        c->waveRecords = 1u << std::clamp(lg, 10, 28);
     }
     *out = c;
     return DXMCB200_OK;
@@ -993,8 +1213,11 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
-    cudaFree(c->dCursor);
-    cudaFree(c->dPhotons);
+    cudaFree(c->dCursors);
+    cudaFreeHost(c->hCursors);
+    cudaFree(c->dPhotons[0]);
+    cudaFree(c->dPhotons[1]);
+    cudaFree(c->dEvents);
     cudaFree(c->dCounters);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
@@ -1096,6 +1319,30 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     c->world.voxels = c->dVoxels;
     c->world.palette = c->dPalette;
     c->world.paletteTable = c->dPaletteTable;
+
+    // Optional (DXMCB200_L2PERSIST=1): pin the voxel grid in L2 with a persisting carve-out + access-policy window.
+    // Measured on B200 with the 105 MB palette grid it LOWERS throughput (1.64e9 vs 2.00e9 histories/s): the carve-out
+    // takes L2 away from the accumulator and record traffic. Off by default, kept for smaller grids.
+    {
+        const char* env = std::getenv("DXMCB200_L2PERSIST");
+        int maxPersist = 0, maxWindow = 0;
+        cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
+        cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
+        cudaStreamAttrValue attr {};
+        if (env && env[0] == '1' && maxPersist > 0 && maxWindow > 0) {
+            const size_t gridBytes = palette ? n : n * sizeof(uint2);
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(maxPersist));
+            attr.accessPolicyWindow.base_ptr = palette ? static_cast<void*>(c->dPalette) : static_cast<void*>(c->dVoxels);
+            attr.accessPolicyWindow.num_bytes = std::min<size_t>(gridBytes, static_cast<size_t>(maxWindow));
+            attr.accessPolicyWindow.hitRatio = std::min(1.0f, static_cast<float>(maxPersist) / static_cast<float>(attr.accessPolicyWindow.num_bytes));
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        } else {
+            attr.accessPolicyWindow.num_bytes = 0;
+        }
+        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        cudaGetLastError(); // a refused hint is not an error
+    }
     return DXMCB200_OK;
 }
 
