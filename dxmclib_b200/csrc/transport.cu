@@ -903,12 +903,22 @@ struct dxmcb200_ctx {
     uint64_t* dPrefix = nullptr;
     uint64_t prefixCapacity = 0;
 
-    // wave buffers: two photon buffers (ping-pong) and the event buffer between transportKernel and interactKernel
-    PhotonRecord* dPhotons[2] = { nullptr, nullptr };
-    EventRecord* dEvents = nullptr;
+    // Two independent wave pipelines on two streams: while one is in its (issue-bound) transport kernel the other runs
+    // its (latency-bound, divergent) interaction and generation kernels on the same SMs. Each owns two photon buffers
+    // (ping-pong), an event buffer and its cursors.
+    struct Pipe {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t done = nullptr;
+        PhotonRecord* dPhotons[2] = { nullptr, nullptr };
+        EventRecord* dEvents = nullptr;
+        WaveCursors* dCursors = nullptr;
+        WaveCursors* hCursors = nullptr; // pinned host copy for the per-wave read-back
+        int cur = 0;
+        unsigned survivors = 0;
+        bool pending = false;
+    } pipes[2];
+    int nPipes = 2;
     uint64_t photonRegion = 0, eventRegion = 0; // slots per shard region of the photon / event buffers
-    WaveCursors* hCursors = nullptr; // pinned host copy for the per-wave read-back
-    WaveCursors* dCursors = nullptr;
     Counters* dCounters = nullptr;
 
     int energyBits = 20, energySqBits = 10;
@@ -949,40 +959,41 @@ T* advancePtr(char*& cursor, size_t count)
 }
 
 // persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
+// with two pipelines every kernel takes half of an SM's block slots so that kernels of both pipelines are co-resident
+int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy) { return std::max(1, c->nPipes > 1 ? occupancy / 2 : occupancy); }
+
 template <typename K>
-cudaError_t launchPersistent(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items, unsigned* blocksOut = nullptr)
+cudaError_t launchPersistent(const dxmcb200_ctx* c, cudaStream_t stream, K kernel, const KernelParams& P, uint64_t items)
 {
     int blocksPerSm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
     if (e != cudaSuccess)
         return e;
-    uint64_t blocks = static_cast<uint64_t>(c->smCount) * std::max(blocksPerSm, 1);
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * blocksPerSmFor(c, blocksPerSm);
     blocks = std::max<uint64_t>(1, std::min(blocks, (items + kThreads - 1) / kThreads));
-    if (blocksOut)
-        *blocksOut = static_cast<unsigned>(blocks);
-    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
+    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
 // interactKernel assigns block b to event shard b % kShards, so its grid is a multiple of kShards
 template <typename K>
-cudaError_t launchSharded(const dxmcb200_ctx* c, K kernel, const KernelParams& P, uint64_t items)
+cudaError_t launchSharded(const dxmcb200_ctx* c, cudaStream_t stream, K kernel, const KernelParams& P, uint64_t items)
 {
     int blocksPerSm = 0;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
     if (e != cudaSuccess)
         return e;
-    uint64_t blocks = static_cast<uint64_t>(c->smCount) * std::max(blocksPerSm, 1);
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * blocksPerSmFor(c, blocksPerSm);
     blocks = std::min(blocks, (items + kThreads - 1) / kThreads);
-    blocks = std::max<uint64_t>(1, (blocks + kShards - 1) / kShards) * kShards;
-    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, c->stream>>>(P);
+    blocks = std::max<uint64_t>(1, blocks / kShards) * kShards;
+    kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
 template <int L>
-cudaError_t launchInteract(const dxmcb200_ctx* c, const KernelParams& P, uint64_t items)
+cudaError_t launchInteract(const dxmcb200_ctx* c, cudaStream_t stream, const KernelParams& P, uint64_t items)
 {
-    return c->collectStats ? launchSharded(c, interactKernel<L, true>, P, items) : launchSharded(c, interactKernel<L, false>, P, items);
+    return c->collectStats ? launchSharded(c, stream, interactKernel<L, true>, P, items) : launchSharded(c, stream, interactKernel<L, false>, P, items);
 }
 
 unsigned maxTransportBlocks(const dxmcb200_ctx* c)
@@ -1034,63 +1045,70 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
 
     // wave buffers sized for this run (kept for the next one when large enough): kShards regions each, with 50 %
     // head-room over an even split (shards fill evenly: every warp appends to shard `global warp index % kShards`)
+    const int nPipes = total >= 4 * static_cast<uint64_t>(c->waveRecords) ? c->nPipes : 1; // small runs: one pipeline
     const uint64_t wave = std::max<uint64_t>(std::min<uint64_t>(c->waveRecords, total), 1024);
     const uint64_t warpsPerShard = (static_cast<uint64_t>(maxTransportBlocks(c)) * (kThreads / 32) + kShards - 1) / kShards;
     const uint64_t photonRegion = ((wave + wave / 2) / kShards + 1024 + 15) & ~15ULL;
     const uint64_t eventRegion = (photonRegion + warpsPerShard * kEventTile + kEventTile - 1) / kEventTile * kEventTile;
     if (photonRegion > c->photonRegion || eventRegion > c->eventRegion) {
-        cudaFree(c->dPhotons[0]);
-        cudaFree(c->dPhotons[1]);
-        cudaFree(c->dEvents);
-        c->dPhotons[0] = c->dPhotons[1] = nullptr;
-        c->dEvents = nullptr;
-        c->photonRegion = c->eventRegion = 0;
-        CU_CHECK(c, cudaMalloc(&c->dPhotons[0], photonRegion * kShards * sizeof(PhotonRecord)));
-        CU_CHECK(c, cudaMalloc(&c->dPhotons[1], photonRegion * kShards * sizeof(PhotonRecord)));
-        CU_CHECK(c, cudaMalloc(&c->dEvents, eventRegion * kShards * sizeof(EventRecord)));
-        c->photonRegion = photonRegion;
-        c->eventRegion = eventRegion;
+        for (auto& pipe : c->pipes) {
+            cudaFree(pipe.dPhotons[0]);
+            cudaFree(pipe.dPhotons[1]);
+            cudaFree(pipe.dEvents);
+            pipe.dPhotons[0] = pipe.dPhotons[1] = nullptr;
+            pipe.dEvents = nullptr;
+        }
+        c->photonRegion = std::max(photonRegion, c->photonRegion);
+        c->eventRegion = std::max(eventRegion, c->eventRegion);
+    }
+    for (int i = 0; i < nPipes; ++i) {
+        auto& pipe = c->pipes[i];
+        if (!pipe.dEvents) {
+            CU_CHECK(c, cudaMalloc(&pipe.dPhotons[0], c->photonRegion * kShards * sizeof(PhotonRecord)));
+            CU_CHECK(c, cudaMalloc(&pipe.dPhotons[1], c->photonRegion * kShards * sizeof(PhotonRecord)));
+            CU_CHECK(c, cudaMalloc(&pipe.dEvents, c->eventRegion * kShards * sizeof(EventRecord)));
+        }
     }
 
-    KernelParams P {};
-    P.world = c->world;
-    P.lut = c->lut;
-    P.beams = c->beams;
-    P.exposures = devExposures;
-    P.prefix = c->dPrefix;
-    P.expBegin = expBegin;
-    P.nExp = static_cast<uint32_t>(nExp);
-    P.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
-    P.refillBatch = c->refillBatch;
-    P.seed = seed;
-    P.events = c->dEvents;
-    P.eventCursors = c->dCursors->events;
-    P.overflow = &c->dCursors->overflow.stored;
-    P.photonRegion = static_cast<uint32_t>(c->photonRegion);
-    P.eventRegion = static_cast<uint32_t>(c->eventRegion);
-    P.acc = c->dAcc;
-    P.counters = c->dCounters;
-    P.energyScale = std::ldexp(1.0f, c->energyBits);
-    P.energySqScale = std::ldexp(1.0f, c->energySqBits);
+    KernelParams base {};
+    base.world = c->world;
+    base.lut = c->lut;
+    base.beams = c->beams;
+    base.exposures = devExposures;
+    base.prefix = c->dPrefix;
+    base.expBegin = expBegin;
+    base.nExp = static_cast<uint32_t>(nExp);
+    base.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
+    base.refillBatch = c->refillBatch;
+    base.seed = seed;
+    base.photonRegion = static_cast<uint32_t>(c->photonRegion);
+    base.eventRegion = static_cast<uint32_t>(c->eventRegion);
+    base.acc = c->dAcc;
+    base.counters = c->dCounters;
+    base.energyScale = std::ldexp(1.0f, c->energyBits);
+    base.energySqScale = std::ldexp(1.0f, c->energySqBits);
 
     uint64_t issuedHistories = 0; // births generated so far
     uint64_t expDone = 0; // exposures of the range whose histories have all been issued, for the progress callback
-    unsigned survivors = 0; // photons waiting in the current buffer
-    int cur = 0;
-    CU_CHECK(c, cudaMemsetAsync(c->dCursors, 0, sizeof(WaveCursors), c->stream));
-    if (!c->hCursors)
-        CU_CHECK(c, cudaMallocHost(&c->hCursors, sizeof(WaveCursors)));
-    CU_CHECK(c, cudaEventRecord(c->evStart, c->stream));
-    while (issuedHistories < total || survivors > 0) {
-        if (cancel && *cancel) {
-            cudaStreamSynchronize(c->stream);
-            return DXMCB200_ERR_CANCELLED;
-        }
-        const int nxt = cur ^ 1;
-        // (a) top the wave up with births
-        const uint64_t births = std::min<uint64_t>(wave - survivors, total - issuedHistories);
-        P.photonsOut = c->dPhotons[cur];
-        P.outCursors = c->dCursors->photons[cur];
+    const int savedPipes = c->nPipes;
+    c->nPipes = nPipes; // grid sizing of the launch helpers
+    struct Restore {
+        dxmcb200_ctx* c;
+        int n;
+        ~Restore() { c->nPipes = n; }
+    } restore { c, savedPipes };
+
+    // one wave of pipeline `pipe`: top up with births, transport, interact, read the survivor count back
+    auto enqueueWave = [&](dxmcb200_ctx::Pipe& pipe) -> int {
+        KernelParams P = base;
+        const int cur = pipe.cur, nxt = cur ^ 1;
+        P.events = pipe.dEvents;
+        P.eventCursors = pipe.dCursors->events;
+        P.overflow = &pipe.dCursors->overflow.stored;
+        // (a) births
+        const uint64_t births = std::min<uint64_t>(wave - pipe.survivors, total - issuedHistories);
+        P.photonsOut = pipe.dPhotons[cur];
+        P.outCursors = pipe.dCursors->photons[cur];
         if (births > 0) {
             P.chunkBegin = issuedHistories;
             P.chunkCount = static_cast<uint32_t>(births);
@@ -1098,49 +1116,101 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
                 P.chunkFirstExposure = static_cast<uint32_t>(issuedHistories / P.uniformHistories);
                 P.chunkFirstOffset = static_cast<uint32_t>(issuedHistories % P.uniformHistories);
             }
-            CU_CHECK(c, c->collectStats ? launchPersistent(c, generateKernel<true>, P, births) : launchPersistent(c, generateKernel<false>, P, births));
+            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, generateKernel<true>, P, births)
+                                        : launchPersistent(c, pipe.stream, generateKernel<false>, P, births));
             issuedHistories += births;
             ++c->launches;
         }
         // (b) step every photon of the wave to its next event
-        const uint64_t records = survivors + births; // upper bound: births that miss the world store nothing
-        P.photonsIn = c->dPhotons[cur];
-        P.inCursors = c->dCursors->photons[cur];
-        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->photons[cur], 0);
-        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->events, 1);
-        CU_CHECK(c, c->collectStats ? launchPersistent(c, transportKernel<true>, P, records) : launchPersistent(c, transportKernel<false>, P, records));
+        const uint64_t records = pipe.survivors + births; // upper bound: births that miss the world store nothing
+        P.photonsIn = pipe.dPhotons[cur];
+        P.inCursors = pipe.dCursors->photons[cur];
+        resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[cur], 0);
+        resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->events, 1);
+        CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true>, P, records)
+                                    : launchPersistent(c, pipe.stream, transportKernel<false>, P, records));
         // (c)+(d) interactions and scoring; survivors open the next wave
-        P.photonsOut = c->dPhotons[nxt];
-        P.outCursors = c->dCursors->photons[nxt];
-        resetCursorsKernel<<<1, kShards, 0, c->stream>>>(c->dCursors->photons[nxt], 1);
-        CU_CHECK(c, model == 0 ? launchInteract<0>(c, P, records) : model == 1 ? launchInteract<1>(c, P, records) : launchInteract<2>(c, P, records));
+        P.photonsOut = pipe.dPhotons[nxt];
+        P.outCursors = pipe.dCursors->photons[nxt];
+        resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[nxt], 1);
+        CU_CHECK(c, model == 0 ? launchInteract<0>(c, pipe.stream, P, records)
+                               : model == 1 ? launchInteract<1>(c, pipe.stream, P, records) : launchInteract<2>(c, pipe.stream, P, records));
         c->launches += 2;
-        CU_CHECK(c, cudaMemcpyAsync(c->hCursors->photons[nxt], c->dCursors->photons[nxt], sizeof(ShardCursor) * kShards, cudaMemcpyDeviceToHost, c->stream));
-        CU_CHECK(c, cudaMemcpyAsync(&c->hCursors->overflow, &c->dCursors->overflow, sizeof(ShardCursor), cudaMemcpyDeviceToHost, c->stream));
-        CU_CHECK(c, cudaStreamSynchronize(c->stream));
-        if (c->hCursors->overflow.stored) {
+        CU_CHECK(c, cudaMemcpyAsync(pipe.hCursors->photons[nxt], pipe.dCursors->photons[nxt], sizeof(ShardCursor) * kShards, cudaMemcpyDeviceToHost,
+                        pipe.stream));
+        CU_CHECK(c, cudaMemcpyAsync(&pipe.hCursors->overflow, &pipe.dCursors->overflow, sizeof(ShardCursor), cudaMemcpyDeviceToHost, pipe.stream));
+        CU_CHECK(c, cudaEventRecord(pipe.done, pipe.stream));
+        pipe.pending = true;
+        return DXMCB200_OK;
+    };
+    // wait for the wave in flight on `pipe` and pick up its survivor count
+    auto completeWave = [&](dxmcb200_ctx::Pipe& pipe) -> int {
+        CU_CHECK(c, cudaEventSynchronize(pipe.done));
+        pipe.pending = false;
+        const int nxt = pipe.cur ^ 1;
+        if (pipe.hCursors->overflow.stored) {
             c->error = "wave buffer region overflow";
             return DXMCB200_ERR_STATE;
         }
         uint64_t alive = 0;
         for (unsigned k = 0; k < kShards; ++k)
-            alive += c->hCursors->photons[nxt][k].stored;
-        survivors = static_cast<unsigned>(alive);
-        if (survivors > wave) {
+            alive += pipe.hCursors->photons[nxt][k].stored;
+        if (alive > wave) {
             c->error = "wave buffer overflow";
             return DXMCB200_ERR_STATE;
         }
-        cur = nxt;
-        if (cb) {
-            const uint64_t before = expDone;
-            while (expDone < nExp && prefix[expDone + 1] <= issuedHistories)
-                ++expDone;
-            if (expDone != before && !(expDone == nExp && survivors > 0))
-                cb(expDone, user);
-        }
+        pipe.survivors = static_cast<unsigned>(alive);
+        pipe.cur = nxt;
+        return DXMCB200_OK;
+    };
+
+    CU_CHECK(c, cudaStreamSynchronize(c->stream)); // uploads issued on the ctx stream are visible to both pipelines
+    for (int i = 0; i < nPipes; ++i) {
+        auto& pipe = c->pipes[i];
+        pipe.cur = 0;
+        pipe.survivors = 0;
+        pipe.pending = false;
+        CU_CHECK(c, cudaMemsetAsync(pipe.dCursors, 0, sizeof(WaveCursors), pipe.stream));
     }
-    CU_CHECK(c, cudaEventRecord(c->evStop, c->stream));
-    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaEventRecord(c->evStart, c->pipes[0].stream));
+    int status = DXMCB200_OK;
+    int turn = 0; // pipelines are served round robin, so the host always waits on the older wave
+    for (;;) {
+        auto& pipe = c->pipes[turn];
+        if (pipe.pending) {
+            status = completeWave(pipe);
+            if (status != DXMCB200_OK)
+                break;
+            if (cb) {
+                const uint64_t before = expDone;
+                while (expDone + 1 < nExp && prefix[expDone + 1] <= issuedHistories)
+                    ++expDone; // the last exposure is reported when everything has drained
+                if (expDone != before)
+                    cb(expDone, user);
+            }
+        }
+        if (cancel && *cancel) {
+            status = DXMCB200_ERR_CANCELLED;
+            break;
+        }
+        if (issuedHistories < total || pipe.survivors > 0) {
+            status = enqueueWave(pipe);
+            if (status != DXMCB200_OK)
+                break;
+        }
+        bool any = false;
+        for (int i = 0; i < nPipes; ++i)
+            any = any || c->pipes[i].pending;
+        if (!any)
+            break;
+        turn = (turn + 1) % nPipes;
+    }
+    for (int i = 0; i < nPipes; ++i)
+        cudaStreamSynchronize(c->pipes[i].stream);
+    if (status != DXMCB200_OK)
+        return status;
+    CU_CHECK(c, cudaEventRecord(c->evStop, c->pipes[0].stream));
+    CU_CHECK(c, cudaStreamSynchronize(c->pipes[0].stream));
     float ms = 0;
     CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
     c->lastRunMs = ms;
@@ -1181,11 +1251,23 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     c->device = device;
     if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->evStart) != cudaSuccess
-        || cudaEventCreate(&c->evStop) != cudaSuccess || cudaMalloc(&c->dCursors, sizeof(WaveCursors)) != cudaSuccess
+        || cudaEventCreate(&c->evStop) != cudaSuccess
         || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemset(c->dCounters, 0, sizeof(Counters)) != cudaSuccess) {
         dxmcb200_destroy(c);
         return DXMCB200_ERR_CUDA;
     }
+    c->pipes[0].stream = c->stream;
+    for (int i = 0; i < 2; ++i) {
+        auto& pipe = c->pipes[i];
+        if ((i > 0 && cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking) != cudaSuccess)
+            || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess
+            || cudaMalloc(&pipe.dCursors, sizeof(WaveCursors)) != cudaSuccess || cudaMallocHost(&pipe.hCursors, sizeof(WaveCursors)) != cudaSuccess) {
+            dxmcb200_destroy(c);
+            return DXMCB200_ERR_CUDA;
+        }
+    }
+    if (const char* env = std::getenv("DXMCB200_PIPES"))
+        c->nPipes = env[0] == '1' ? 1 : 2;
     const char* stats = std::getenv("DXMCB200_STATS");
     c->collectStats = stats && stats[0] == '1';
     if (const char* env = std::getenv("DXMCB200_PALETTE"))
@@ -1213,11 +1295,18 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
-    cudaFree(c->dCursors);
-    cudaFreeHost(c->hCursors);
-    cudaFree(c->dPhotons[0]);
-    cudaFree(c->dPhotons[1]);
-    cudaFree(c->dEvents);
+    for (int i = 0; i < 2; ++i) {
+        auto& pipe = c->pipes[i];
+        cudaFree(pipe.dCursors);
+        cudaFreeHost(pipe.hCursors);
+        cudaFree(pipe.dPhotons[0]);
+        cudaFree(pipe.dPhotons[1]);
+        cudaFree(pipe.dEvents);
+        if (pipe.done)
+            cudaEventDestroy(pipe.done);
+        if (i > 0 && pipe.stream)
+            cudaStreamDestroy(pipe.stream); // pipes[0] runs on the ctx stream
+    }
     cudaFree(c->dCounters);
     if (c->evStart)
         cudaEventDestroy(c->evStart);
