@@ -33,6 +33,10 @@ sys.path.insert(0, ROOT)
 from dxmclib_b200 import phantoms  # noqa: E402
 from dxmclib_b200 import scene as S  # noqa: E402
 
+# dram__bytes_read.sum + dram__bytes_write.sum of one full-size transportKernel launch, from the committed
+# `ncu --set full` capture (profiles/r1_v4_*): null until measured for the current kernel version
+TRAFFIC_PER_LAUNCH = None
+
 DIM = (512, 512, 400)
 SPACING = (1.0, 1.0, 1.0)
 EXPOSURES = 3600
@@ -151,7 +155,8 @@ def workload_config(n_ranks, hist):
                     f"{DIM[0]}x{DIM[1]}x{DIM[2]} @1 mm, 10 materials, {EXPOSURES * n_ranks} exposures x {hist} histories",
         "voxels": int(np.prod(DIM)), "exposures": EXPOSURES * n_ranks, "histories_per_exposure": hist,
         "histories_per_step": EXPOSURES * n_ranks * hist, "sharding": f"exposures block-partitioned over {n_ranks} GPU(s)",
-        "l2_note": "voxel grid 839 MB + accumulators 3.4 GB exceed the 126 MB L2; accumulators are cleared every step",
+        "l2_note": "accumulators 3.4 GB + photon/event record streams (>10 GB per wave pair) exceed the 126 MB L2; the palette voxel "
+                   "grid is 105 MB; accumulators are cleared every step",
     }
 
 
@@ -221,6 +226,7 @@ def main():
 
     kernel_ms = []
     launches = 0
+    per_kernel = {"generate": [0.0, 0], "transport": [0.0, 0], "interact": [0.0, 0]}
 
     def step(record):
         nonlocal launches
@@ -231,7 +237,10 @@ def main():
             torch.cuda.synchronize()
         if record:
             kernel_ms.append(ms)
-            launches += ctx.stats()["kernel_launches"]  # our transport kernel launches (memset and NCCL not counted)
+            launches += ctx.stats()["kernel_launches"]  # generate / transport / interact launches (cursor resets and NCCL not counted)
+            for k, v in ctx.kernel_times().items():
+                per_kernel[k][0] += v["ms"]
+                per_kernel[k][1] += v["launches"]
 
     for _ in range(args.warmup):
         step(False)
@@ -260,15 +269,28 @@ def main():
     ctx.enable_stats(False)
     L = st["lookups"] / max(st["histories"], 1)
     Sev = st["score_events"] / max(st["histories"], 1)
-    b_alg = 6.0 * L + 24.0 * Sev  # u8+f32+u8 per look-up, r+w of f32,u32,f32 per scoring event
-    kernel_s_per_step = kernel_total_ms / args.steps / 1e3
-    achieved = EXPOSURES * hist * b_alg / kernel_s_per_step / 1e9
+    hist_rank = EXPOSURES * hist
     peak, peak_src = measured_peak()
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "kernel": "generateKernel + transportKernel + interactKernel<1> (whole wave pipeline)", "bytes_per_history": b_alg, "lookups_per_history": L,
-                "score_events_per_history": Sev, "steps_per_history": st["steps"] / max(st["histories"], 1),
+    # Dominant kernel = transportKernel (Woodcock stepping): its algorithmic bytes are the voxel look-ups, 6 B each in the
+    # reference layout (u8 material + f32 density + u8 measurement); the scoring bytes (24 B per event) belong
+    # to interactKernel. achieved = bytes per launch / average launch duration, both from the timed steps.
+    t_ms, t_n = per_kernel["transport"]
+    t_launch_ms = t_ms / max(t_n, 1)
+    lookups_per_launch = L * hist_rank * args.steps / max(t_n, 1)
+    achieved = 6.0 * lookups_per_launch / (t_launch_ms * 1e-3) / 1e9 if t_launch_ms > 0 else 0.0
+    b_alg = 6.0 * L + 24.0 * Sev
+    pipeline_s = kernel_total_ms / args.steps / 1e3
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_PER_LAUNCH,
+                "kernel": "transportKernel<false> (Woodcock stepping; one launch = one wave of <= 2^25 photon segments)",
+                "algorithmic_bytes_per_launch": 6.0 * lookups_per_launch, "launch_ms": t_launch_ms, "launches": t_n,
+                "kernel_share_of_step": {k: v[0] / max(kernel_total_ms, 1e-9) for k, v in per_kernel.items()},
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in per_kernel.items()},
+                "pipelines": 2, "note": "two wave pipelines overlap on the GPU, so per-kernel device times add up to more than the step",
+                "whole_pipeline": {"bytes_per_history": b_alg, "achieved": hist_rank * b_alg / pipeline_s / 1e9,
+                                   "frac": hist_rank * b_alg / pipeline_s / 1e9 / peak},
+                "lookups_per_history": L, "score_events_per_history": Sev, "steps_per_history": st["steps"] / max(st["histories"], 1),
                 "interactions_per_history": st["interactions"] / max(st["histories"], 1),
-                "kernel_ms_per_step": kernel_total_ms / args.steps, "peak_source": peak_src}
+                "pipeline_ms_per_step": kernel_total_ms / args.steps, "peak_source": peak_src}
 
     # ---- e2e: Transport::operator() with host arrays in and out (N=1), or prepare/run/all-reduce/collect (N>1)
     e2e = None

@@ -24,7 +24,7 @@ CABI_SYMBOLS = [
     "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
-    "dxmcb200_get_stats", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
+    "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
     "dxmcb200_sample_interaction",
 ]
 
@@ -233,6 +233,14 @@ class Context:
         s = Stats()
         self._chk(self.l.dxmcb200_get_stats(self.h, C.byref(s)), "dxmcb200_get_stats")
         return {k: getattr(s, k) for k, _ in Stats._fields_}
+
+    def kernel_times(self) -> dict:
+        """Device milliseconds and launch counts of generate / transport / interact kernels since clear()."""
+        ms = (C.c_double * 3)()
+        n = (C.c_uint64 * 3)()
+        self._chk(self.l.dxmcb200_get_kernel_times(self.h, ms, n), "dxmcb200_get_kernel_times")
+        names = ("generate", "transport", "interact")
+        return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
 
     def enable_stats(self, on=True):
         self._chk(self.l.dxmcb200_enable_stats(self.h, int(on)), "dxmcb200_enable_stats")

@@ -909,6 +909,8 @@ struct dxmcb200_ctx {
     struct Pipe {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
+        cudaEvent_t mark[4] = { nullptr, nullptr, nullptr, nullptr }; // around generate / transport / interact of the wave in flight
+        bool generated = false;
         PhotonRecord* dPhotons[2] = { nullptr, nullptr };
         EventRecord* dEvents = nullptr;
         WaveCursors* dCursors = nullptr;
@@ -918,6 +920,8 @@ struct dxmcb200_ctx {
         bool pending = false;
     } pipes[2];
     int nPipes = 2;
+    double kernelMs[3] = { 0, 0, 0 }; // summed device time of generate / transport / interact launches since clear
+    uint64_t kernelLaunches[3] = { 0, 0, 0 };
     uint64_t photonRegion = 0, eventRegion = 0; // slots per shard region of the photon / event buffers
     Counters* dCounters = nullptr;
 
@@ -1109,6 +1113,8 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         const uint64_t births = std::min<uint64_t>(wave - pipe.survivors, total - issuedHistories);
         P.photonsOut = pipe.dPhotons[cur];
         P.outCursors = pipe.dCursors->photons[cur];
+        CU_CHECK(c, cudaEventRecord(pipe.mark[0], pipe.stream));
+        pipe.generated = births > 0;
         if (births > 0) {
             P.chunkBegin = issuedHistories;
             P.chunkCount = static_cast<uint32_t>(births);
@@ -1127,14 +1133,17 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         P.inCursors = pipe.dCursors->photons[cur];
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[cur], 0);
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->events, 1);
+        CU_CHECK(c, cudaEventRecord(pipe.mark[1], pipe.stream));
         CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true>, P, records)
                                     : launchPersistent(c, pipe.stream, transportKernel<false>, P, records));
+        CU_CHECK(c, cudaEventRecord(pipe.mark[2], pipe.stream));
         // (c)+(d) interactions and scoring; survivors open the next wave
         P.photonsOut = pipe.dPhotons[nxt];
         P.outCursors = pipe.dCursors->photons[nxt];
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[nxt], 1);
         CU_CHECK(c, model == 0 ? launchInteract<0>(c, pipe.stream, P, records)
                                : model == 1 ? launchInteract<1>(c, pipe.stream, P, records) : launchInteract<2>(c, pipe.stream, P, records));
+        CU_CHECK(c, cudaEventRecord(pipe.mark[3], pipe.stream));
         c->launches += 2;
         CU_CHECK(c, cudaMemcpyAsync(pipe.hCursors->photons[nxt], pipe.dCursors->photons[nxt], sizeof(ShardCursor) * kShards, cudaMemcpyDeviceToHost,
                         pipe.stream));
@@ -1148,6 +1157,13 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         CU_CHECK(c, cudaEventSynchronize(pipe.done));
         pipe.pending = false;
         const int nxt = pipe.cur ^ 1;
+        for (int k = 0; k < 3; ++k) { // device time of the wave's kernels (mark[1] is recorded after the tiny cursor resets)
+            float ms = 0;
+            if ((k > 0 || pipe.generated) && cudaEventElapsedTime(&ms, pipe.mark[k], pipe.mark[k + 1]) == cudaSuccess) {
+                c->kernelMs[k] += ms;
+                ++c->kernelLaunches[k];
+            }
+        }
         if (pipe.hCursors->overflow.stored) {
             c->error = "wave buffer region overflow";
             return DXMCB200_ERR_STATE;
@@ -1260,7 +1276,8 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     for (int i = 0; i < 2; ++i) {
         auto& pipe = c->pipes[i];
         if ((i > 0 && cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking) != cudaSuccess)
-            || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess
+            || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&pipe.mark[0]) != cudaSuccess
+            || cudaEventCreate(&pipe.mark[1]) != cudaSuccess || cudaEventCreate(&pipe.mark[2]) != cudaSuccess || cudaEventCreate(&pipe.mark[3]) != cudaSuccess
             || cudaMalloc(&pipe.dCursors, sizeof(WaveCursors)) != cudaSuccess || cudaMallocHost(&pipe.hCursors, sizeof(WaveCursors)) != cudaSuccess) {
             dxmcb200_destroy(c);
             return DXMCB200_ERR_CUDA;
@@ -1304,6 +1321,9 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
         cudaFree(pipe.dEvents);
         if (pipe.done)
             cudaEventDestroy(pipe.done);
+        for (auto& m : pipe.mark)
+            if (m)
+                cudaEventDestroy(m);
         if (i > 0 && pipe.stream)
             cudaStreamDestroy(pipe.stream); // pipes[0] runs on the ctx stream
     }
@@ -1605,6 +1625,10 @@ int dxmcb200_clear(dxmcb200_ctx* c)
     c->totalMs = 0;
     c->lastRunMs = 0;
     c->launches = 0;
+    for (int k = 0; k < 3; ++k) {
+        c->kernelMs[k] = 0;
+        c->kernelLaunches[k] = 0;
+    }
     return DXMCB200_OK;
 }
 
@@ -1774,6 +1798,17 @@ int dxmcb200_get_stats(dxmcb200_ctx* c, dxmcb200_stats* s)
     s->score_events = h.scores;
     s->kernel_launches = c->launches;
     s->kernel_ms = c->totalMs;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_kernel_times(dxmcb200_ctx* c, double ms[3], uint64_t launches[3])
+{
+    if (!c || !ms || !launches)
+        return DXMCB200_ERR_ARG;
+    for (int k = 0; k < 3; ++k) {
+        ms[k] = c->kernelMs[k];
+        launches[k] = c->kernelLaunches[k];
+    }
     return DXMCB200_OK;
 }
 

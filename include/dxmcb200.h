@@ -182,6 +182,10 @@ typedef struct dxmcb200_stats {
     double kernel_ms;          /* summed over all runs since dxmcb200_clear */
 } dxmcb200_stats;
 int dxmcb200_get_stats(dxmcb200_ctx*, dxmcb200_stats*);
+/* Device time (CUDA events on the launching streams) and launch counts of the three wave kernels since
+ * dxmcb200_clear: [0] generateKernel, [1] transportKernel (includes two one-block cursor resets), [2] interactKernel.
+ * With two pipelines the kernels of both overlap on the GPU, so the three sums can exceed the wall time. */
+int dxmcb200_get_kernel_times(dxmcb200_ctx*, double ms[3], uint64_t launches[3]);
 /* The per-history work counters (histories .. score_events) cost registers, so the transport kernel is
  * compiled twice; on != 0 selects the counting variant for subsequent runs (default off, or
  * DXMCB200_STATS=1 in the environment at create time). kernel_launches / kernel_ms are always kept. */
