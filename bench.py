@@ -118,7 +118,7 @@ def measured_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def run_reference(args, rank):
+def run_reference(args, rank, emit):
     """The reference's own multithreaded CPU Transport (oracle/_ref, built from the unmodified reference) on a bounded
     sample of the same workload: same world, same source, fewer histories per exposure."""
     if rank != 0:
@@ -146,7 +146,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "histories/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(n_ranks, hist):
@@ -161,6 +161,13 @@ def workload_config(n_ranks, hist):
 
 
 def main():
+    # stdout carries exactly ONE JSON line: anything libraries print (NCCL banners, warnings) is sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
+
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -180,7 +187,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
     if args.impl == "reference":
-        run_reference(args, rank)
+        run_reference(args, rank, emit)
         return
 
     import torch
@@ -348,7 +355,7 @@ def main():
             "dtype": "f32", "data": "synthetic", "config": workload_config(n, hist) | {"prepare_s": round(prepare_s, 2)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clocks.summary(),
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -685,24 +685,33 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
             tr.setNumberOfWorkers(nWorkers);
         tr.setLowEnergyCorrectionModel(static_cast<LOWENERGYCORRECTION>(model));
         tr.setOutputMode(outputMode == DXS_OUT_DOSE ? Transport<float>::OUTPUTMODE::DOSE : Transport<float>::OUTPUTMODE::EV_PER_HISTORY);
+        detail::PhaseTrace trace;
         s->world->makeValid();
+        trace("World::makeValid");
         if (seed != 0)
             tr.setSeed(seed);
         (void)nWorkers; // n_workers selects host threads / stream mode in the reference harness only
         Result<float> res = tr(*s->world, s->source.get(), nullptr, useCalibration != 0);
+        trace("Transport::operator()");
         const auto n = res.dose.size();
-        if (dose)
-            std::memcpy(dose, res.dose.data(), n * sizeof(float));
-        if (nEvents)
-            std::memcpy(nEvents, res.nEvents.data(), n * sizeof(std::uint32_t));
-        if (variance)
-            std::memcpy(variance, res.variance.data(), n * sizeof(float));
+        // the caller's arrays are usually untouched pages: copy (and fault them in) on several host threads
+        const void* src[3] = { res.dose.data(), res.nEvents.data(), res.variance.data() };
+        void* dst[3] = { dose, nEvents, variance };
+        const std::size_t pieces = n > (std::size_t { 1 } << 22) ? 4 : 1;
+        dxmc::detail::parallelFor(3 * pieces, [&](std::size_t job) {
+            const std::size_t a = job / pieces, piece = job % pieces;
+            if (!dst[a])
+                return;
+            const std::size_t begin = n * piece / pieces * 4, end = n * (piece + 1) / pieces * 4;
+            std::memcpy(static_cast<char*>(dst[a]) + begin, static_cast<const char*>(src[a]) + begin, end - begin);
+        });
         if (info) {
             info->histories = res.numberOfHistories;
             info->seconds = res.simulationTime.count();
             std::memset(info->units, 0, sizeof(info->units));
             std::strncpy(info->units, std::string(res.dose_units).c_str(), sizeof(info->units) - 1);
         }
+        trace("copy to caller arrays");
         return DXS_OK;
     });
 }
@@ -750,12 +759,17 @@ int dxs_b200_collect(dxs_scene* s, int outputMode, int useCalibration, uint64_t 
         res.numberOfHistories = histories ? histories : tr.preparedHistories();
         tr.collect(*s->world, s->source.get(), res, useCalibration != 0, nullptr);
         const auto n = res.dose.size();
-        if (dose)
-            std::memcpy(dose, res.dose.data(), n * sizeof(float));
-        if (nEvents)
-            std::memcpy(nEvents, res.nEvents.data(), n * sizeof(std::uint32_t));
-        if (variance)
-            std::memcpy(variance, res.variance.data(), n * sizeof(float));
+        // the caller's arrays are usually untouched pages: copy (and fault them in) on several host threads
+        const void* src[3] = { res.dose.data(), res.nEvents.data(), res.variance.data() };
+        void* dst[3] = { dose, nEvents, variance };
+        const std::size_t pieces = n > (std::size_t { 1 } << 22) ? 4 : 1;
+        dxmc::detail::parallelFor(3 * pieces, [&](std::size_t job) {
+            const std::size_t a = job / pieces, piece = job % pieces;
+            if (!dst[a])
+                return;
+            const std::size_t begin = n * piece / pieces * 4, end = n * (piece + 1) / pieces * 4;
+            std::memcpy(static_cast<char*>(dst[a]) + begin, static_cast<const char*>(src[a]) + begin, end - begin);
+        });
         if (info) {
             info->histories = res.numberOfHistories;
             info->seconds = 0;

@@ -18,6 +18,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -251,12 +252,21 @@ namespace {
         return 2.0 * sum * h / 3.0;
     }
 
+    // published pointers: the common path (model already built) takes no lock, so the per-material table builders
+    // can run on several host threads
+    std::atomic<const ElementModel*> g_modelOf[128] {};
+
     const ElementModel& model(int Z)
     {
+        const int slot = Z & 127;
+        if (const ElementModel* ready = g_modelOf[slot].load(std::memory_order_acquire))
+            return *ready;
         std::lock_guard<std::mutex> lock(g_mutex);
         auto it = g_models.find(Z);
-        if (it != g_models.end())
+        if (it != g_models.end()) {
+            g_modelOf[slot].store(&it->second, std::memory_order_release);
             return it->second;
+        }
         ElementModel m;
         m.groups = slaterGroups(Z);
         constexpr int NE = 140;
@@ -279,7 +289,9 @@ namespace {
             m.lnCoh.push_back(std::log(std::max(coh, 1e-300)));
             m.lnIncoh.push_back(std::log(std::max(incoh, 1e-300)));
         }
-        return g_models.emplace(Z, std::move(m)).first->second;
+        const ElementModel& stored = g_models.emplace(Z, std::move(m)).first->second; // std::map nodes never move
+        g_modelOf[slot].store(&stored, std::memory_order_release);
+        return stored;
     }
 
     double interpLogGrid(const std::vector<double>& x, const std::vector<double>& y, double lx)

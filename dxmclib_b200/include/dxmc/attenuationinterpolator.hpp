@@ -17,7 +17,9 @@
 #include <algorithm>
 #include <array>
 #include <cmath>
+#include <iterator>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 namespace dxmc {
@@ -174,12 +176,30 @@ protected:
     template <typename DensIter, typename MatIter>
     void buildMajorant(const std::vector<Material>& materials, const DensIter densBegin, const DensIter densEnd, const MatIter matBegin, const T firstKnot)
     {
-        // one pass over the voxels instead of one per material (same maxima)
+        // one pass over the voxels instead of one per material, split over the host cores (maxima do not depend on
+        // the order; the reference scans once per material, attenuationinterpolator.hpp:48-59)
         std::vector<T> maxDens(materials.size(), T { 0 });
-        auto m = matBegin;
-        for (auto d = densBegin; d != densEnd; ++d, ++m)
-            if (static_cast<std::size_t>(*m) < maxDens.size())
-                maxDens[*m] = std::max(maxDens[*m], *d);
+        const std::size_t nVoxels = static_cast<std::size_t>(std::distance(densBegin, densEnd));
+        const std::size_t nChunks = nVoxels > (std::size_t { 1 } << 22) ? std::max(1u, std::thread::hardware_concurrency()) : 1;
+        std::vector<std::vector<T>> partial(nChunks, std::vector<T>(materials.size(), T { 0 }));
+        std::vector<std::thread> pool;
+        auto scan = [&](std::size_t chunk) {
+            const std::size_t begin = nVoxels * chunk / nChunks, end = nVoxels * (chunk + 1) / nChunks;
+            auto& local = partial[chunk];
+            auto d = densBegin + static_cast<std::ptrdiff_t>(begin);
+            auto m = matBegin + static_cast<std::ptrdiff_t>(begin);
+            for (std::size_t i = begin; i < end; ++i, ++d, ++m)
+                if (static_cast<std::size_t>(*m) < local.size())
+                    local[*m] = std::max(local[*m], *d);
+        };
+        for (std::size_t chunk = 1; chunk < nChunks; ++chunk)
+            pool.emplace_back(scan, chunk);
+        scan(0);
+        for (auto& t : pool)
+            t.join();
+        for (const auto& local : partial)
+            for (std::size_t i = 0; i < maxDens.size(); ++i)
+                maxDens[i] = std::max(maxDens[i], local[i]);
 
         std::vector<T> x;
         x.reserve(m_x.size() + 1);

@@ -14,9 +14,37 @@
 #include "dxmc/world.hpp"
 
 #include <array>
+#include <atomic>
+#include <optional>
+#include <thread>
 #include <vector>
 
 namespace dxmc {
+
+namespace detail {
+    // fn(i) for i in [0, n) on up to hardware_concurrency host threads; every i is independent
+    template <typename F>
+    inline void parallelFor(std::size_t n, F fn)
+    {
+        const std::size_t workers = std::min<std::size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
+        if (workers <= 1) {
+            for (std::size_t i = 0; i < n; ++i)
+                fn(i);
+            return;
+        }
+        std::atomic<std::size_t> next { 0 };
+        auto work = [&]() {
+            for (std::size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
+                fn(i);
+        };
+        std::vector<std::thread> pool;
+        for (std::size_t t = 1; t < workers; ++t)
+            pool.emplace_back(work);
+        work();
+        for (auto& t : pool)
+            t.join();
+    }
+}
 
 template <Floating T = double>
 class AttenuationLut {
@@ -42,13 +70,31 @@ public:
     {
         m_minEnergy = std::max(MIN_PHOTON_ENERGY(), std::min(maxEnergy, minEnergy));
         m_maxEnergy = std::min(MAX_PHOTON_ENERGY(), std::max(maxEnergy, minEnergy));
-        buildFormFactorSamplers(materials);
-        buildScatterFunctions(materials);
+        // The per-material tables are independent of each other: build them on all host cores (the reference builds
+        // them one after the other, attenuationlut.hpp:84-92; the values are the same).
+        std::vector<std::optional<FormFactorSampler>> samplers(materials.size());
+        std::vector<std::optional<ScatterFunction>> scatter(materials.size());
+        std::vector<std::array<ElectronShellConfiguration<T>, 12>> shells(materials.size());
+        detail::parallelFor(materials.size() * 3, [&](std::size_t job) {
+            const std::size_t i = job / 3;
+            if (job % 3 == 0)
+                samplers[i].emplace(buildFormFactorSampler(materials[i]));
+            else if (job % 3 == 1)
+                scatter[i].emplace(buildScatterFunction(materials[i]));
+            else
+                shells[i] = materials[i].template getElectronConfiguration<T>();
+        });
+        m_formFactor.clear();
+        m_comptonScatterFactor.clear();
+        for (std::size_t i = 0; i < materials.size(); ++i) {
+            m_formFactor.push_back(std::move(*samplers[i]));
+            m_comptonScatterFactor.push_back(std::move(*scatter[i]));
+        }
         // appended, never cleared: a second generate() on the same object keeps the first entries in
         // front (and thereby in use), exactly like the reference (attenuationlut.hpp:89-92)
-        m_electronShellConfiguration.reserve(materials.size());
-        for (const auto& m : materials)
-            m_electronShellConfiguration.push_back(m.getElectronConfiguration<T>());
+        m_electronShellConfiguration.reserve(m_electronShellConfiguration.size() + materials.size());
+        for (const auto& sh : shells)
+            m_electronShellConfiguration.push_back(sh);
         if (generatePhotonData)
             m_attenuationData = AttenuationLutInterpolator<T>(materials, m_maxEnergy, m_minEnergy);
     }
@@ -97,38 +143,30 @@ public:
 
 protected:
     // RITA over q^2 in [0, q2max] where q2max is stepped up until F^2 < 0.001 or the kinematic limit
-    void buildFormFactorSamplers(const std::vector<Material>& materials)
+    FormFactorSampler buildFormFactorSampler(const Material& m) const
     {
-        m_formFactor.clear();
-        m_formFactor.reserve(materials.size());
         const auto qmax = momentumTransferMax(m_maxEnergy);
         const auto qmaxSquared = qmax * qmax;
-        for (const auto& m : materials) {
-            T upper = 1;
-            T ff = m.getRayleightFormFactorSquared(upper);
-            while (upper < qmaxSquared && ff > T { 0.001 }) {
-                upper += ff > T { 0.5 } ? T { 0.5 } : T { 0.1 };
-                ff = m.getRayleightFormFactorSquared(upper);
-            }
-            m_formFactor.emplace_back(T { 0 }, upper, [&](T q2) -> T { return m.getRayleightFormFactorSquared(std::sqrt(q2)); });
+        T upper = 1;
+        T ff = m.getRayleightFormFactorSquared(upper);
+        while (upper < qmaxSquared && ff > T { 0.001 }) {
+            upper += ff > T { 0.5 } ? T { 0.5 } : T { 0.1 };
+            ff = m.getRayleightFormFactorSquared(upper);
         }
+        return FormFactorSampler(T { 0 }, upper, [&](T q2) -> T { return m.getRayleightFormFactorSquared(std::sqrt(q2)); });
     }
 
     // spline over q in [0, qmax] where qmax is stepped up until S/Z > 0.999 or the kinematic limit
-    void buildScatterFunctions(const std::vector<Material>& materials)
+    ScatterFunction buildScatterFunction(const Material& m) const
     {
-        m_comptonScatterFactor.clear();
-        m_comptonScatterFactor.reserve(materials.size());
-        for (const auto& m : materials) {
-            const T qmaxEnergy = momentumTransferMax(m_maxEnergy);
-            T upper = 0.5;
-            T sf = m.getComptonNormalizedScatterFactor(upper);
-            while (sf < T { 0.999 } && upper < qmaxEnergy) {
-                sf = m.getComptonNormalizedScatterFactor(upper);
-                upper += sf < T { 0.5 } ? T { 0.5 } : T { 0.1 };
-            }
-            m_comptonScatterFactor.emplace_back(T { 0 }, upper, [&](const T q) -> T { return m.getComptonNormalizedScatterFactor(q); });
+        const T qmaxEnergy = momentumTransferMax(m_maxEnergy);
+        T upper = 0.5;
+        T sf = m.getComptonNormalizedScatterFactor(upper);
+        while (sf < T { 0.999 } && upper < qmaxEnergy) {
+            sf = m.getComptonNormalizedScatterFactor(upper);
+            upper += sf < T { 0.5 } ? T { 0.5 } : T { 0.1 };
         }
+        return ScatterFunction(T { 0 }, upper, [&](const T q) -> T { return m.getComptonNormalizedScatterFactor(q); });
     }
 
 private:

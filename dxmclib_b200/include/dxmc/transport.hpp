@@ -22,6 +22,8 @@
 #include <chrono>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <stdexcept>
@@ -102,6 +104,25 @@ namespace detail {
         double maxWeight = 0; // largest possible photon birth weight
     };
 
+    // DXMCB200_TRACE=1: phase timings of Transport::operator() on stderr
+    struct PhaseTrace {
+        bool on = false;
+        std::chrono::steady_clock::time_point t = std::chrono::steady_clock::now();
+        PhaseTrace()
+        {
+            const char* env = std::getenv("DXMCB200_TRACE");
+            on = env && env[0] == '1';
+        }
+        void operator()(const char* what)
+        {
+            if (!on)
+                return;
+            const auto now = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[dxmcb200] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t).count());
+            t = now;
+        }
+    };
+
     template <typename V>
     inline void appendFloats(std::vector<float>& out, const V& v)
     {
@@ -141,16 +162,34 @@ public:
         requires std::is_base_of_v<World<T>, U>
     Result<T> operator()(const U& world, Source<T>* source, ProgressBar<T>* progressbar = nullptr, bool useSourceDoseCalibration = true)
     {
+        detail::PhaseTrace trace;
         if (!prepare(world, source))
             return Result<T>(world.size());
-        Result<T> result(world.size());
+        trace("prepare (total)");
+        Result<T> result(0);
+        bool completed = false;
+        if (progressbar) { // the progress image reads result.dose while the run is in flight (progressbar.hpp:86-109)
+            result = Result<T>(world.size());
+            trace("Result allocation");
+            completed = run(0, m_totalExposures, progressbar, &result, &world);
+        } else { // otherwise the three result arrays (zero-filled, page-faulted) are made while the GPU works
+            std::thread allocation([&]() { result = Result<T>(world.size()); });
+            struct Join {
+                std::thread& t;
+                ~Join() { t.join(); }
+            } join { allocation };
+            completed = run<U>(0, m_totalExposures, nullptr, nullptr, nullptr);
+        }
         result.numberOfHistories = m_histories;
-        const bool completed = run(0, m_totalExposures, progressbar, &result, &world);
+        result.simulationTime = m_lastRunTime;
+        trace("run");
         if (completed)
             collect(world, source, result, useSourceDoseCalibration, progressbar);
         else
             result.numberOfHistories = 0; // cancelled: all zeros, like a cancelled reference run
+        trace("collect");
         release();
+        trace("release");
         return result;
     }
 
@@ -165,19 +204,23 @@ public:
     bool prepare(const U& world, Source<T>* source, std::uint64_t historiesAllRanks = 0)
     {
         release();
+        detail::PhaseTrace trace;
         if (!world.isValid() || !source)
             return false;
         source->updateFromWorld(world);
         source->validate();
         if (!source->isValid())
             return false;
+        trace("  source update/validate");
         m_histories = source->historiesPerExposure() * source->totalExposures();
         m_totalExposures = source->totalExposures();
         m_attenuationLut.generate(world, source->maxPhotonEnergyProduced());
+        trace("  AttenuationLut::generate");
 
         m_flat = detail::FlatTables {};
         flattenLuts(m_flat);
         flattenExposures(world, *source, m_totalExposures, m_flat);
+        trace("  flatten tables/exposures");
 
         dxmcb200_ctx* raw = nullptr;
         const int created = dxmcb200_create(m_device, &raw);
@@ -185,7 +228,9 @@ public:
             throw std::runtime_error("dxmcb200: no usable CUDA device " + std::to_string(m_device) + " (status " + std::to_string(created)
                 + "); this library has no CPU fallback");
         m_ctx.reset(raw);
+        trace("  create context");
         uploadWorld(m_ctx.get(), world);
+        trace("  upload world");
         detail::check(m_ctx.get(), dxmcb200_set_luts(m_ctx.get(), &m_flat.luts), "set_luts");
         uploadBeamTables(m_ctx.get(), m_flat);
         int energyBits = 20, energySqBits = 10;
@@ -226,8 +271,9 @@ public:
         const auto start = std::chrono::system_clock::now();
         const int ran = dxmcb200_run(m_ctx.get(), m_flat.exposures.data(), begin, end, static_cast<int>(m_lowenergyCorrection), m_seed, &progress.cancel,
             callback, &progress);
+        m_lastRunTime = std::chrono::system_clock::now() - start;
         if (result)
-            result->simulationTime = std::chrono::system_clock::now() - start;
+            result->simulationTime = m_lastRunTime;
         detail::check(m_ctx.get(), ran, "run");
         dxmcb200_get_stats(m_ctx.get(), &m_stats);
         if (progressbar) {
@@ -468,6 +514,7 @@ private:
     int m_device = 0;
     std::uint64_t m_seed = 0xD1C02026ULL;
     dxmcb200_stats m_stats {};
+    std::chrono::duration<float> m_lastRunTime {};
     detail::ContextPtr m_ctx;
     detail::FlatTables m_flat;
     std::uint64_t m_totalExposures = 0;
