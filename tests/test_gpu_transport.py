@@ -95,6 +95,34 @@ def test_bit_reproducible_and_shard_invariant(gpu, product):
         assert T.bit_equal(x, z)
 
 
+def test_schedule_and_layout_invariance(gpu, product, monkeypatch):
+    """The grids do not depend on how the wavefront is scheduled or how the voxel grid is stored: wave size (down to
+    1024 photons, i.e. hundreds of waves and drains), re-fill batch, one or two wave pipelines, palette or 8-byte voxel
+    records all give bit-identical accumulators."""
+    sc = T.isotropic_scene(product, histories=40000, exposures=6, forced=True)
+    flat = T.flatten_scene(sc)
+    exps = T.exposures_of(sc)
+
+    def run(batch, palette, pipes):
+        monkeypatch.setenv("DXMCB200_BATCH", batch)
+        monkeypatch.setenv("DXMCB200_PALETTE", palette)
+        monkeypatch.setenv("DXMCB200_PIPES", pipes)
+        ctx = cabi.Context(0)  # the switches are read when the context is created
+        T.load_context(ctx, flat)
+        ctx.set_fixed_point(20, 10)
+        ctx.run(exps, 0, 6, model=1, seed=99)
+        raw = ctx.get_raw()
+        ctx.close()
+        return raw
+
+    base = run("4,25", "1", "2")
+    assert base[2].sum() > 50000
+    for setting in [("1,10", "1", "2"), ("32,12", "1", "1"), ("8,14", "0", "2"), ("4,25", "0", "1")]:
+        other = run(*setting)
+        for x, y in zip(base, other):
+            assert T.bit_equal(x, y), f"grids differ for DXMCB200_BATCH/PALETTE/PIPES = {setting}"
+
+
 def test_fixed_point_grid_against_oracle(gpu, product):
     """The raw 64-bit fixed-point grids against the restatement with the same streams and the same scales."""
     sc = T.isotropic_scene(product, histories=30000, exposures=3)
@@ -117,6 +145,32 @@ def test_fixed_point_grid_against_oracle(gpu, product):
     assert np.all(np.abs(e[same] - oe[same]) <= 64 * np.maximum(ev[same], 1) * 2 ** 6)
     np.testing.assert_allclose(e.sum() / 2.0 ** 22, oe.sum() / 2.0 ** 22, rtol=1e-5)
     np.testing.assert_allclose(e2.astype(np.float64).sum(), oe2.astype(np.float64).sum(), rtol=1e-4)
+
+
+def test_continuous_density_takes_record_grid(gpu, product):
+    """A world with more than 256 distinct {density, material} records cannot be palettised: the 8-byte record grid is
+    used and the result still follows the restatement history by history (densities scaled per voxel within 10 %, so
+    the majorant built for the nominal densities stays valid)."""
+    sc = T.isotropic_scene(product, histories=20000, exposures=3)
+    flat = dict(T.flatten_scene(sc))
+    rng = np.random.default_rng(5)
+    flat["density"] = (flat["density"] * rng.uniform(0.9, 1.0, flat["density"].size)).astype(np.float32)
+    assert np.unique(flat["density"]).size > 256
+    exps = T.exposures_of(sc)
+    ctx = cabi.Context(0)
+    T.load_context(ctx, flat)
+    ctx.set_fixed_point(22, 12)
+    ctx.run(exps, 0, 3, model=1, seed=11)
+    e, e2, ev = ctx.get_raw()
+    o = pyoracle.Oracle()
+    o.load(flat)
+    o.set_fixed_point(22, 12)
+    o.run(exps, 0, 3, model=1, seed=11, per_history_streams=True)
+    oe, _ = o.get_fixed()
+    _, oev, _ = o.get_raw()
+    assert ev.sum() > 10000
+    assert (ev.astype(np.int64) != oev.astype(np.int64)).mean() < 5e-3
+    np.testing.assert_allclose(e.sum() / 2.0 ** 22, oe.sum() / 2.0 ** 22, rtol=1e-4)
 
 
 def test_uneven_histories_and_empty_exposures(gpu, product):
