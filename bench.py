@@ -34,8 +34,8 @@ from dxmclib_b200 import phantoms  # noqa: E402
 from dxmclib_b200 import scene as S  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size transportKernel launch, from the committed
-# `ncu --set full` capture (profiles/r1_v4_*): null until measured for the current kernel version
-TRAFFIC_PER_LAUNCH = None
+# `ncu --set full` capture (profiles/r1_v4_*), bytes
+TRAFFIC_PER_LAUNCH = 7.119e9  # profiles/r1_v4_transportKernel_ncu_summary.csv: 5.182 GB read + 1.937 GB written, 2^25-record wave
 
 DIM = (512, 512, 400)
 SPACING = (1.0, 1.0, 1.0)
@@ -270,7 +270,7 @@ def main():
     # ---- roofline: algorithmic bytes per history from the kernel's own work counters (short counted run)
     ctx.enable_stats(True)
     ctx.clear()
-    for k in range(0, EXPOSURES, 36):  # every 36th exposure: the counters must sample the whole scan, not one end of it
+    for k in range(0, EXPOSURES, 180):  # every 180th exposure: the counters must sample the whole scan, not one end of it
         sc.b200_run(e0 + k, e0 + k + 1)
     st = ctx.stats()
     ctx.enable_stats(False)
