@@ -22,7 +22,7 @@ _u64p = C.POINTER(C.c_uint64)
 CABI_SYMBOLS = [
     "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world",
     "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point",
-    "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident",
+    "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident", "dxmcb200_run_strided",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
     "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
     "dxmcb200_sample_interaction",
@@ -204,6 +204,10 @@ class Context:
 
     def run_resident(self, begin, end, model=1, seed=1):
         self._chk(self.l.dxmcb200_run_resident(self.h, C.c_uint64(begin), C.c_uint64(end), int(model), C.c_uint64(seed)), "dxmcb200_run_resident")
+
+    def run_strided(self, first, stride, count, model=1, seed=1):
+        self._chk(self.l.dxmcb200_run_strided(self.h, C.c_uint64(first), C.c_uint64(stride), C.c_uint64(count), int(model), C.c_uint64(seed)),
+                  "dxmcb200_run_strided")
 
     def last_run_ms(self) -> float:
         ms = C.c_double(0)

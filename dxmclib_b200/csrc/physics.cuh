@@ -280,12 +280,17 @@ __device__ __forceinline__ uint32_t segmentIndex(const LutView& l, float logE, b
 __device__ __forceinline__ void attenuationAt(const LutView& l, uint32_t material, uint32_t segment, float logE, float& photo, float& compton,
     float& rayleigh)
 {
-    const float4* c = reinterpret_cast<const float4*>(l.coeff + (material * l.nSegments + segment) * kCoeffStride);
-    const float4 pc = __ldg(c); // photo {b, a}, Compton {b, a}
-    const float2 cr = __ldg(reinterpret_cast<const float2*>(c + 1));
-    photo = fastExp10(__fadd_rn(pc.x, __fmul_rn(pc.y, logE)));
-    compton = fastExp10(__fadd_rn(pc.z, __fmul_rn(pc.w, logE)));
-    rayleigh = fastExp10(__fadd_rn(cr.x, __fmul_rn(cr.y, logE)));
+    // one 256-bit load (sm_100 LDG.E.256) of the 32-byte record: photo {b, a}, Compton {b, a}, Rayleigh {b, a}, pad.
+    // Lanes of a warp sit in different (material, segment) records, so every load instruction costs one L1 pass per
+    // distinct line; ncu showed the former 128-bit + 64-bit pair taking 2 x 12.8 passes per warp-step.
+    const float* c = l.coeff + (material * l.nSegments + segment) * kCoeffStride;
+    float pb, pa, cb, ca, rb, ra, pad0, pad1;
+    asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+        : "=f"(pb), "=f"(pa), "=f"(cb), "=f"(ca), "=f"(rb), "=f"(ra), "=f"(pad0), "=f"(pad1)
+        : "l"(c));
+    photo = fastExp10(__fadd_rn(pb, __fmul_rn(pa, logE)));
+    compton = fastExp10(__fadd_rn(cb, __fmul_rn(ca, logE)));
+    rayleigh = fastExp10(__fadd_rn(rb, __fmul_rn(ra, logE)));
 }
 
 __device__ __forceinline__ void attenuation(const LutView& l, uint32_t material, float logE, float& photo, float& compton, float& rayleigh)

@@ -80,6 +80,7 @@ struct KernelParams {
     const dxmcb200_exposure* exposures; // absolute indexing
     const uint64_t* prefix; // [nExp+1] cumulative histories of the run's exposure range
     uint64_t expBegin; // first exposure of the run's range
+    uint64_t expStride; // the range holds exposures expBegin + k * expStride (multi-GPU interleaving), k < nExp
     uint32_t nExp;
     uint32_t uniformHistories; // >0: every exposure of the range has this many histories (< 2^31)
     uint64_t chunkBegin; // first history generateKernel makes, counted from the start of the range
@@ -172,7 +173,7 @@ __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant
                 e = lo;
                 history = g - __ldg(P.prefix + lo);
             }
-            const uint64_t exposure = P.expBegin + e;
+            const uint64_t exposure = P.expBegin + e * P.expStride;
             historyStream(P.seed, exposure, history, rng.state, rng.inc);
             p = sampleParticle(P.exposures[exposure], P.beams, rng);
             keep = transportToWorld(P.world, p);
@@ -222,41 +223,6 @@ struct Pending { // what an INTERACT lane needs from the step that found the eve
     uint32_t voxel;
     uint32_t material; // bits 0-7 material, bits 8-15 measurement flag (forced interaction when non-zero)
 };
-
-// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
-template <int L, bool kStats>
-__device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores)
-{
-    const uint32_t mat = pe.material & 0xffu;
-    const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
-    const float r3 = rng.uniform(attTotal);
-    if (r3 < pe.attPhoto) {
-        const float e = photoAbsorption<L>(P.lut, p, mat, rng);
-        if constexpr (kStats)
-            ++nScores;
-        if (p.energy < kEnergyCutoff) {
-            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
-            p.energy = 0.0f;
-            return false;
-        }
-        scoreEnergy(P, pe.voxel, e * p.weight);
-        energyChanged = true;
-    } else if (r3 < (pe.attPhoto + pe.attCompton)) {
-        const float e = comptonScatter<L>(P.lut, p, mat, rng);
-        if constexpr (kStats)
-            ++nScores;
-        if (p.energy < kEnergyCutoff) {
-            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
-            p.energy = 0.0f;
-            return false;
-        }
-        scoreEnergy(P, pe.voxel, e * p.weight);
-        energyChanged = true;
-    } else {
-        rayleighScatter<L>(P.lut, p, mat, rng);
-    }
-    return true;
-}
 
 // computeInteractionsForced (transport.hpp:523-581)
 template <int L, bool kStats>
@@ -333,6 +299,8 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
         __syncthreads();
     }
+    // shared-state-space address of the table: the look-up below is one LEA + LDS instead of a generic-window address
+    const unsigned paletteBase = static_cast<unsigned>(__cvta_generic_to_shared(sPalette));
 
     Rng rng { 0, 1 };
     Photon p {};
@@ -352,6 +320,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     unsigned ringPos = 0, ringEnd = 0; // ring slots of the current group not yet handed out: [ringPos, ringEnd)
     unsigned outPos = 0, outEnd = 0; // event slots of the current tile not yet written
     unsigned exhaustedMask = 0;
+    unsigned refillAt = P.refillBatch; // empty lanes that trigger a service: refillBatch + the exhausted ones
     enum { TILE_NEXT, TILE_END, SHARDS_TRIED, ISSUED, CONSUMED, COUNT0, COUNT1, IN_SHARD };
     volatile unsigned* const st = stage[threadIdx.x >> 5];
     if (lane < 8)
@@ -433,9 +402,10 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 voxel = voxelIndex(P.world, p.px, p.py, p.pz);
                 uint2 rec;
                 // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
-                if (paletteForm)
-                    rec = sPalette[__ldcg(P.world.palette + voxel)];
-                else
+                if (paletteForm) {
+                    const unsigned slot = paletteBase + 8u * __ldcg(P.world.palette + voxel);
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rec.x), "=r"(rec.y) : "r"(slot));
+                } else
                     rec = __ldcg(P.world.voxels + voxel);
                 const float density = __uint_as_float(rec.x);
                 material = rec.y;
@@ -443,7 +413,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                     ++cLookups;
                 float aP, aC, aR;
                 attenuationAt(P.lut, material & 0xffu, seg, logE, aP, aC, aR);
-                const float attTotal = (((0.0f + aP) + aC) + aR) * density;
+                const float attTotal = ((aP + aC) + aR) * density; // the reference's 0 + aP is aP exactly
                 eventProbability = attTotal * maxAttInv;
                 bool event = (material & 0xff00u) != 0; // measurement voxel: forced interaction, no draw
                 if (!event)
@@ -462,11 +432,11 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 }
             }
         }
+        const unsigned notStepping = __ballot_sync(kFull, state != STEP); // lanes with an event due, dead or exhausted
+        if (static_cast<unsigned>(__popc(notStepping)) < refillAt && notStepping != kFull)
+            continue; // keep stepping until enough lanes are empty
         const unsigned eventMask = __ballot_sync(kFull, state == EVENT);
         unsigned deadMask = __ballot_sync(kFull, state == DEAD);
-        const unsigned idle = eventMask | deadMask;
-        if (static_cast<unsigned>(__popc(idle)) < P.refillBatch && (idle | exhaustedMask) != kFull)
-            continue; // keep stepping until enough lanes are empty
 
         // ---- lanes with an interaction due append their photon to the event buffer and become empty
         if (eventMask) {
@@ -513,6 +483,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 if (state == DEAD)
                     state = EXHAUSTED;
                 exhaustedMask |= deadMask;
+                refillAt = P.refillBatch + static_cast<unsigned>(__popc(exhaustedMask));
                 break;
             }
             const unsigned rank = __popc(deadMask & laneLt);
@@ -554,11 +525,29 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     }
 }
 
-// ---- (c) interactions + (d) scoring: one event per thread ------------------------------------------
+// ---- (c) interactions + (d) scoring -----------------------------------------------------------------
+// The interaction channels cost very different numbers of instructions (photoelectric absorption: a few; Compton: a
+// rejection loop with a spline evaluation; Rayleigh: a binary search in the form-factor sampler inside a rejection
+// loop) and a warp pays for every channel any of its lanes takes: with one event per thread in arrival order ncu
+// showed the Rayleigh code running with 2.3 and the Compton loop with 9 of 32 lanes active, 30 % and 46 % of the
+// kernel's instructions. So a block first draws the channel of each of its 256 events (the first random number of
+// computeInteractions, transport.hpp:591-594), then counting-sorts the photons by channel through shared memory, and
+// only then samples: warps are channel-pure (except at the class boundaries), the cheap channels retire at once.
+// Every history still consumes its own random stream in the reference's order, so results are unchanged bit for bit.
+enum EventClass : uint32_t { CLS_COMPTON = 0, CLS_RAYLEIGH = 1, CLS_FORCED = 2, CLS_PHOTO = 3, CLS_NONE = 4 };
+constexpr unsigned kClasses = 4;
+constexpr unsigned kWarpsPerBlock = kThreads / 32;
+
 template <int L, bool kStats>
-__global__ void __launch_bounds__(kThreads) interactKernel(const __grid_constant__ KernelParams P)
+__global__ void __launch_bounds__(kThreads, 5) interactKernel(const __grid_constant__ KernelParams P)
 {
+    __shared__ float4 sPosE[kThreads], sDirW[kThreads], sLut[kThreads];
+    __shared__ uint4 sRng[kThreads];
+    __shared__ uint2 sWhere[kThreads];
+    __shared__ unsigned sCount[kClasses * kWarpsPerBlock + 1]; // events per (class, warp), then their exclusive prefix sums
+
     const unsigned lane = threadIdx.x & 31u;
+    const unsigned warp = threadIdx.x >> 5;
     const unsigned laneLt = (1u << lane) - 1u;
     uint32_t cInter = 0, cScores = 0;
     // block b works on event shard b % kShards together with the other blocks of the same residue
@@ -566,32 +555,111 @@ __global__ void __launch_bounds__(kThreads) interactKernel(const __grid_constant
     const unsigned shard = blockIdx.x % kShards;
     const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion); // a multiple of kEventTile
     const EventRecord* const region = P.events + static_cast<size_t>(shard) * P.eventRegion;
-    for (unsigned i = (blockIdx.x / kShards) * kThreads + threadIdx.x; i < nSlots; i += blocksPerShard * kThreads) {
-        const EventRecord* e = region + i;
-        const uint4 where = e->where;
+    for (unsigned tile = (blockIdx.x / kShards) * kThreads; tile < nSlots; tile += blocksPerShard * kThreads) {
+        // ---- phase 1: load the event, draw its channel
+        const unsigned i = tile + threadIdx.x;
+        uint32_t cls = CLS_NONE;
+        float4 a, b, d;
+        uint4 c;
+        uint2 where = make_uint2(0u, kNoEvent);
+        if (i < nSlots) {
+            const EventRecord* e = region + i;
+            const uint4 w = e->where;
+            where = make_uint2(w.x, w.y);
+            if (w.y != kNoEvent) {
+                a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
+                c = e->photon.rng;
+                if (w.y & 0xff00u) {
+                    cls = CLS_FORCED; // computeInteractionsForced draws nothing before the photoelectric part
+                } else {
+                    float attPhoto, attCompton, attRayleigh;
+                    attenuationAt(P.lut, w.y & 0xffu, __float_as_uint(d.z), d.x, attPhoto, attCompton, attRayleigh);
+                    Rng rng { (static_cast<uint64_t>(c.y) << 32) | c.x, (static_cast<uint64_t>(c.w) << 32) | c.z };
+                    const float attTotal = ((0.0f + attPhoto) + attCompton) + attRayleigh;
+                    const float r3 = rng.uniform(attTotal);
+                    cls = r3 < attPhoto ? CLS_PHOTO : r3 < (attPhoto + attCompton) ? CLS_COMPTON : CLS_RAYLEIGH;
+                    c.x = static_cast<uint32_t>(rng.state), c.y = static_cast<uint32_t>(rng.state >> 32);
+                }
+            }
+        }
+        // ---- counting sort by class over the block
+        unsigned myRank = 0;
+#pragma unroll
+        for (unsigned k = 0; k < kClasses; ++k) {
+            const unsigned m = __ballot_sync(kFull, cls == k);
+            if (cls == k)
+                myRank = __popc(m & laneLt);
+            if (lane == 0)
+                sCount[k * kWarpsPerBlock + warp] = __popc(m);
+        }
+        __syncthreads();
+        if (warp == 0) { // exclusive prefix sums in (class, warp) order = first sorted slot of every (class, warp) group
+            const unsigned v = sCount[lane];
+            unsigned incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(kFull, incl, o);
+                if (static_cast<int>(lane) >= o)
+                    incl += t;
+            }
+            __syncwarp();
+            sCount[lane] = incl - v;
+            if (lane == 31)
+                sCount[32] = incl;
+        }
+        __syncthreads();
+        if (cls != CLS_NONE) {
+            const unsigned dst = sCount[cls * kWarpsPerBlock + warp] + myRank;
+            sPosE[dst] = a, sDirW[dst] = b, sLut[dst] = d, sRng[dst] = c, sWhere[dst] = where;
+        }
+        __syncthreads();
+
+        // ---- phase 2: thread t samples the interaction of sorted event t
+        const unsigned nEvents = sCount[32];
+        const unsigned t = threadIdx.x;
         bool alive = false;
         Photon p {};
         Rng rng { 0, 1 };
         float logE = 0.0f, maxAttInv = 0.0f;
         uint32_t seg = 0;
-        if (where.y != kNoEvent) {
-            const float4 a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
-            const uint4 c = e->photon.rng;
+        if (t < nEvents) {
+            const uint32_t myCls = t < sCount[CLS_RAYLEIGH * kWarpsPerBlock] ? CLS_COMPTON
+                : t < sCount[CLS_FORCED * kWarpsPerBlock]                     ? CLS_RAYLEIGH
+                : t < sCount[CLS_PHOTO * kWarpsPerBlock]                      ? CLS_FORCED
+                                                                               : CLS_PHOTO;
+            a = sPosE[t], b = sDirW[t], d = sLut[t];
+            c = sRng[t];
+            where = sWhere[t];
             p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
             p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
             rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
             rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
             logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
-            Pending pe;
-            pe.eventProbability = d.w;
-            pe.voxel = where.x;
-            pe.material = where.y;
-            attenuationAt(P.lut, where.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
+            const uint32_t mat = where.y & 0xffu;
             bool energyChanged = false;
-            if (where.y & 0xff00u)
+            alive = true;
+            if (myCls == CLS_COMPTON || myCls == CLS_PHOTO) { // computeInteractions, transport.hpp:596-627
+                const float e = myCls == CLS_COMPTON ? comptonScatter<L>(P.lut, p, mat, rng) : photoAbsorption<L>(P.lut, p, mat, rng);
+                if constexpr (kStats)
+                    ++cScores;
+                if (p.energy < kEnergyCutoff) {
+                    scoreEnergy(P, where.x, (e + p.energy) * p.weight);
+                    p.energy = 0.0f;
+                    alive = false;
+                } else {
+                    scoreEnergy(P, where.x, e * p.weight);
+                    energyChanged = true;
+                }
+            } else if (myCls == CLS_RAYLEIGH) {
+                rayleighScatter<L>(P.lut, p, mat, rng);
+            } else {
+                Pending pe;
+                pe.eventProbability = d.w;
+                pe.voxel = where.x;
+                pe.material = where.y;
+                attenuationAt(P.lut, mat, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
                 alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
-            else
-                alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
+            }
             if constexpr (kStats)
                 ++cInter;
             // Russian roulette (transport.hpp:684-693)
@@ -608,16 +676,17 @@ __global__ void __launch_bounds__(kThreads) interactKernel(const __grid_constant
                 energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
         }
         const unsigned aliveMask = __ballot_sync(kFull, alive);
-        if (aliveMask == 0)
-            continue;
-        PhotonRecord* r = appendPhotons(P, aliveMask, lane);
-        if (r) {
-            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
-            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
-                static_cast<uint32_t>(rng.inc >> 32));
-            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
+        if (aliveMask != 0) {
+            PhotonRecord* r = appendPhotons(P, aliveMask, lane);
+            if (r) {
+                r->posE = make_float4(p.px, p.py, p.pz, p.energy);
+                r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+                r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                    static_cast<uint32_t>(rng.inc >> 32));
+                r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
+            }
         }
+        __syncthreads(); // the staging arrays are rewritten by the next tile
     }
     if constexpr (kStats) {
         const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
@@ -1008,16 +1077,16 @@ unsigned maxTransportBlocks(const dxmcb200_ctx* c)
     return static_cast<unsigned>(c->smCount) * static_cast<unsigned>(std::max({ a, b, 1 }));
 }
 
+// transports exposures expBegin + k * stride, k in [0, nExp)
 int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmcb200_exposure* devExposures, uint64_t expBegin,
-    uint64_t expEnd, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
+    uint64_t nExp, uint64_t stride, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
 {
     if ((!c->dVoxels && !c->dPalette) || !c->dLutBlob)
         return DXMCB200_ERR_STATE;
-    if (model < 0 || model > 2 || expEnd < expBegin)
+    if (model < 0 || model > 2 || stride == 0)
         return DXMCB200_ERR_ARG;
     CU_CHECK(c, cudaSetDevice(c->device));
     c->lastRunMs = 0;
-    const uint64_t nExp = expEnd - expBegin;
     if (nExp == 0)
         return DXMCB200_OK;
     if (nExp >= (1ULL << 32)) {
@@ -1029,8 +1098,8 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     std::vector<uint64_t> prefix(nExp + 1, 0);
     bool uniform = hostExposures[expBegin].histories > 0 && hostExposures[expBegin].histories < (1ULL << 31);
     for (uint64_t e = 0; e < nExp; ++e) {
-        prefix[e + 1] = prefix[e] + hostExposures[expBegin + e].histories;
-        uniform = uniform && hostExposures[expBegin + e].histories == hostExposures[expBegin].histories;
+        prefix[e + 1] = prefix[e] + hostExposures[expBegin + e * stride].histories;
+        uniform = uniform && hostExposures[expBegin + e * stride].histories == hostExposures[expBegin].histories;
     }
     const uint64_t total = prefix.back();
     if (total == 0) {
@@ -1081,6 +1150,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     base.exposures = devExposures;
     base.prefix = c->dPrefix;
     base.expBegin = expBegin;
+    base.expStride = stride;
     base.nExp = static_cast<uint32_t>(nExp);
     base.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
     base.refillBatch = c->refillBatch;
@@ -1661,7 +1731,20 @@ int dxmcb200_run_resident(dxmcb200_ctx* c, uint64_t expBegin, uint64_t expEnd, i
 {
     if (!c || !c->dExposures || expEnd > c->nExposuresResident)
         return DXMCB200_ERR_STATE;
-    return runRange(c, c->hExposures.data(), c->dExposures, expBegin, expEnd, model, seed, nullptr, nullptr, nullptr);
+    return runRange(c, c->hExposures.data(), c->dExposures, expBegin, expEnd - expBegin, 1, model, seed, nullptr, nullptr, nullptr);
+}
+
+int dxmcb200_run_strided(dxmcb200_ctx* c, uint64_t expFirst, uint64_t expStride, uint64_t expCount, int model, uint64_t seed)
+{
+    if (!c || !c->dExposures)
+        return DXMCB200_ERR_STATE;
+    if (expStride == 0)
+        return DXMCB200_ERR_ARG;
+    if (expCount == 0)
+        return DXMCB200_OK;
+    if (expFirst >= c->nExposuresResident || (c->nExposuresResident - 1 - expFirst) / expStride < expCount - 1)
+        return DXMCB200_ERR_STATE;
+    return runRange(c, c->hExposures.data(), c->dExposures, expFirst, expCount, expStride, model, seed, nullptr, nullptr, nullptr);
 }
 
 int dxmcb200_run(dxmcb200_ctx* c, const dxmcb200_exposure* exposures, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed,
@@ -1674,7 +1757,7 @@ int dxmcb200_run(dxmcb200_ctx* c, const dxmcb200_exposure* exposures, uint64_t e
     const int up = dxmcb200_upload_exposures(c, exposures, expEnd);
     if (up != DXMCB200_OK)
         return up;
-    return runRange(c, exposures, c->dExposures, expBegin, expEnd, model, seed, cancel, cb, user);
+    return runRange(c, exposures, c->dExposures, expBegin, expEnd - expBegin, 1, model, seed, cancel, cb, user);
 }
 
 int dxmcb200_last_run_ms(dxmcb200_ctx* c, double* ms)

@@ -747,6 +747,18 @@ int dxs_b200_run(dxs_scene* s, uint64_t expBegin, uint64_t expEnd, double* kerne
     });
 }
 
+int dxs_b200_run_strided(dxs_scene* s, uint64_t expFirst, uint64_t expStride, uint64_t expCount, double* kernelMs)
+{
+    if (!s || !s->prepared)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        s->prepared->runStrided(expFirst, expStride, expCount);
+        if (kernelMs)
+            dxmcb200_last_run_ms(s->prepared->context(), kernelMs);
+        return DXS_OK;
+    });
+}
+
 int dxs_b200_collect(dxs_scene* s, int outputMode, int useCalibration, uint64_t histories, float* dose, uint32_t* nEvents, float* variance,
     dxs_result_info* info)
 {

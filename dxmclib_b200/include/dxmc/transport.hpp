@@ -284,6 +284,18 @@ public:
         return ran != DXMCB200_ERR_CANCELLED;
     }
 
+    // multi-GPU interleaving: transport exposures first, first + stride, ... (count of them); see dxmcb200_run_strided
+    void runStrided(std::uint64_t first, std::uint64_t stride, std::uint64_t count)
+    {
+        if (!m_ctx)
+            throw std::runtime_error("dxmcb200: Transport::runStrided called before prepare");
+        const auto start = std::chrono::system_clock::now();
+        const int ran = dxmcb200_run_strided(m_ctx.get(), first, stride, count, static_cast<int>(m_lowenergyCorrection), m_seed);
+        m_lastRunTime = std::chrono::system_clock::now() - start;
+        detail::check(m_ctx.get(), ran, "run_strided");
+        dxmcb200_get_stats(m_ctx.get(), &m_stats);
+    }
+
     // decode the accumulators with the reference's post-processing for the current output mode
     template <typename U>
         requires std::is_base_of_v<World<T>, U>

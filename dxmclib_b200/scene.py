@@ -71,7 +71,7 @@ SCENE_SYMBOLS = [
     "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
     "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport",
-    "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
+    "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_run_strided", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
 ]
 
 _libs: dict[str, C.CDLL] = {}
@@ -425,6 +425,13 @@ class Scene:
         """Transport exposures [exp_begin, exp_end); returns the CUDA-event time of the kernels in ms."""
         ms = C.c_double(0)
         _chk(self.lib.dxs_b200_run(self.h, C.c_uint64(exp_begin), C.c_uint64(exp_end), C.byref(ms)), "dxs_b200_run")
+        return float(ms.value)
+
+    def b200_run_strided(self, exp_first, exp_stride, exp_count) -> float:
+        """Transport exposures exp_first + k * exp_stride, k < exp_count (the interleaved multi-GPU partition)."""
+        ms = C.c_double(0)
+        _chk(self.lib.dxs_b200_run_strided(self.h, C.c_uint64(exp_first), C.c_uint64(exp_stride), C.c_uint64(exp_count), C.byref(ms)),
+             "dxs_b200_run_strided")
         return float(ms.value)
 
     def b200_collect(self, output=OUT_EV_PER_HISTORY, use_calibration=False, histories=0, want_events=True,

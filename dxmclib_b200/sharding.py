@@ -15,6 +15,14 @@ def exposure_block(n_exposures: int, rank: int, world_size: int) -> tuple[int, i
     return begin, begin + base + (1 if rank < extra else 0)
 
 
+def exposure_stride(n_exposures: int, rank: int, world_size: int) -> tuple[int, int, int]:
+    """(first, stride, count) of the interleaved partition: rank r transports exposures r, r + N, r + 2N, ... Every GPU
+    then sees the same mix of scan positions (a CT spiral's cost per history varies along the patient), so the slowest
+    rank is no slower than the average one; the summed grids are the same bits as with exposure_block."""
+    n, r, w = int(n_exposures), int(rank), int(world_size)
+    return r, w, (n - r + w - 1) // w if r < n else 0
+
+
 def fixed_point_bits(total_histories_all_ranks: int, max_energy_weight: float) -> tuple[int, int]:
     """The fixed-point scales every rank must agree on (dxmcb200_suggest_fixed_point over the WHOLE job)."""
     e, e2 = C.c_int(0), C.c_int(0)

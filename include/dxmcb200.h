@@ -149,6 +149,12 @@ int dxmcb200_run(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t exp
  * dxmcb200_upload_exposures); used by bench.py's device-resident timing. */
 int dxmcb200_upload_exposures(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t n);
 int dxmcb200_run_resident(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed);
+/* Interleaved partition for multi-GPU runs: transports the resident exposures exp_first + k * exp_stride,
+ * k in [0, exp_count). Rank r of N calls (r, N, ceil((n - r) / N)): every GPU then sees the same mix of scan
+ * positions ("or strided for load balance"), and because exposures are indexed absolutely the summed
+ * grids stay bit-identical to the single-GPU grids. */
+int dxmcb200_run_strided(dxmcb200_ctx*, uint64_t exp_first, uint64_t exp_stride, uint64_t exp_count, int low_energy_model,
+    uint64_t seed);
 
 /* milliseconds the transport kernels of the last run took (CUDA events on the ctx stream) */
 int dxmcb200_last_run_ms(dxmcb200_ctx*, double* kernel_ms);

@@ -209,6 +209,8 @@ int dxs_transport(dxs_scene*, int model, int output_mode, int use_calibration, u
 int dxs_b200_prepare(dxs_scene*, int device, int model, uint64_t seed, uint64_t total_histories_all_ranks);
 /* Transport::run on exposures [begin, end); kernel_ms (may be NULL) = CUDA-event time of the transport kernels */
 int dxs_b200_run(dxs_scene*, uint64_t exp_begin, uint64_t exp_end, double* kernel_ms);
+/* Transport::runStrided: exposures exp_first + k * exp_stride, k < exp_count (interleaved multi-GPU partition) */
+int dxs_b200_run_strided(dxs_scene*, uint64_t exp_first, uint64_t exp_stride, uint64_t exp_count, double* kernel_ms);
 /* Transport::collect: decode accumulators into Result arrays (any pointer may be NULL) */
 int dxs_b200_collect(dxs_scene*, int output_mode, int use_calibration, uint64_t histories, float* dose, uint32_t* n_events,
     float* variance, dxs_result_info* info);

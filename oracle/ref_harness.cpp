@@ -825,6 +825,7 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
 // B200 extensions do not exist in the reference
 int dxs_b200_prepare(dxs_scene*, int, int, uint64_t, uint64_t) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_run(dxs_scene*, uint64_t, uint64_t, double*) { return DXS_ERR_UNSUPPORTED; }
+int dxs_b200_run_strided(dxs_scene*, uint64_t, uint64_t, uint64_t, double*) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_collect(dxs_scene*, int, int, uint64_t, float*, uint32_t*, float*, dxs_result_info*) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_context(dxs_scene*, void**) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_release(dxs_scene*) { return DXS_ERR_UNSUPPORTED; }

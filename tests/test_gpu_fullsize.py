@@ -34,6 +34,15 @@ def test_full_size_ct_spiral_properties(gpu, product):
     again = ctx.get_raw()
     for x, y in zip(whole, again):
         assert T.bit_equal(x, y)
+    # third run, as the interleaved 3-GPU partition (rank r: exposures r, r+3, ...): same bits again
+    from dxmclib_b200 import sharding
+
+    ctx.clear()
+    for rank in range(3):
+        sc.b200_run_strided(*sharding.exposure_stride(3600, rank, 3))
+    strided = ctx.get_raw()
+    for x, y in zip(whole, strided):
+        assert T.bit_equal(x, y)
     # energy bookkeeping: nothing is scored outside the body+table, and less energy is deposited than emitted
     mat = phantom[0]
     energy_kev = whole[0].astype(np.float64) / 2.0 ** 0  # fixed point, decode below

@@ -11,6 +11,7 @@ for b in settings:
                          env=env, capture_output=True, text=True)
     try:
         j = json.loads(out.stdout.strip().splitlines()[-1])
-        print(f"setting {b:10s} value {j['value']:.4e} hist/s  kernel_ms/step {j['roofline']['kernel_ms_per_step']:.1f}", flush=True)
+        km = j['roofline']['kernel_ms_per_step']
+        print(f"setting {b:10s} value {j['value']:.4e} hist/s  ms/step {j['ms_per_step']:.1f}  kernel ms/step " + " ".join(f"{k}={v:.0f}" for k, v in km.items()), flush=True)
     except Exception as e:
         print("setting", b, "failed", e, out.stderr[-500:], flush=True)
