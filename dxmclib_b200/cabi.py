@@ -20,7 +20,7 @@ _u64p = C.POINTER(C.c_uint64)
 
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
-    "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world",
+    "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_trim_pool",
     "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident", "dxmcb200_run_strided",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
@@ -139,6 +139,13 @@ class Context:
             w.measurement = me.ctypes.data_as(_u8p)
         self._chk(self.l.dxmcb200_set_world(self.h, C.byref(w)), "dxmcb200_set_world")
         self.n_voxels = int(np.prod([int(x) for x in dim]))
+
+    def material_max_density(self, n_materials: int) -> np.ndarray:
+        """Per-material maximum density of the uploaded grid (device pass; input of the Woodcock majorant)."""
+        out = np.zeros(int(n_materials), np.float32)
+        self._chk(self.l.dxmcb200_material_max_density(self.h, C.c_uint32(int(n_materials)), out.ctypes.data_as(_f32p)),
+                  "dxmcb200_material_max_density")
+        return out
 
     def set_luts_from_scene(self, sc: "_scene.Scene"):
         """Flatten the LUT tables of a scene (after lut_generate) with the layout of dxmcb200_luts."""

@@ -19,9 +19,11 @@
 // One wave = births + survivors of the previous wave, at most `waveRecords` photons; the host tops every wave up
 // with new births until all histories are issued and then drains. Scoring is integer atomics and every history
 // carries its own random stream, so results do not depend on the wave size, scheduling or GPU partition.
+#include "hostio.cuh"
 #include "physics.cuh"
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -223,6 +225,41 @@ struct Pending { // what an INTERACT lane needs from the step that found the eve
     uint32_t voxel;
     uint32_t material; // bits 0-7 material, bits 8-15 measurement flag (forced interaction when non-zero)
 };
+
+// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
+template <int L, bool kStats>
+__device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores)
+{
+    const uint32_t mat = pe.material & 0xffu;
+    const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
+    const float r3 = rng.uniform(attTotal);
+    if (r3 < pe.attPhoto) {
+        const float e = photoAbsorption<L>(P.lut, p, mat, rng);
+        if constexpr (kStats)
+            ++nScores;
+        if (p.energy < kEnergyCutoff) {
+            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
+            p.energy = 0.0f;
+            return false;
+        }
+        scoreEnergy(P, pe.voxel, e * p.weight);
+        energyChanged = true;
+    } else if (r3 < (pe.attPhoto + pe.attCompton)) {
+        const float e = comptonScatter<L>(P.lut, p, mat, rng);
+        if constexpr (kStats)
+            ++nScores;
+        if (p.energy < kEnergyCutoff) {
+            scoreEnergy(P, pe.voxel, (e + p.energy) * p.weight);
+            p.energy = 0.0f;
+            return false;
+        }
+        scoreEnergy(P, pe.voxel, e * p.weight);
+        energyChanged = true;
+    } else {
+        rayleighScatter<L>(P.lut, p, mat, rng);
+    }
+    return true;
+}
 
 // computeInteractionsForced (transport.hpp:523-581)
 template <int L, bool kStats>
@@ -525,29 +562,11 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     }
 }
 
-// ---- (c) interactions + (d) scoring -----------------------------------------------------------------
-// The interaction channels cost very different numbers of instructions (photoelectric absorption: a few; Compton: a
-// rejection loop with a spline evaluation; Rayleigh: a binary search in the form-factor sampler inside a rejection
-// loop) and a warp pays for every channel any of its lanes takes: with one event per thread in arrival order ncu
-// showed the Rayleigh code running with 2.3 and the Compton loop with 9 of 32 lanes active, 30 % and 46 % of the
-// kernel's instructions. So a block first draws the channel of each of its 256 events (the first random number of
-// computeInteractions, transport.hpp:591-594), then counting-sorts the photons by channel through shared memory, and
-// only then samples: warps are channel-pure (except at the class boundaries), the cheap channels retire at once.
-// Every history still consumes its own random stream in the reference's order, so results are unchanged bit for bit.
-enum EventClass : uint32_t { CLS_COMPTON = 0, CLS_RAYLEIGH = 1, CLS_FORCED = 2, CLS_PHOTO = 3, CLS_NONE = 4 };
-constexpr unsigned kClasses = 4;
-constexpr unsigned kWarpsPerBlock = kThreads / 32;
-
+// ---- (c) interactions + (d) scoring: one event per thread ------------------------------------------
 template <int L, bool kStats>
-__global__ void __launch_bounds__(kThreads, 5) interactKernel(const __grid_constant__ KernelParams P)
+__global__ void __launch_bounds__(kThreads) interactKernel(const __grid_constant__ KernelParams P)
 {
-    __shared__ float4 sPosE[kThreads], sDirW[kThreads], sLut[kThreads];
-    __shared__ uint4 sRng[kThreads];
-    __shared__ uint2 sWhere[kThreads];
-    __shared__ unsigned sCount[kClasses * kWarpsPerBlock + 1]; // events per (class, warp), then their exclusive prefix sums
-
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned warp = threadIdx.x >> 5;
     const unsigned laneLt = (1u << lane) - 1u;
     uint32_t cInter = 0, cScores = 0;
     // block b works on event shard b % kShards together with the other blocks of the same residue
@@ -555,111 +574,32 @@ __global__ void __launch_bounds__(kThreads, 5) interactKernel(const __grid_const
     const unsigned shard = blockIdx.x % kShards;
     const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion); // a multiple of kEventTile
     const EventRecord* const region = P.events + static_cast<size_t>(shard) * P.eventRegion;
-    for (unsigned tile = (blockIdx.x / kShards) * kThreads; tile < nSlots; tile += blocksPerShard * kThreads) {
-        // ---- phase 1: load the event, draw its channel
-        const unsigned i = tile + threadIdx.x;
-        uint32_t cls = CLS_NONE;
-        float4 a, b, d;
-        uint4 c;
-        uint2 where = make_uint2(0u, kNoEvent);
-        if (i < nSlots) {
-            const EventRecord* e = region + i;
-            const uint4 w = e->where;
-            where = make_uint2(w.x, w.y);
-            if (w.y != kNoEvent) {
-                a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
-                c = e->photon.rng;
-                if (w.y & 0xff00u) {
-                    cls = CLS_FORCED; // computeInteractionsForced draws nothing before the photoelectric part
-                } else {
-                    float attPhoto, attCompton, attRayleigh;
-                    attenuationAt(P.lut, w.y & 0xffu, __float_as_uint(d.z), d.x, attPhoto, attCompton, attRayleigh);
-                    Rng rng { (static_cast<uint64_t>(c.y) << 32) | c.x, (static_cast<uint64_t>(c.w) << 32) | c.z };
-                    const float attTotal = ((0.0f + attPhoto) + attCompton) + attRayleigh;
-                    const float r3 = rng.uniform(attTotal);
-                    cls = r3 < attPhoto ? CLS_PHOTO : r3 < (attPhoto + attCompton) ? CLS_COMPTON : CLS_RAYLEIGH;
-                    c.x = static_cast<uint32_t>(rng.state), c.y = static_cast<uint32_t>(rng.state >> 32);
-                }
-            }
-        }
-        // ---- counting sort by class over the block
-        unsigned myRank = 0;
-#pragma unroll
-        for (unsigned k = 0; k < kClasses; ++k) {
-            const unsigned m = __ballot_sync(kFull, cls == k);
-            if (cls == k)
-                myRank = __popc(m & laneLt);
-            if (lane == 0)
-                sCount[k * kWarpsPerBlock + warp] = __popc(m);
-        }
-        __syncthreads();
-        if (warp == 0) { // exclusive prefix sums in (class, warp) order = first sorted slot of every (class, warp) group
-            const unsigned v = sCount[lane];
-            unsigned incl = v;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(kFull, incl, o);
-                if (static_cast<int>(lane) >= o)
-                    incl += t;
-            }
-            __syncwarp();
-            sCount[lane] = incl - v;
-            if (lane == 31)
-                sCount[32] = incl;
-        }
-        __syncthreads();
-        if (cls != CLS_NONE) {
-            const unsigned dst = sCount[cls * kWarpsPerBlock + warp] + myRank;
-            sPosE[dst] = a, sDirW[dst] = b, sLut[dst] = d, sRng[dst] = c, sWhere[dst] = where;
-        }
-        __syncthreads();
-
-        // ---- phase 2: thread t samples the interaction of sorted event t
-        const unsigned nEvents = sCount[32];
-        const unsigned t = threadIdx.x;
+    for (unsigned i = (blockIdx.x / kShards) * kThreads + threadIdx.x; i < nSlots; i += blocksPerShard * kThreads) {
+        const EventRecord* e = region + i;
+        const uint4 where = e->where;
         bool alive = false;
         Photon p {};
         Rng rng { 0, 1 };
         float logE = 0.0f, maxAttInv = 0.0f;
         uint32_t seg = 0;
-        if (t < nEvents) {
-            const uint32_t myCls = t < sCount[CLS_RAYLEIGH * kWarpsPerBlock] ? CLS_COMPTON
-                : t < sCount[CLS_FORCED * kWarpsPerBlock]                     ? CLS_RAYLEIGH
-                : t < sCount[CLS_PHOTO * kWarpsPerBlock]                      ? CLS_FORCED
-                                                                               : CLS_PHOTO;
-            a = sPosE[t], b = sDirW[t], d = sLut[t];
-            c = sRng[t];
-            where = sWhere[t];
+        if (where.y != kNoEvent) {
+            const float4 a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
+            const uint4 c = e->photon.rng;
             p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
             p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
             rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
             rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
             logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
-            const uint32_t mat = where.y & 0xffu;
+            Pending pe;
+            pe.eventProbability = d.w;
+            pe.voxel = where.x;
+            pe.material = where.y;
+            attenuationAt(P.lut, where.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
             bool energyChanged = false;
-            alive = true;
-            if (myCls == CLS_COMPTON || myCls == CLS_PHOTO) { // computeInteractions, transport.hpp:596-627
-                const float e = myCls == CLS_COMPTON ? comptonScatter<L>(P.lut, p, mat, rng) : photoAbsorption<L>(P.lut, p, mat, rng);
-                if constexpr (kStats)
-                    ++cScores;
-                if (p.energy < kEnergyCutoff) {
-                    scoreEnergy(P, where.x, (e + p.energy) * p.weight);
-                    p.energy = 0.0f;
-                    alive = false;
-                } else {
-                    scoreEnergy(P, where.x, e * p.weight);
-                    energyChanged = true;
-                }
-            } else if (myCls == CLS_RAYLEIGH) {
-                rayleighScatter<L>(P.lut, p, mat, rng);
-            } else {
-                Pending pe;
-                pe.eventProbability = d.w;
-                pe.voxel = where.x;
-                pe.material = where.y;
-                attenuationAt(P.lut, mat, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
+            if (where.y & 0xff00u)
                 alive = interactForced<L, kStats>(P, p, pe, rng, energyChanged, cScores);
-            }
+            else
+                alive = interact<L, kStats>(P, p, pe, rng, energyChanged, cScores);
             if constexpr (kStats)
                 ++cInter;
             // Russian roulette (transport.hpp:684-693)
@@ -676,17 +616,16 @@ __global__ void __launch_bounds__(kThreads, 5) interactKernel(const __grid_const
                 energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
         }
         const unsigned aliveMask = __ballot_sync(kFull, alive);
-        if (aliveMask != 0) {
-            PhotonRecord* r = appendPhotons(P, aliveMask, lane);
-            if (r) {
-                r->posE = make_float4(p.px, p.py, p.pz, p.energy);
-                r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-                r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
-                    static_cast<uint32_t>(rng.inc >> 32));
-                r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
-            }
+        if (aliveMask == 0)
+            continue;
+        PhotonRecord* r = appendPhotons(P, aliveMask, lane);
+        if (r) {
+            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
+            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                static_cast<uint32_t>(rng.inc >> 32));
+            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
         }
-        __syncthreads(); // the staging arrays are rewritten by the next tile
     }
     if constexpr (kStats) {
         const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
@@ -798,6 +737,24 @@ __global__ void paletteIndexKernel(const float* __restrict__ density, const uint
             h = (h + 1) & (kPaletteSlots - 1);
         out[i] = static_cast<uint8_t>(slotIndex[h]);
     }
+}
+
+// Per-material maximum density of the grid: the input of the Woodcock majorant (attenuationinterpolator.hpp:48-59,
+// where it is one transform_reduce over all voxels per material). Densities are non-negative (World::validate), so
+// their bit patterns order like unsigned integers; block maxima in shared memory, one atomicMax per material and block.
+__global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, unsigned* __restrict__ maxBits)
+{
+    __shared__ unsigned sMax[256];
+    sMax[threadIdx.x] = 0u;
+    __syncthreads();
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint2 r = records[i];
+        if (sMax[r.y & 0xffu] < r.x) // racy pre-check only saves atomics; the atomicMax decides
+            atomicMax(&sMax[r.y & 0xffu], r.x);
+    }
+    __syncthreads();
+    if (sMax[threadIdx.x])
+        atomicMax(maxBits + threadIdx.x, sMax[threadIdx.x]);
 }
 
 // normalizeScoring / energyImpartedToDose (transport.hpp:780-816) fused with the fixed-point decode
@@ -997,7 +954,7 @@ struct dxmcb200_ctx {
     int energyBits = 20, energySqBits = 10;
     bool collectStats = false;
     uint32_t waveRecords = 1u << 25; // photons per wave (2 GiB per photon buffer, 2.5 GiB of event records)
-    uint32_t refillBatch = 4; // empty lanes that make a warp stop stepping and re-fill
+    uint32_t refillBatch = 8; // empty lanes that make a warp stop stepping and re-fill (measured: 4: 2.17e9, 8: 2.20e9, 12: 2.18e9 histories/s)
 
     double lastRunMs = 0, totalMs = 0;
     uint64_t launches = 0;
@@ -1125,9 +1082,9 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     const uint64_t eventRegion = (photonRegion + warpsPerShard * kEventTile + kEventTile - 1) / kEventTile * kEventTile;
     if (photonRegion > c->photonRegion || eventRegion > c->eventRegion) {
         for (auto& pipe : c->pipes) {
-            cudaFree(pipe.dPhotons[0]);
-            cudaFree(pipe.dPhotons[1]);
-            cudaFree(pipe.dEvents);
+            hostio::poolFree(pipe.dPhotons[0]);
+            hostio::poolFree(pipe.dPhotons[1]);
+            hostio::poolFree(pipe.dEvents);
             pipe.dPhotons[0] = pipe.dPhotons[1] = nullptr;
             pipe.dEvents = nullptr;
         }
@@ -1137,9 +1094,9 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     for (int i = 0; i < nPipes; ++i) {
         auto& pipe = c->pipes[i];
         if (!pipe.dEvents) {
-            CU_CHECK(c, cudaMalloc(&pipe.dPhotons[0], c->photonRegion * kShards * sizeof(PhotonRecord)));
-            CU_CHECK(c, cudaMalloc(&pipe.dPhotons[1], c->photonRegion * kShards * sizeof(PhotonRecord)));
-            CU_CHECK(c, cudaMalloc(&pipe.dEvents, c->eventRegion * kShards * sizeof(EventRecord)));
+            CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dPhotons[0], c->photonRegion * kShards * sizeof(PhotonRecord)));
+            CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dPhotons[1], c->photonRegion * kShards * sizeof(PhotonRecord)));
+            CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dEvents, c->eventRegion * kShards * sizeof(EventRecord)));
         }
     }
 
@@ -1360,7 +1317,7 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     if (const char* env = std::getenv("DXMCB200_PALETTE"))
         c->allowPalette = env[0] != '0';
     if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill batch>[,<log2 wave records>]
-        int r = 4, lg = 25;
+        int r = 8, lg = 25;
         std::sscanf(env, "%d,%d", &r, &lg);
         c->refillBatch = static_cast<uint32_t>(std::clamp(r, 1, 32));
         c->waveRecords = 1u << std::clamp(lg, 10, 28);
@@ -1373,22 +1330,40 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
 {
     if (!c)
         return;
+    const char* traceEnv = std::getenv("DXMCB200_TRACE");
+    const bool trace = traceEnv && traceEnv[0] == '1';
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dxmcb200]     destroy: %-18s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    };
     cudaSetDevice(c->device);
-    cudaFree(c->dVoxels);
-    cudaFree(c->dPalette);
+    // nothing may still be running on the blocks that go back to the pool
+    if (c->stream)
+        cudaStreamSynchronize(c->stream);
+    if (c->pipes[1].stream)
+        cudaStreamSynchronize(c->pipes[1].stream);
+    lap("stream sync");
+    hostio::poolFree(c->dVoxels);
+    hostio::poolFree(c->dPalette);
     cudaFree(c->dPaletteTable);
-    cudaFree(c->dAcc);
+    hostio::poolFree(c->dAcc);
     cudaFree(c->dLutBlob);
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
+    lap("world, tables");
     for (int i = 0; i < 2; ++i) {
         auto& pipe = c->pipes[i];
         cudaFree(pipe.dCursors);
         cudaFreeHost(pipe.hCursors);
-        cudaFree(pipe.dPhotons[0]);
-        cudaFree(pipe.dPhotons[1]);
-        cudaFree(pipe.dEvents);
+        lap("cursors");
+        hostio::poolFree(pipe.dPhotons[0]);
+        hostio::poolFree(pipe.dPhotons[1]);
+        hostio::poolFree(pipe.dEvents);
         if (pipe.done)
             cudaEventDestroy(pipe.done);
         for (auto& m : pipe.mark)
@@ -1396,6 +1371,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
                 cudaEventDestroy(m);
         if (i > 0 && pipe.stream)
             cudaStreamDestroy(pipe.stream); // pipes[0] runs on the ctx stream
+        lap("wave buffers");
     }
     cudaFree(c->dCounters);
     if (c->evStart)
@@ -1405,9 +1381,41 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     if (c->stream)
         cudaStreamDestroy(c->stream);
     delete c;
+    lap("events, streams");
 }
 
 const char* dxmcb200_last_error(dxmcb200_ctx* c) { return c ? c->error.c_str() : "null context"; }
+
+int dxmcb200_trim_pool(int device)
+{
+    hostio::Pool::instance().trim(device);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_material_max_density(dxmcb200_ctx* c, uint32_t nMaterials, float* out)
+{
+    if (!c || !out || nMaterials == 0 || nMaterials > 256 || (!c->dVoxels && !c->dPalette))
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    unsigned* dMax = nullptr;
+    CU_CHECK(c, cudaMalloc(&dMax, 256 * sizeof(unsigned)));
+    CU_CHECK(c, cudaMemsetAsync(dMax, 0, 256 * sizeof(unsigned), c->stream));
+    if (c->dPalette) // every distinct {density, material} record of the grid is in the 256-entry table already
+        maxDensityKernel<<<1, 256, 0, c->stream>>>(c->dPaletteTable, 256, dMax);
+    else
+        maxDensityKernel<<<gridFor(c, c->nVoxels), 256, 0, c->stream>>>(c->dVoxels, c->nVoxels, dMax);
+    unsigned bits[256];
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(bits, dMax, sizeof(bits), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(dMax);
+    CU_CHECK(c, e);
+    for (uint32_t m = 0; m < nMaterials; ++m)
+        std::memcpy(out + m, bits + m, sizeof(float));
+    return DXMCB200_OK;
+}
 
 int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
 {
@@ -1420,30 +1428,46 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     }
     CU_CHECK(c, cudaSetDevice(c->device));
     if (n != c->nVoxels) {
-        cudaFree(c->dAcc);
+        hostio::poolFree(c->dAcc);
         c->dAcc = nullptr;
         c->nVoxels = 0;
-        CU_CHECK(c, cudaMalloc(&c->dAcc, n * 4 * sizeof(unsigned long long)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &c->dAcc, n * 4 * sizeof(unsigned long long)));
         c->nVoxels = n;
     }
-    cudaFree(c->dVoxels);
-    cudaFree(c->dPalette);
+    hostio::poolFree(c->dVoxels);
+    hostio::poolFree(c->dPalette);
     cudaFree(c->dPaletteTable);
     c->dVoxels = nullptr;
     c->dPalette = nullptr;
     c->dPaletteTable = nullptr;
-    float* dDensity = nullptr;
-    uint8_t* dMat = nullptr;
-    uint8_t* dMeas = nullptr;
-    CU_CHECK(c, cudaMalloc(&dDensity, n * sizeof(float)));
-    CU_CHECK(c, cudaMalloc(&dMat, n));
+    // the reference's three arrays (world.hpp:48-50), staged on the device only until they are packed
+    struct Staged {
+        float* density = nullptr;
+        uint8_t* material = nullptr;
+        uint8_t* measurement = nullptr;
+        ~Staged()
+        {
+            hostio::poolFree(density);
+            hostio::poolFree(material);
+            hostio::poolFree(measurement);
+        }
+    } staged;
+    CU_CHECK(c, hostio::poolAlloc(c->device, &staged.density, n * sizeof(float)));
+    CU_CHECK(c, hostio::poolAlloc(c->device, &staged.material, n));
     if (w->measurement)
-        CU_CHECK(c, cudaMalloc(&dMeas, n));
-    CU_CHECK(c, cudaMemcpyAsync(dDensity, w->density, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-    CU_CHECK(c, cudaMemcpyAsync(dMat, w->material, n, cudaMemcpyHostToDevice, c->stream));
-    if (w->measurement)
-        CU_CHECK(c, cudaMemcpyAsync(dMeas, w->measurement, n, cudaMemcpyHostToDevice, c->stream));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &staged.measurement, n));
+    float* const dDensity = staged.density;
+    uint8_t* const dMat = staged.material;
+    uint8_t* const dMeas = staged.measurement;
     CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, n * 4 * sizeof(unsigned long long), c->stream));
+    { // caller arrays are pageable: chunked copies through pinned staging on several host threads
+        std::vector<hostio::Segment> up;
+        up.push_back({ reinterpret_cast<char*>(const_cast<float*>(w->density)), reinterpret_cast<char*>(dDensity), n * sizeof(float) });
+        up.push_back({ reinterpret_cast<char*>(const_cast<uint8_t*>(w->material)), reinterpret_cast<char*>(dMat), n });
+        if (w->measurement)
+            up.push_back({ reinterpret_cast<char*>(const_cast<uint8_t*>(w->measurement)), reinterpret_cast<char*>(dMeas), n });
+        CU_CHECK(c, hostio::copyChunked(c->device, up, true));
+    }
 
     // palette form when the grid holds at most 256 distinct records, 8-byte records otherwise
     bool palette = false;
@@ -1461,7 +1485,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         CU_CHECK(c, cudaMemcpyAsync(&distinct, dDistinct, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CU_CHECK(c, cudaStreamSynchronize(c->stream));
         if (distinct <= 256u) {
-            CU_CHECK(c, cudaMalloc(&c->dPalette, n));
+            CU_CHECK(c, hostio::poolAlloc(c->device, &c->dPalette, n));
             CU_CHECK(c, cudaMalloc(&c->dPaletteTable, 256 * sizeof(uint2)));
             CU_CHECK(c, cudaMemsetAsync(c->dPaletteTable, 0, 256 * sizeof(uint2), c->stream));
             paletteNumberKernel<<<1, 256, 0, c->stream>>>(dTable, dSlotIndex, c->dPaletteTable);
@@ -1474,14 +1498,11 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         cudaFree(dSlotIndex);
     }
     if (!palette) {
-        CU_CHECK(c, cudaMalloc(&c->dVoxels, n * sizeof(uint2)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &c->dVoxels, n * sizeof(uint2)));
         packVoxelsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, c->dVoxels, n);
         CU_CHECK(c, cudaGetLastError());
     }
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dDensity);
-    cudaFree(dMat);
-    cudaFree(dMeas);
     for (int i = 0; i < 3; ++i) {
         c->world.dim[i] = static_cast<uint32_t>(w->dim[i]);
         c->world.spacing[i] = w->spacing[i];
@@ -1774,29 +1795,36 @@ int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, floa
         return DXMCB200_ERR_STATE;
     CU_CHECK(c, cudaSetDevice(c->device));
     const uint64_t n = c->nVoxels;
-    float* dDose = nullptr;
-    float* dVar = nullptr;
-    uint32_t* dEv = nullptr;
+    struct Decoded { // device copies of the Result arrays, back to the pool on every exit path
+        float* dose = nullptr;
+        float* variance = nullptr;
+        uint32_t* events = nullptr;
+        ~Decoded()
+        {
+            hostio::poolFree(dose);
+            hostio::poolFree(variance);
+            hostio::poolFree(events);
+        }
+    } d;
     if (dose)
-        CU_CHECK(c, cudaMalloc(&dDose, n * sizeof(float)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.dose, n * sizeof(float)));
     if (variance)
-        CU_CHECK(c, cudaMalloc(&dVar, n * sizeof(float)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.variance, n * sizeof(float)));
     if (nEvents)
-        CU_CHECK(c, cudaMalloc(&dEv, n * sizeof(uint32_t)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.events, n * sizeof(uint32_t)));
     const float voxelVolume = c->world.spacing[0] * c->world.spacing[1] * c->world.spacing[2] / 1000.0f;
     resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, n, mode, std::ldexp(1.0f, -c->energyBits),
-        std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, dDose, dEv, dVar);
+        std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, d.dose, d.events, d.variance);
     CU_CHECK(c, cudaGetLastError());
-    if (dose)
-        CU_CHECK(c, cudaMemcpyAsync(dose, dDose, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (variance)
-        CU_CHECK(c, cudaMemcpyAsync(variance, dVar, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    if (nEvents)
-        CU_CHECK(c, cudaMemcpyAsync(nEvents, dEv, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dDose);
-    cudaFree(dVar);
-    cudaFree(dEv);
+    std::vector<hostio::Segment> down; // caller arrays are pageable: chunked copies through pinned staging
+    if (dose)
+        down.push_back({ reinterpret_cast<char*>(dose), reinterpret_cast<char*>(d.dose), n * sizeof(float) });
+    if (variance)
+        down.push_back({ reinterpret_cast<char*>(variance), reinterpret_cast<char*>(d.variance), n * sizeof(float) });
+    if (nEvents)
+        down.push_back({ reinterpret_cast<char*>(nEvents), reinterpret_cast<char*>(d.events), n * sizeof(uint32_t) });
+    CU_CHECK(c, hostio::copyChunked(c->device, down, false));
     return DXMCB200_OK;
 }
 
@@ -1806,27 +1834,34 @@ int dxmcb200_get_raw(dxmcb200_ctx* c, int64_t* energy, uint64_t* energySq, uint6
         return DXMCB200_ERR_STATE;
     CU_CHECK(c, cudaSetDevice(c->device));
     const uint64_t n = c->nVoxels;
-    long long* dE = nullptr;
-    unsigned long long* dE2 = nullptr;
-    unsigned long long* dN = nullptr;
+    struct Raw {
+        long long* energy = nullptr;
+        unsigned long long* energySq = nullptr;
+        unsigned long long* events = nullptr;
+        ~Raw()
+        {
+            hostio::poolFree(energy);
+            hostio::poolFree(energySq);
+            hostio::poolFree(events);
+        }
+    } d;
     if (energy)
-        CU_CHECK(c, cudaMalloc(&dE, n * 8));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.energy, n * 8));
     if (energySq)
-        CU_CHECK(c, cudaMalloc(&dE2, n * 8));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.energySq, n * 8));
     if (events)
-        CU_CHECK(c, cudaMalloc(&dN, n * 8));
-    rawKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, n, dE, dE2, dN);
+        CU_CHECK(c, hostio::poolAlloc(c->device, &d.events, n * 8));
+    rawKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, n, d.energy, d.energySq, d.events);
     CU_CHECK(c, cudaGetLastError());
-    if (energy)
-        CU_CHECK(c, cudaMemcpyAsync(energy, dE, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (energySq)
-        CU_CHECK(c, cudaMemcpyAsync(energySq, dE2, n * 8, cudaMemcpyDeviceToHost, c->stream));
-    if (events)
-        CU_CHECK(c, cudaMemcpyAsync(events, dN, n * 8, cudaMemcpyDeviceToHost, c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(dE);
-    cudaFree(dE2);
-    cudaFree(dN);
+    std::vector<hostio::Segment> down;
+    if (energy)
+        down.push_back({ reinterpret_cast<char*>(energy), reinterpret_cast<char*>(d.energy), n * 8 });
+    if (energySq)
+        down.push_back({ reinterpret_cast<char*>(energySq), reinterpret_cast<char*>(d.energySq), n * 8 });
+    if (events)
+        down.push_back({ reinterpret_cast<char*>(events), reinterpret_cast<char*>(d.events), n * 8 });
+    CU_CHECK(c, hostio::copyChunked(c->device, down, false));
     return DXMCB200_OK;
 }
 

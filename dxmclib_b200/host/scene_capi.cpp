@@ -355,10 +355,17 @@ int dxs_lut_sample_form_factor(dxs_scene* s, int material, float qmaxSq, uint64_
 
 int dxs_lut_table(dxs_scene* s, int what, float* out, uint64_t* count)
 {
-    if (!s || !s->lutValid)
+    if (!s)
         return DXS_ERR_STATE;
+    // what >= 16: the tables of the prepared Transport (dxs_b200_prepare), which builds its majorant from the device's
+    // per-material density maxima; below 16: the scene's own AttenuationLut (dxs_lut_generate, host scan)
+    const bool fromTransport = what >= 16;
+    if (fromTransport ? !s->prepared : !s->lutValid)
+        return DXS_ERR_STATE;
+    const AttenuationLut<float>& lut = fromTransport ? s->prepared->attenuationLut() : s->lut;
+    what &= 15;
     std::vector<float> v;
-    const auto& ip = s->lut.attenuationData();
+    const auto& ip = lut.attenuationData();
     switch (what) {
     case 0:
         v = ip.knots();
@@ -373,7 +380,7 @@ int dxs_lut_table(dxs_scene* s, int what, float* out, uint64_t* count)
         v = { static_cast<float>(ip.linearIndex()), ip.linearStep(), ip.linearEnergy(), static_cast<float>(ip.resolution()) };
         break;
     case 4:
-        for (const auto& r : s->lut.formFactorSamplers()) {
+        for (const auto& r : lut.formFactorSamplers()) {
             v.insert(v.end(), r.x().begin(), r.x().end());
             v.insert(v.end(), r.e().begin(), r.e().end());
             v.insert(v.end(), r.a().begin(), r.a().end());
@@ -381,7 +388,7 @@ int dxs_lut_table(dxs_scene* s, int what, float* out, uint64_t* count)
         }
         break;
     case 5:
-        for (const auto& c : s->lut.scatterFunctions()) {
+        for (const auto& c : lut.scatterFunctions()) {
             v.insert(v.end(), c.coefficients().begin(), c.coefficients().end());
             v.insert(v.end(), c.knots().begin(), c.knots().end());
             v.push_back(c.step());

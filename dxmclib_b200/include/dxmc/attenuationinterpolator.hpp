@@ -37,6 +37,23 @@ public:
         generate(world.materialMap(), world.densityArray()->cbegin(), world.densityArray()->cend(), world.materialIndexArray()->cbegin(), maxEnergy,
             minEnergy);
     }
+    // tables for a world whose per-material maximum density is already known (computed on the device from the uploaded
+    // grid, dxmcb200_material_max_density): same energy range and same tables as the constructor above, without
+    // the pass over all voxels. maxDensity[i] belongs to material i; 0 for a material no voxel uses.
+    AttenuationLutInterpolator(const World<T>& world, const std::vector<T>& maxDensity, T maxEnergy, T minEnergy)
+    {
+        minEnergy = std::max(T { 0.1 }, minEnergy);
+        maxEnergy = std::max(maxEnergy, T { 50 });
+        const auto& materials = world.materialMap();
+        std::vector<T> dens(materials.size(), T { 0 });
+        std::vector<std::uint8_t> idx(materials.size());
+        for (std::size_t i = 0; i < materials.size(); ++i) {
+            if (i < maxDensity.size())
+                dens[i] = maxDensity[i];
+            idx[i] = static_cast<std::uint8_t>(i);
+        }
+        generate(materials, dens.cbegin(), dens.cend(), idx.cbegin(), maxEnergy, minEnergy);
+    }
     // tables for a bare material list at standard densities (note: caps the range at 50 keV)
     AttenuationLutInterpolator(const std::vector<Material>& materials, T maxEnergy, T minEnergy)
     {

@@ -9,6 +9,7 @@
 #include "dxmc/attenuationinterpolator.hpp"
 #include "dxmc/constants.hpp"
 #include "dxmc/dxmcrandom.hpp"
+#include "dxmc/hostparallel.hpp"
 #include "dxmc/interpolation.hpp"
 #include "dxmc/material.hpp"
 #include "dxmc/world.hpp"
@@ -20,31 +21,6 @@
 #include <vector>
 
 namespace dxmc {
-
-namespace detail {
-    // fn(i) for i in [0, n) on up to hardware_concurrency host threads; every i is independent
-    template <typename F>
-    inline void parallelFor(std::size_t n, F fn)
-    {
-        const std::size_t workers = std::min<std::size_t>(n, std::max(1u, std::thread::hardware_concurrency()));
-        if (workers <= 1) {
-            for (std::size_t i = 0; i < n; ++i)
-                fn(i);
-            return;
-        }
-        std::atomic<std::size_t> next { 0 };
-        auto work = [&]() {
-            for (std::size_t i = next.fetch_add(1); i < n; i = next.fetch_add(1))
-                fn(i);
-        };
-        std::vector<std::thread> pool;
-        for (std::size_t t = 1; t < workers; ++t)
-            pool.emplace_back(work);
-        work();
-        for (auto& t : pool)
-            t.join();
-    }
-}
 
 template <Floating T = double>
 class AttenuationLut {
@@ -63,6 +39,18 @@ public:
     {
         generate(world.materialMap(), maxEnergy, minEnergy, false);
         m_attenuationData = AttenuationLutInterpolator<T>(world, m_maxEnergy, m_minEnergy);
+    }
+
+    // the same with the per-material maximum densities supplied by the caller (Transport gets them from the device)
+    void generate(const World<T>& world, const std::vector<T>& maxDensity, T maxEnergy = 150, T minEnergy = 1)
+    {
+        generate(world.materialMap(), maxEnergy, minEnergy, false);
+        generateAttenuation(world, maxDensity);
+    }
+    // second half of the above, for a caller that ran generate(materials, maxEnergy, minEnergy, false) itself
+    void generateAttenuation(const World<T>& world, const std::vector<T>& maxDensity)
+    {
+        m_attenuationData = AttenuationLutInterpolator<T>(world, maxDensity, m_maxEnergy, m_minEnergy);
     }
 
     // material i of the vector gets table index i

@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <exception>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -214,13 +215,6 @@ public:
         trace("  source update/validate");
         m_histories = source->historiesPerExposure() * source->totalExposures();
         m_totalExposures = source->totalExposures();
-        m_attenuationLut.generate(world, source->maxPhotonEnergyProduced());
-        trace("  AttenuationLut::generate");
-
-        m_flat = detail::FlatTables {};
-        flattenLuts(m_flat);
-        flattenExposures(world, *source, m_totalExposures, m_flat);
-        trace("  flatten tables/exposures");
 
         dxmcb200_ctx* raw = nullptr;
         const int created = dxmcb200_create(m_device, &raw);
@@ -229,8 +223,40 @@ public:
                 + "); this library has no CPU fallback");
         m_ctx.reset(raw);
         trace("  create context");
-        uploadWorld(m_ctx.get(), world);
-        trace("  upload world");
+        // The voxel grid goes to the device first, on a helper thread, while this thread builds the per-material
+        // tables (form-factor samplers, scatter functions, shells: independent of the grid). The one thing the
+        // Woodcock majorant needs from the grid, the per-material maximum density, then comes back from the device
+        // instead of a host pass over all voxels (reference attenuationinterpolator.hpp:48-59).
+        std::vector<T> maxDensity;
+        std::exception_ptr uploadError;
+        std::thread upload([&]() {
+            try {
+                uploadWorld(m_ctx.get(), world);
+                std::vector<float> md(std::min<std::size_t>(world.materialMap().size(), 256), 0.0f);
+                detail::check(m_ctx.get(), dxmcb200_material_max_density(m_ctx.get(), static_cast<std::uint32_t>(md.size()), md.data()),
+                    "material_max_density");
+                maxDensity.assign(md.begin(), md.end());
+            } catch (...) {
+                uploadError = std::current_exception();
+            }
+        });
+        try {
+            m_attenuationLut.generate(world.materialMap(), source->maxPhotonEnergyProduced(), T { 1 }, false);
+        } catch (...) {
+            upload.join();
+            throw;
+        }
+        upload.join();
+        if (uploadError)
+            std::rethrow_exception(uploadError);
+        trace("  upload world || material tables");
+        m_attenuationLut.generateAttenuation(world, maxDensity);
+        trace("  attenuation fits + majorant");
+
+        m_flat = detail::FlatTables {};
+        flattenLuts(m_flat);
+        flattenExposures(world, *source, m_totalExposures, m_flat);
+        trace("  flatten tables/exposures");
         detail::check(m_ctx.get(), dxmcb200_set_luts(m_ctx.get(), &m_flat.luts), "set_luts");
         uploadBeamTables(m_ctx.get(), m_flat);
         int energyBits = 20, energySqBits = 10;

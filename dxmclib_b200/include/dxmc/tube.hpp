@@ -7,6 +7,7 @@
 #include "dxmc/betheHeitlerCrossSection.hpp"
 #include "dxmc/constants.hpp"
 #include "dxmc/floating.hpp"
+#include "dxmc/hostparallel.hpp"
 #include "dxmc/material.hpp"
 
 #include <algorithm>
@@ -106,8 +107,9 @@ public:
     std::vector<T> getSpecter(const std::vector<T>& energies, const T anodeAngle, bool normalize = true) const
     {
         std::vector<T> specter(energies.size());
-        std::transform(std::execution::par_unseq, energies.begin(), energies.end(), specter.begin(),
-            [&](auto hv) -> T { return BetheHeitlerCrossSection::betheHeitlerSpectra(m_voltage, hv, anodeAngle); });
+        // one Bethe-Heitler depth integral per energy bin, independent of each other (reference tube.hpp:191-208)
+        detail::parallelFor(energies.size(),
+            [&](std::size_t i) { specter[i] = BetheHeitlerCrossSection::betheHeitlerSpectra(m_voltage, energies[i], anodeAngle); });
         addCharacteristicLines(energies, specter);
         applyFiltration(energies, specter);
         if (normalize) {

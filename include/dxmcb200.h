@@ -115,6 +115,13 @@ void dxmcb200_destroy(dxmcb200_ctx*);
 const char* dxmcb200_last_error(dxmcb200_ctx*);
 
 int dxmcb200_set_world(dxmcb200_ctx*, const dxmcb200_world*);
+/* Per-material maximum density of the uploaded grid, out[m] for m < n_materials (<= 256): the one whole-grid
+ * quantity the Woodcock majorant needs (replaces the per-material transform_reduce over all voxels of
+ * attenuationinterpolator.hpp:48-59 with one device pass, or a look at the 256-entry table of a palette grid). */
+int dxmcb200_material_max_density(dxmcb200_ctx*, uint32_t n_materials, float* out);
+/* Large device blocks (accumulators, wave buffers, staging arrays) are parked in a per-process pool when a context
+ * is destroyed and reused by the next one; this returns the parked blocks of `device` (< 0: all) to the driver. */
+int dxmcb200_trim_pool(int device);
 int dxmcb200_set_luts(dxmcb200_ctx*, const dxmcb200_luts*);
 int dxmcb200_set_beam_tables(dxmcb200_ctx*, uint32_t n_spectra, const dxmcb200_spectrum* spectra, uint32_t n_heel,
     const dxmcb200_heel* heel, uint32_t n_bowtie, const dxmcb200_bowtie* bowtie);

@@ -96,7 +96,8 @@ int dxs_lut_sample_form_factor(dxs_scene*, int material, float qmax_squared, uin
 /* raw tables for bit-exact comparison. sizes are returned when the pointer is NULL.
  * what: 0 knots m_x, 1 coefficients, 2 majorant coefficients,
  *       3 {linearIndex, linearStep, linearEnergy, resolution} as 4 floats,
- *       4 RITA x|e|a|b (4*56 per material), 5 spline coeffs+x+step/start/stop (60+16+3 per material) */
+ *       4 RITA x|e|a|b (4*56 per material), 5 spline coeffs+x+step/start/stop (60+16+3 per material)
+ *       16 + k (product library only): table k of the Transport prepared by dxs_b200_prepare */
 int dxs_lut_table(dxs_scene*, int what, float* out, uint64_t* count);
 
 /* ---- Sources (reference source.hpp) ---------------------------------------------------- */

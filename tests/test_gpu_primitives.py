@@ -148,3 +148,39 @@ def test_interaction_sampling(gpu, product, kind, model, energy):
         assert close.mean() > 0.995, f"only {close.mean():.4f} of histories agree"
         np.testing.assert_allclose(a[:, 0].mean(), b[:, 0].mean(), rtol=2e-3, atol=1e-3)  # mean energy imparted
         np.testing.assert_allclose(a[:, 4].mean(), b[:, 4].mean(), atol=5e-3)  # mean cos(theta)
+
+
+@pytest.mark.parametrize("palette", [True, False])
+def test_material_max_density_device_pass(gpu, product, palette, monkeypatch):
+    """the per-material maximum density behind the Woodcock majorant (reference
+    attenuationinterpolator.hpp:48-59) computed on the device, for both voxel-grid layouts. Bit-exact (a maximum)."""
+    rng = np.random.default_rng(5)
+    dim = (96, 64, 48)
+    n = int(np.prod(dim))
+    material = rng.integers(0, 7, n, dtype=np.uint8)
+    material[material == 5] = 4  # material 5 is used by no voxel
+    if palette:  # few distinct records: the grid is stored as palette indices
+        density = np.array([0.0012, 1.0, 1.06, 1.9, 0.3, 0.0, 0.95], np.float32)[material] * np.where(rng.random(n) < 0.5, 1.0, 0.5).astype(np.float32)
+    else:  # continuous densities: 8-byte voxel records
+        density = rng.random(n, dtype=np.float32) * np.float32(2.0)
+    monkeypatch.setenv("DXMCB200_PALETTE", "1" if palette else "0")
+    ctx = cabi.Context(0)
+    half = [d * 0.5 for d in dim]
+    ctx.set_world(dim, (1.0, 1.0, 1.0), (-half[0], half[0], -half[1], half[1], -half[2], half[2]), density, material)
+    got = ctx.material_max_density(7)
+    want = np.array([density[material == m].max() if (material == m).any() else 0.0 for m in range(7)], np.float32)
+    assert T.bit_equal(got, want)
+    assert got[5] == 0.0
+
+
+def test_transport_lut_from_device_maxima_equals_host_scan(gpu, product):
+    """Transport::prepare builds the majorant from the device maxima (dxmcb200_material_max_density); every table it
+    uploads must have the bits the host-side scan over all voxels gives (dxs_lut_generate = AttenuationLut::generate(world))."""
+    sc = T.ct_scene(product, histories=200)
+    sc.lut_generate(sc.max_energy())
+    host = [sc.lut_table(k).copy() for k in range(6)]
+    sc.b200_prepare(device=0, model=S.MODEL_LIVERMORE, seed=3)
+    for k in range(6):
+        assert T.bit_equal(sc.lut_table(16 + k), host[k]), f"table {k}"
+    assert host[2].size > 0
+    sc.b200_release()

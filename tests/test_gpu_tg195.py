@@ -1,4 +1,4 @@
-"""AAPM TG-195 Case 2 (radiography of a soft-tissue slab with nine volumes of interest) as the reference's validation
+"""AAPM TG-195 Case 2 and Case 4.1 (the second further down). Case 2 (radiography of a soft-tissue slab with nine volumes of interest) as the reference's validation
 program sets it up (validation/validation.cpp:318-393 world, :425-471 source, :496-512 published values): 80x200x360
 voxels of 5 mm, 390x390x200 mm soft tissue at z = 1550 mm, isotropic point source at the origin collimated to the slab,
 56.4 keV, 0 degrees, forced interactions in the VOIs.
@@ -101,3 +101,82 @@ def test_tg195_case2_against_reference_and_published(gpu, product, reference):
           + ", ".join(f"{g:.2f}/{p:.2f}" for g, p in zip(voi_ev, TG195_VOI)) + f"; worst z vs reference {z.max():.2f}")
     assert abs(total_ev - TG195_TOTAL) / TG195_TOTAL < 0.10
     assert np.all(np.abs(voi_ev - np.array(TG195_VOI)) / np.array(TG195_VOI) < 0.15)
+
+
+# ---- Case 4.1: computed tomography, PMMA cylinder, one projection ---------------------------------------------------
+# validation/validation.cpp:877-927 (world), :930-1052 (source, scoring, published values): 400x400x600 voxels of
+# 3x3x5 mm, PMMA cylinder of 160 mm radius along z in air, four 10 mm thick scoring slabs (material indices 2..5) at
+# z = 0, -10, -20, -30 mm; isotropic point source at x = -600 mm with a fan of +-atan(160/600) and a 10 mm or 80 mm
+# beam width at the isocentre; 56.4 keV.
+TG195_CASE41 = {False: [11592.27, 2576.72, 1766.85, 1330.53], True: [3380.39, 3332.64, 3176.44, 2559.58]}  # :1024-1027
+PMMA = "H53.2813989847746C33.3715774096566O13.3470236055689"
+
+
+def case41_arrays():
+    dim, sp = (400, 400, 600), (3.0, 3.0, 5.0)
+    # circleIndices (:556-574) tests the voxel's lower corner, not its centre: x = xi * dx - nx * dx / 2
+    x = np.arange(dim[0]) * sp[0] - dim[0] * sp[0] / 2
+    y = np.arange(dim[1]) * sp[1] - dim[1] * sp[1] / 2
+    disc = (x[None, :] ** 2 + y[:, None] ** 2) <= 160.0 ** 2
+    zc = np.arange(dim[2]) * sp[2] - dim[2] * sp[2] / 2 + sp[2] / 2  # zpos + spacing/2 of :893-903
+    index = np.ones(dim[2], np.uint8)
+    for k, (lo, hi) in enumerate(((-5, 5), (-15, -5), (-25, -15), (-35, -25))):
+        index[(zc >= lo) & (zc < hi)] = 2 + k
+    mat = np.where(disc[None, :, :], index[:, None, None], np.uint8(0)).astype(np.uint8)
+    dens = np.where(mat > 0, np.float32(1.19), np.float32(0.001205)).astype(np.float32)
+    return dim, sp, mat, dens
+
+
+def case41_scene(lib, arrays, histories, exposures, wide):
+    dim, sp, mat, dens = arrays
+    sc = S.Scene(lib)
+    sc.world(dim, sp)
+    sc.add_material(T.AIR, 0.001205)
+    for _ in range(5):
+        sc.add_material(PMMA, 1.19)
+    sc.arrays(dens, mat)
+    assert sc.validate()
+    fan, beam = math.atan(160.0 / 600.0), math.atan((40.0 if wide else 5.0) / 600.0)
+    sc.source_isotropic((-600.0, 0.0, 0.0), (0, 1, 0, 0, 0, 1), (-fan, fan, -beam, beam), np.array([1.0], np.float32),
+                        np.array([56.4], np.float32), histories, exposures)
+    return sc
+
+
+@pytest.mark.parametrize("wide", [False, True])
+def test_tg195_case41_against_reference_and_published(gpu, product, reference, wide):
+    arrays = case41_arrays()
+    mat = arrays[2].ravel()
+    voxel = float(np.prod(arrays[1]))
+    correction = 160.0 * 160.0 * math.pi * 10.0 / (voxel * np.count_nonzero(mat == 2))  # :996-999
+    masks = [mat == 2 + k for k in range(4)]
+
+    def voi_ev(result):
+        d = result.dose.astype(np.float64)
+        return np.array([correction * d[m].sum() for m in masks]), d[mat > 0].sum()
+
+    replicas, histories, exposures = 6, 1_000_000, 4
+    got, body = [], []
+    for r in range(replicas):
+        sc = case41_scene(product, arrays, histories, exposures, wide)
+        res = sc.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 31 * r)
+        assert res.histories == histories * exposures
+        v, b = voi_ev(res)
+        got.append(v)
+        body.append(b)
+        sc.close()
+    got = np.array(got)
+    mean_a, sigma_a = got.mean(axis=0), got.std(axis=0, ddof=1)
+    sb = case41_scene(reference, arrays, histories, exposures, wide)
+    rb = sb.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 5, workers=S.WORKERS_COUNTER_STREAMS)
+    mean_b, body_b = voi_ev(rb)
+    sb.close()
+    # (1) same inputs, two implementations: energy deposited in the whole cylinder within 0.5 %, every slab within
+    # 3.5 sigma of the combined uncertainty (one reference run + the mean of the product replicas; sigma from replicas)
+    assert abs(np.mean(body) - body_b) / body_b < 5e-3
+    z = np.abs(mean_a - mean_b) / (sigma_a * math.sqrt(1.0 + 1.0 / replicas))
+    assert np.all(z < 3.5), (mean_a, mean_b, sigma_a, z)
+    # (2) the published TG-195 values, informational bound (approximate cross-section data on both sides)
+    pub = np.array(TG195_CASE41[wide])
+    print(f"TG-195 case 4.1, 56.4 keV, {'80' if wide else '10'} mm: slabs product/published eV per history "
+          + ", ".join(f"{g:.1f}/{p:.1f}" for g, p in zip(mean_a, pub)) + f"; worst z vs reference {z.max():.2f}")
+    assert np.all(np.abs(mean_a - pub) / pub < 0.15)
