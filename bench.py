@@ -34,8 +34,8 @@ from dxmclib_b200 import phantoms, sharding  # noqa: E402
 from dxmclib_b200 import scene as S  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size transportKernel launch, from the committed
-# `ncu --set full` capture (profiles/r1_v4_*), bytes
-TRAFFIC_PER_LAUNCH = 7.119e9  # profiles/r1_v4_transportKernel_ncu_summary.csv: 5.182 GB read + 1.937 GB written, 2^25-record wave
+# `ncu --set full` capture (profiles/r1_v6_*), bytes
+TRAFFIC_PER_LAUNCH = 11.960e9  # profiles/r1_v6_transportKernel_ncu_summary.csv: 8.212 GB read + 3.748 GB written, 2^26-record wave
 
 DIM = (512, 512, 400)
 SPACING = (1.0, 1.0, 1.0)
@@ -155,7 +155,7 @@ def workload_config(n_ranks, hist):
                     f"{DIM[0]}x{DIM[1]}x{DIM[2]} @1 mm, 10 materials, {EXPOSURES * n_ranks} exposures x {hist} histories",
         "voxels": int(np.prod(DIM)), "exposures": EXPOSURES * n_ranks, "histories_per_exposure": hist,
         "histories_per_step": EXPOSURES * n_ranks * hist, "sharding": f"exposures interleaved over {n_ranks} GPU(s) (rank r: r, r+N, ...), one all-reduce of the fixed-point grids",
-        "l2_note": "accumulators 3.4 GB + photon/event record streams (>10 GB per wave pair) exceed the 126 MB L2; the palette voxel "
+        "l2_note": "accumulators 3.4 GB + photon/event record streams (>20 GB per wave pair) exceed the 126 MB L2; the palette voxel "
                    "grid is 105 MB; accumulators are cleared every step",
     }
 
@@ -290,7 +290,7 @@ def main():
     b_alg = 6.0 * L + 24.0 * Sev
     pipeline_s = kernel_total_ms / args.steps / 1e3
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": TRAFFIC_PER_LAUNCH,
-                "kernel": "transportKernel<false> (Woodcock stepping; one launch = one wave of <= 2^25 photon segments)",
+                "kernel": "transportKernel<false> (Woodcock stepping; one launch = one wave of <= 2^26 photon segments)",
                 "algorithmic_bytes_per_launch": 6.0 * lookups_per_launch, "launch_ms": t_launch_ms, "launches": t_n,
                 "kernel_share_of_step": {k: v[0] / max(kernel_total_ms, 1e-9) for k, v in per_kernel.items()},
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in per_kernel.items()},

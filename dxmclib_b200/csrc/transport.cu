@@ -898,6 +898,8 @@ __global__ void sampleInteractionKernel(LutView lut, int kind, uint8_t material,
 // ================================================================================================
 // runtime
 // ================================================================================================
+constexpr int kMaxPipes = 4;
+
 struct dxmcb200_ctx {
     int device = 0;
     int smCount = 0;
@@ -944,7 +946,7 @@ struct dxmcb200_ctx {
         int cur = 0;
         unsigned survivors = 0;
         bool pending = false;
-    } pipes[2];
+    } pipes[kMaxPipes];
     int nPipes = 2;
     double kernelMs[3] = { 0, 0, 0 }; // summed device time of generate / transport / interact launches since clear
     uint64_t kernelLaunches[3] = { 0, 0, 0 };
@@ -953,7 +955,8 @@ struct dxmcb200_ctx {
 
     int energyBits = 20, energySqBits = 10;
     bool collectStats = false;
-    uint32_t waveRecords = 1u << 25; // photons per wave (2 GiB per photon buffer, 2.5 GiB of event records)
+    uint32_t waveRecords = 1u << 26; // photons per wave: 6.4 GB per photon buffer, 8.1 GB of event records, x2 pipelines (measured at 1e10
+                                     // histories: 2^25: 2.38e9, 2^26: 2.44e9, 2^27: 2.45e9 histories/s; a third pipeline adds < 0.5 %)
     uint32_t refillBatch = 8; // empty lanes that make a warp stop stepping and re-fill (measured: 4: 2.17e9, 8: 2.20e9, 12: 2.18e9 histories/s)
 
     double lastRunMs = 0, totalMs = 0;
@@ -990,7 +993,7 @@ T* advancePtr(char*& cursor, size_t count)
 
 // persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
 // with two pipelines every kernel takes half of an SM's block slots so that kernels of both pipelines are co-resident
-int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy) { return std::max(1, c->nPipes > 1 ? occupancy / 2 : occupancy); }
+int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy) { return std::max(1, occupancy / std::max(1, c->nPipes)); }
 
 template <typename K>
 cudaError_t launchPersistent(const dxmcb200_ctx* c, cudaStream_t stream, K kernel, const KernelParams& P, uint64_t items)
@@ -1300,7 +1303,7 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
         return DXMCB200_ERR_CUDA;
     }
     c->pipes[0].stream = c->stream;
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxPipes; ++i) {
         auto& pipe = c->pipes[i];
         if ((i > 0 && cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking) != cudaSuccess)
             || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&pipe.mark[0]) != cudaSuccess
@@ -1311,13 +1314,13 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
         }
     }
     if (const char* env = std::getenv("DXMCB200_PIPES"))
-        c->nPipes = env[0] == '1' ? 1 : 2;
+        c->nPipes = std::clamp(std::atoi(env), 1, kMaxPipes);
     const char* stats = std::getenv("DXMCB200_STATS");
     c->collectStats = stats && stats[0] == '1';
     if (const char* env = std::getenv("DXMCB200_PALETTE"))
         c->allowPalette = env[0] != '0';
     if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill batch>[,<log2 wave records>]
-        int r = 8, lg = 25;
+        int r = 8, lg = 26;
         std::sscanf(env, "%d,%d", &r, &lg);
         c->refillBatch = static_cast<uint32_t>(std::clamp(r, 1, 32));
         c->waveRecords = 1u << std::clamp(lg, 10, 28);
@@ -1344,8 +1347,9 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     // nothing may still be running on the blocks that go back to the pool
     if (c->stream)
         cudaStreamSynchronize(c->stream);
-    if (c->pipes[1].stream)
-        cudaStreamSynchronize(c->pipes[1].stream);
+    for (int i = 1; i < kMaxPipes; ++i)
+        if (c->pipes[i].stream)
+            cudaStreamSynchronize(c->pipes[i].stream);
     lap("stream sync");
     hostio::poolFree(c->dVoxels);
     hostio::poolFree(c->dPalette);
@@ -1356,7 +1360,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
     lap("world, tables");
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kMaxPipes; ++i) {
         auto& pipe = c->pipes[i];
         cudaFree(pipe.dCursors);
         cudaFreeHost(pipe.hCursors);
