@@ -123,7 +123,7 @@ def run_reference(args, rank, emit):
     sample of the same workload: same world, same source, fewer histories per exposure."""
     if rank != 0:
         return
-    lib = S.reference_lib()
+    lib, how = S.reference_timing_lib()
     cores = os.cpu_count() or 1
     hist = max(1, args.ref_histories // EXPOSURES)
     t0 = time.time()
@@ -136,7 +136,7 @@ def run_reference(args, rank, emit):
             times.append(r.seconds)
     per_step = float(np.mean(times))
     value = hist * EXPOSURES / per_step
-    sample = f"{EXPOSURES} exposures x {hist} histories per step (stock Transport::operator(), Result::simulationTime)"
+    sample = f"{EXPOSURES} exposures x {hist} histories per step (stock Transport::operator(), Result::simulationTime; reference built with {how})"
     line = {
         "impl": "reference", "metric": "photon histories/s", "value": value, "unit": "histories/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": per_step * 1e3, "higher_is_better": True, "scaling": "weak",
@@ -339,12 +339,13 @@ def main():
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
-            ref = S.reference_lib()
+            ref, how = S.reference_timing_lib()
             h = max(1, args.cpu_baseline_histories // EXPOSURES)
             rs = build_scene(ref, h, phantom=phantom)
             r = rs.transport(model=MODEL, output=S.OUT_EV_PER_HISTORY, seed=0, workers=0, want_events=False, want_variance=False)
             cpu = {"value": r.histories / r.seconds, "unit": "histories/s", "cores": os.cpu_count(), "kind": "reference",
-                   "sample": f"{EXPOSURES} exposures x {h} histories, stock multithreaded Transport::operator(), Result::simulationTime",
+                   "sample": f"{EXPOSURES} exposures x {h} histories, stock multithreaded Transport::operator(), Result::simulationTime; "
+                             f"reference built with {how}",
                    "seconds": r.seconds}
             rs.close()
         except Exception as e:  # the checker is optional for the measurement, never for the product

@@ -88,6 +88,7 @@ struct WorldView {
     const uint2* voxels; // {density bits, material | measurement<<8}; null when the grid is in palette form
     const uint8_t* palette; // palette form: index per voxel into paletteTable (grids with <= 256 distinct records)
     const uint2* paletteTable; // [256] records as in `voxels`
+    uint32_t paletteNibbles; // 1: at most 16 distinct records, two 4-bit indices per byte (voxel i in byte i/2, low nibble first)
 };
 
 struct SpectrumView {
@@ -214,6 +215,14 @@ __device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, floa
         iz = truncDiv(__fsub_rn(z, w.ext[4]), w.spacing[2], w.invSpacing[2]);
     }
     return (iz * w.dim[1] + iy) * w.dim[0] + ix;
+}
+
+// palette index of a voxel; random look-ups have no reuse in L1: cache them in L2 only (ld.global.cg)
+__device__ __forceinline__ uint32_t paletteIndex(const WorldView& w, uint32_t voxel)
+{
+    if (w.paletteNibbles)
+        return (static_cast<uint32_t>(__ldcg(w.palette + (voxel >> 1))) >> ((voxel & 1u) * 4u)) & 15u;
+    return __ldcg(w.palette + voxel);
 }
 
 __device__ __forceinline__ void advance(Photon& p, float step)

@@ -440,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 uint2 rec;
                 // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
                 if (paletteForm) {
-                    const unsigned slot = paletteBase + 8u * __ldcg(P.world.palette + voxel);
+                    const unsigned slot = paletteBase + 8u * paletteIndex(P.world, voxel);
                     asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rec.x), "=r"(rec.y) : "r"(slot));
                 } else
                     rec = __ldcg(P.world.voxels + voxel);
@@ -725,17 +725,27 @@ __global__ void paletteNumberKernel(const unsigned long long* table, unsigned* s
     }
 }
 
-// pass 3: one byte per voxel
+// pass 3: one byte per voxel (or, with at most 16 distinct records, one byte per two voxels)
 __global__ void paletteIndexKernel(const float* __restrict__ density, const uint8_t* __restrict__ material,
     const uint8_t* __restrict__ measurement, uint64_t n, const unsigned long long* __restrict__ table, const unsigned* __restrict__ slotIndex,
-    uint8_t* __restrict__ out)
+    uint8_t* __restrict__ out, int nibbles)
 {
-    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    auto indexOf = [&](uint64_t i) {
         const unsigned long long key = voxelKey(density, material, measurement, i);
         unsigned h = paletteHash(key);
         while (table[h] != key)
             h = (h + 1) & (kPaletteSlots - 1);
-        out[i] = static_cast<uint8_t>(slotIndex[h]);
+        return slotIndex[h];
+    };
+    const uint64_t items = nibbles ? (n + 1) / 2 : n; // output bytes
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < items; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        if (nibbles) {
+            const unsigned lo = indexOf(2 * i);
+            const unsigned hi = 2 * i + 1 < n ? indexOf(2 * i + 1) : 0u;
+            out[i] = static_cast<uint8_t>(lo | (hi << 4));
+        } else {
+            out[i] = static_cast<uint8_t>(indexOf(i));
+        }
     }
 }
 
@@ -759,7 +769,7 @@ __global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, 
 
 // normalizeScoring / energyImpartedToDose (transport.hpp:780-816) fused with the fixed-point decode
 __global__ void resultKernel(const unsigned long long* __restrict__ acc, const uint2* __restrict__ voxels, const uint8_t* __restrict__ palette,
-    const uint2* __restrict__ paletteTable, uint64_t n, int mode,
+    const uint2* __restrict__ paletteTable, int paletteNibbles, uint64_t n, int mode,
     float energyLsb, float energySqLsb, uint64_t histories, float calibration, float voxelVolume, float* __restrict__ dose,
     uint32_t* __restrict__ nEvents, float* __restrict__ variance)
 {
@@ -775,7 +785,8 @@ __global__ void resultKernel(const unsigned long long* __restrict__ acc, const u
             d = e * hdInv;
             v = (e2 * hvInv - d * d) * hInv;
         } else if (mode == 1) {
-            const float de = __uint_as_float(palette ? paletteTable[palette[i]].x : voxels[i].x);
+            const unsigned slot = !palette ? 0u : paletteNibbles ? (palette[i >> 1] >> ((i & 1) * 4)) & 15u : palette[i];
+            const float de = __uint_as_float(palette ? paletteTable[slot].x : voxels[i].x);
             const float voxelMass = de * voxelVolume * 0.001f;
             const float factor = calibration / voxelMass;
             d = de > 0.0f ? e * factor : 0.0f;
@@ -914,6 +925,7 @@ struct dxmcb200_ctx {
     uint8_t* dPalette = nullptr; // palette form: one byte per voxel ...
     uint2* dPaletteTable = nullptr; // ... into this 256-entry record table
     bool allowPalette = true;
+    bool allowNibbles = true;
     unsigned long long* dAcc = nullptr;
 
     // luts
@@ -1317,8 +1329,10 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
         c->nPipes = std::clamp(std::atoi(env), 1, kMaxPipes);
     const char* stats = std::getenv("DXMCB200_STATS");
     c->collectStats = stats && stats[0] == '1';
-    if (const char* env = std::getenv("DXMCB200_PALETTE"))
+    if (const char* env = std::getenv("DXMCB200_PALETTE")) { // 0: 8-byte records, 8: byte indices only, else automatic
         c->allowPalette = env[0] != '0';
+        c->allowNibbles = env[0] != '8';
+    }
     if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill batch>[,<log2 wave records>]
         int r = 8, lg = 26;
         std::sscanf(env, "%d,%d", &r, &lg);
@@ -1473,8 +1487,10 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         CU_CHECK(c, hostio::copyChunked(c->device, up, true));
     }
 
-    // palette form when the grid holds at most 256 distinct records, 8-byte records otherwise
+    // palette form when the grid holds at most 256 distinct records (4-bit indices when at most 16: a 512x512x400 grid is
+    // then 52 MB and stays resident in one 63 MB L2 partition), 8-byte records otherwise
     bool palette = false;
+    c->world.paletteNibbles = 0;
     if (c->allowPalette) {
         unsigned long long* dTable = nullptr;
         unsigned* dSlotIndex = nullptr; // [kPaletteSlots] + the distinct-record counter
@@ -1489,14 +1505,16 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         CU_CHECK(c, cudaMemcpyAsync(&distinct, dDistinct, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
         CU_CHECK(c, cudaStreamSynchronize(c->stream));
         if (distinct <= 256u) {
-            CU_CHECK(c, hostio::poolAlloc(c->device, &c->dPalette, n));
+            const int nibbles = distinct <= 16u && c->allowNibbles ? 1 : 0;
+            CU_CHECK(c, hostio::poolAlloc(c->device, &c->dPalette, nibbles ? (n + 1) / 2 : n));
             CU_CHECK(c, cudaMalloc(&c->dPaletteTable, 256 * sizeof(uint2)));
             CU_CHECK(c, cudaMemsetAsync(c->dPaletteTable, 0, 256 * sizeof(uint2), c->stream));
             paletteNumberKernel<<<1, 256, 0, c->stream>>>(dTable, dSlotIndex, c->dPaletteTable);
-            paletteIndexKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, n, dTable, dSlotIndex, c->dPalette);
+            paletteIndexKernel<<<gridFor(c, n), 256, 0, c->stream>>>(dDensity, dMat, dMeas, n, dTable, dSlotIndex, c->dPalette, nibbles);
             CU_CHECK(c, cudaGetLastError());
             CU_CHECK(c, cudaStreamSynchronize(c->stream));
             palette = true;
+            c->world.paletteNibbles = static_cast<uint32_t>(nibbles);
         }
         cudaFree(dTable);
         cudaFree(dSlotIndex);
@@ -1534,7 +1552,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
         cudaStreamAttrValue attr {};
         if (env && env[0] == '1' && maxPersist > 0 && maxWindow > 0) {
-            const size_t gridBytes = palette ? n : n * sizeof(uint2);
+            const size_t gridBytes = palette ? (c->world.paletteNibbles ? (n + 1) / 2 : n) : n * sizeof(uint2);
             cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(maxPersist));
             attr.accessPolicyWindow.base_ptr = palette ? static_cast<void*>(c->dPalette) : static_cast<void*>(c->dVoxels);
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(gridBytes, static_cast<size_t>(maxWindow));
@@ -1817,7 +1835,8 @@ int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, floa
     if (nEvents)
         CU_CHECK(c, hostio::poolAlloc(c->device, &d.events, n * sizeof(uint32_t)));
     const float voxelVolume = c->world.spacing[0] * c->world.spacing[1] * c->world.spacing[2] / 1000.0f;
-    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, n, mode, std::ldexp(1.0f, -c->energyBits),
+    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, static_cast<int>(c->world.paletteNibbles), n, mode,
+        std::ldexp(1.0f, -c->energyBits),
         std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, d.dose, d.events, d.variance);
     CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaStreamSynchronize(c->stream));

@@ -774,26 +774,14 @@ int dxs_b200_collect(dxs_scene* s, int outputMode, int useCalibration, uint64_t 
     return guarded([&] {
         auto& tr = *s->prepared;
         tr.setOutputMode(outputMode == DXS_OUT_DOSE ? Transport<float>::OUTPUTMODE::DOSE : Transport<float>::OUTPUTMODE::EV_PER_HISTORY);
-        Result<float> res(s->world->size());
-        res.numberOfHistories = histories ? histories : tr.preparedHistories();
-        tr.collect(*s->world, s->source.get(), res, useCalibration != 0, nullptr);
-        const auto n = res.dose.size();
-        // the caller's arrays are usually untouched pages: copy (and fault them in) on several host threads
-        const void* src[3] = { res.dose.data(), res.nEvents.data(), res.variance.data() };
-        void* dst[3] = { dose, nEvents, variance };
-        const std::size_t pieces = n > (std::size_t { 1 } << 22) ? 4 : 1;
-        dxmc::detail::parallelFor(3 * pieces, [&](std::size_t job) {
-            const std::size_t a = job / pieces, piece = job % pieces;
-            if (!dst[a])
-                return;
-            const std::size_t begin = n * piece / pieces * 4, end = n * (piece + 1) / pieces * 4;
-            std::memcpy(static_cast<char*>(dst[a]) + begin, static_cast<const char*>(src[a]) + begin, end - begin);
-        });
+        // straight into the caller's arrays: the download's host threads fault the (usually untouched) pages in
+        const std::uint64_t n = histories ? histories : tr.preparedHistories();
+        const std::string_view units = tr.collectInto(*s->world, s->source.get(), n, dose, nEvents, variance, useCalibration != 0);
         if (info) {
-            info->histories = res.numberOfHistories;
+            info->histories = n;
             info->seconds = 0;
             std::memset(info->units, 0, sizeof(info->units));
-            std::strncpy(info->units, std::string(res.dose_units).c_str(), sizeof(info->units) - 1);
+            std::strncpy(info->units, std::string(units).c_str(), sizeof(info->units) - 1);
         }
         return DXS_OK;
     });

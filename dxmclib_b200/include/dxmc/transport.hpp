@@ -352,6 +352,35 @@ public:
         download(m_ctx.get(), mode, result, calibration);
     }
 
+    // collect() straight into caller-owned arrays (any may be null), without the intermediate Result: what a multi-GPU
+    // driver calls on the rank that keeps the summed grids. Returns the dose units.
+    template <typename U>
+        requires std::is_base_of_v<World<T>, U> && std::is_same_v<T, float>
+    std::string_view collectInto(const U& world, Source<T>* source, std::uint64_t histories, float* dose, std::uint32_t* nEvents, float* variance,
+        bool useSourceDoseCalibration = true)
+    {
+        if (!m_ctx)
+            throw std::runtime_error("dxmcb200: Transport::collectInto called before prepare");
+        (void)world;
+        int mode = 0;
+        float calibration = 1.0f;
+        std::string_view units = "eV/history";
+        if (m_outputmode == OUTPUTMODE::DOSE) {
+            mode = 1;
+            units = "keV/kg";
+            if (useSourceDoseCalibration) {
+                const int outer = detail::currentDevice();
+                detail::currentDevice() = m_device;
+                calibration = static_cast<float>(source->getCalibrationValue(m_lowenergyCorrection, nullptr));
+                detail::currentDevice() = outer;
+                units = "mGy";
+            }
+        }
+        detail::check(m_ctx.get(), dxmcb200_get_result(m_ctx.get(), mode, histories ? histories : m_histories, calibration, dose, nEvents, variance),
+            "get_result");
+        return units;
+    }
+
     // device context of a prepared Transport, for direct C-ABI calls (accumulator address, stats, raw grids)
     dxmcb200_ctx* context() const { return m_ctx.get(); }
     std::uint64_t preparedExposures() const { return m_totalExposures; }

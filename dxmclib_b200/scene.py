@@ -17,6 +17,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_HERE)
 PRODUCT_LIB = os.path.join(_HERE, "libdxmcb200.so")
 REFERENCE_LIB = os.path.join(ROOT, "oracle", "_ref", "libdxmc_ref.so")
+# the same reference sources built -O3 -march=x86-64-v3 (its own Release flags, portable level): timing baseline only
+REFERENCE_TIMING_LIB = os.path.join(ROOT, "oracle", "_ref", "libdxmc_ref_o3.so")
 
 MODEL_NONE, MODEL_LIVERMORE, MODEL_IA = 0, 1, 2
 OUT_EV_PER_HISTORY, OUT_DOSE = 0, 1
@@ -103,6 +105,26 @@ def product_lib() -> C.CDLL:
 
 def reference_lib() -> C.CDLL:
     return load(REFERENCE_LIB)
+
+
+def reference_timing_lib() -> tuple[C.CDLL, str]:
+    """The reference library bench.py times as the CPU baseline, and a word on how it was built: the -O3 AVX2 build when it
+    exists and this host can execute it (probed in a child process, an illegal instruction must not take the caller down),
+    otherwise the exact-arithmetic build the parity tests use."""
+    import subprocess
+    import sys
+
+    if os.path.exists(REFERENCE_TIMING_LIB):
+        probe = ("import ctypes as C, sys; l = C.CDLL(sys.argv[1]); l.dxs_create.restype = C.c_void_p; s = C.c_void_p(l.dxs_create()); "
+                 "assert l.dxs_world_add_material(s, b'Water, Liquid', C.c_double(1.0)) == 0; "
+                 "out = (C.c_double * 4)(); assert l.dxs_material_attenuation(s, 0, C.c_double(60.0), out) == 0 and out[3] > 0")
+        try:
+            ok = subprocess.run([sys.executable, "-c", probe, REFERENCE_TIMING_LIB], capture_output=True, timeout=120).returncode == 0
+        except Exception:
+            ok = False
+        if ok:
+            return load(REFERENCE_TIMING_LIB), "g++ -O3 -march=x86-64-v3"
+    return load(REFERENCE_LIB), "g++ -O2 -ffp-contract=off"
 
 
 class SceneError(RuntimeError):
@@ -437,9 +459,9 @@ class Scene:
     def b200_collect(self, output=OUT_EV_PER_HISTORY, use_calibration=False, histories=0, want_events=True,
                      want_variance=True) -> Result:
         n = int(np.prod(self.dim))
-        dose = np.zeros(n, np.float32)
-        ev = np.zeros(n, np.uint32) if want_events else None
-        var = np.zeros(n, np.float32) if want_variance else None
+        dose = np.empty(n, np.float32)  # every element is written by the download
+        ev = np.empty(n, np.uint32) if want_events else None
+        var = np.empty(n, np.float32) if want_variance else None
         info = ResultInfo()
         _chk(self.lib.dxs_b200_collect(self.h, output, int(use_calibration), C.c_uint64(histories), dose.ctypes.data_as(_f32p),
                                        None if ev is None else ev.ctypes.data_as(_u32p),

@@ -97,8 +97,8 @@ def test_bit_reproducible_and_shard_invariant(gpu, product):
 
 def test_schedule_and_layout_invariance(gpu, product, monkeypatch):
     """The grids do not depend on how the wavefront is scheduled or how the voxel grid is stored: wave size (down to
-    1024 photons, i.e. hundreds of waves and drains), re-fill batch, one or two wave pipelines, palette or 8-byte voxel
-    records all give bit-identical accumulators."""
+    1024 photons, i.e. hundreds of waves and drains), re-fill batch, one to three wave pipelines, 4-bit palette (the automatic
+    choice for this grid), byte palette ("8") or 8-byte voxel records ("0") all give bit-identical accumulators."""
     sc = T.isotropic_scene(product, histories=40000, exposures=6, forced=True)
     flat = T.flatten_scene(sc)
     exps = T.exposures_of(sc)
@@ -117,7 +117,7 @@ def test_schedule_and_layout_invariance(gpu, product, monkeypatch):
 
     base = run("4,25", "1", "2")
     assert base[2].sum() > 50000
-    for setting in [("1,10", "1", "2"), ("32,12", "1", "1"), ("8,14", "0", "2"), ("4,25", "0", "1")]:
+    for setting in [("1,10", "1", "2"), ("32,12", "1", "1"), ("8,14", "0", "2"), ("4,25", "0", "1"), ("8,13", "8", "3"), ("8,26", "8", "2")]:
         other = run(*setting)
         for x, y in zip(base, other):
             assert T.bit_equal(x, y), f"grids differ for DXMCB200_BATCH/PALETTE/PIPES = {setting}"
