@@ -943,9 +943,10 @@ struct dxmcb200_ctx {
     uint64_t* dPrefix = nullptr;
     uint64_t prefixCapacity = 0;
 
-    // Two independent wave pipelines on two streams: while one is in its (issue-bound) transport kernel the other runs
-    // its (latency-bound, divergent) interaction and generation kernels on the same SMs. Each owns two photon buffers
-    // (ping-pong), an event buffer and its cursors.
+    // Independent wave pipelines on their own streams (two by default; DXMCB200_PIPES=1..4 for experiments: three add
+    // < 0.5 %, four leave one block per SM and kernel and lose 18 %): while one is in its (issue-bound) transport kernel
+    // another runs its (latency-bound, divergent) interaction and generation kernels on the same SMs. Each owns two
+    // photon buffers (ping-pong), an event buffer and its cursors.
     struct Pipe {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
@@ -1004,7 +1005,7 @@ T* advancePtr(char*& cursor, size_t count)
 }
 
 // persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
-// with two pipelines every kernel takes half of an SM's block slots so that kernels of both pipelines are co-resident
+// with n pipelines every kernel takes 1/n of an SM's block slots so that kernels of all pipelines are co-resident
 int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy) { return std::max(1, occupancy / std::max(1, c->nPipes)); }
 
 template <typename K>
