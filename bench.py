@@ -337,7 +337,7 @@ def main():
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same workload
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # N=1 only: at N>1 the host cores are busy feeding the other ranks
         try:
             ref, how = S.reference_timing_lib()
             h = max(1, args.cpu_baseline_histories // EXPOSURES)

@@ -184,3 +184,28 @@ def test_transport_lut_from_device_maxima_equals_host_scan(gpu, product):
         assert T.bit_equal(sc.lut_table(16 + k), host[k]), f"table {k}"
     assert host[2].size > 0
     sc.b200_release()
+
+
+def test_device_pool_reuse_and_trim(gpu, product):
+    """Large device blocks are parked when a context is destroyed and reused by the next one (csrc/hostio.cuh); results
+    must not depend on whether a block is fresh or recycled, and dxmcb200_trim_pool must leave the library usable."""
+    import ctypes as C
+
+    rng = np.random.default_rng(11)
+    dim = (160, 160, 160)  # 4 M voxels: accumulators (131 MB) and staging arrays are pool-sized
+    n = int(np.prod(dim))
+    material = rng.integers(0, 3, n, dtype=np.uint8)
+    density = np.array([0.0012, 1.0, 1.9], np.float32)[material]
+    half = [d * 0.5 for d in dim]
+    ext = (-half[0], half[0], -half[1], half[1], -half[2], half[2])
+    maxima = []
+    for trip in range(3):
+        ctx = cabi.Context(0)
+        ctx.set_world(dim, (1.0, 1.0, 1.0), ext, density, material)
+        maxima.append(ctx.material_max_density(3))
+        raw = ctx.get_raw()
+        assert not raw[0].any() and not raw[2].any()  # recycled accumulators are cleared
+        ctx.close()
+        if trip == 1:
+            assert cabi.lib().dxmcb200_trim_pool(C.c_int(-1)) == 0
+    assert all(T.bit_equal(m, maxima[0]) for m in maxima)
