@@ -327,11 +327,12 @@ protected:
         const auto slice = dim[0] * dim[1];
         const auto voxelArea = spacing[0] * spacing[1];
         std::vector<std::pair<T, T>> massExposure(dim[2]);
-        for (std::size_t k = 0; k < dim[2]; ++k) {
-            // slice mass accumulated in double by the same library reduction the reference calls
+        // one slice per task on all host cores; each slice mass is still accumulated in double by the same library
+        // reduction the reference calls, so the table has the reference's bits
+        detail::parallelFor(dim[2], [&](std::size_t k) {
             const auto sum = std::reduce(std::execution::par_unseq, densBeg + slice * k, densBeg + slice * (k + 1), 0.0);
             massExposure[k] = { static_cast<T>(sum * voxelArea), exposure[k] };
-        }
+        });
         std::sort(massExposure.begin(), massExposure.end());
         const T mean = std::reduce(std::execution::par_unseq, exposure.cbegin(), exposure.cend(), T { 0.0 }) / dim[2];
         m_mass.resize(dim[2]);
@@ -352,10 +353,10 @@ protected:
         m_positionIntensity.resize(dim[2]);
         const auto slice = dim[0] * dim[1];
         const auto voxelArea = spacing[0] * spacing[1];
-        for (std::size_t k = 0; k < dim[2]; ++k) {
+        detail::parallelFor(dim[2], [&](std::size_t k) {
             const T mass = std::reduce(std::execution::par_unseq, densBeg + slice * k, densBeg + slice * (k + 1), T { 0.0 }) * voxelArea;
             m_positionIntensity[k] = intensityForMass(mass);
-        }
+        });
         m_valid = true;
     }
 
