@@ -1241,11 +1241,9 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             if (status != DXMCB200_OK)
                 break;
             if (cb) {
-                const uint64_t before = expDone;
                 while (expDone + 1 < nExp && prefix[expDone + 1] <= issuedHistories)
                     ++expDone; // the last exposure is reported when everything has drained
-                if (expDone != before)
-                    cb(expDone, user);
+                cb(expDone, user); // every wave, also without news: the callee polls its cancel request here
             }
         }
         if (cancel && *cancel) {

@@ -4,6 +4,7 @@
 // path through these calls. oracle/ref_harness.cpp implements the same header on the unmodified
 // reference for comparison; nothing here touches oracle/.
 #include "dxmcb200_scene.h"
+#include "dxmcb200_scene_monitor.hpp"
 
 #include "dxmc.hpp"
 #include "dxmc/attenuationlut.hpp"
@@ -719,6 +720,38 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
             std::strncpy(info->units, std::string(res.dose_units).c_str(), sizeof(info->units) - 1);
         }
         trace("copy to caller arrays");
+        return DXS_OK;
+    });
+}
+
+int dxs_transport_monitored(dxs_scene* s, int model, int outputMode, int useCalibration, uint64_t seed, int nWorkers, double cancelAtPercent,
+    float* dose, uint32_t* nEvents, float* variance, dxs_result_info* info, dxs_progress_report* report)
+{
+    if (!s || !s->source)
+        return DXS_ERR_STATE;
+    return guarded([&] {
+        Transport<float> tr;
+        if (nWorkers > 0)
+            tr.setNumberOfWorkers(nWorkers);
+        tr.setLowEnergyCorrectionModel(static_cast<LOWENERGYCORRECTION>(model));
+        tr.setOutputMode(outputMode == DXS_OUT_DOSE ? Transport<float>::OUTPUTMODE::DOSE : Transport<float>::OUTPUTMODE::EV_PER_HISTORY);
+        s->world->makeValid();
+        if (seed != 0)
+            tr.setSeed(seed);
+        Result<float> res = dxs_monitor::run<Result<float>, ProgressBar<float>>(tr, *s->world, s->source.get(), useCalibration != 0, cancelAtPercent, report);
+        const auto n = res.dose.size();
+        if (dose)
+            std::memcpy(dose, res.dose.data(), n * sizeof(float));
+        if (nEvents)
+            std::memcpy(nEvents, res.nEvents.data(), n * sizeof(std::uint32_t));
+        if (variance)
+            std::memcpy(variance, res.variance.data(), n * sizeof(float));
+        if (info) {
+            info->histories = res.numberOfHistories;
+            info->seconds = res.simulationTime.count();
+            std::memset(info->units, 0, sizeof(info->units));
+            std::strncpy(info->units, std::string(res.dose_units).c_str(), sizeof(info->units) - 1);
+        }
         return DXS_OK;
     });
 }

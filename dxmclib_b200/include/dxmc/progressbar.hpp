@@ -4,7 +4,8 @@
 // B200 path exposures complete in launch-sized groups: Transport calls exposureCompleted(n) after
 // each launch and checks cancel() between launches. The preview image is a maximum-intensity
 // projection of the dose buffer registered with setDoseData(); Transport refreshes that host
-// buffer from the device accumulators between launches when a ProgressBar is attached.
+// buffer from the device accumulators between waves (at most four times a second) when a
+// ProgressBar is attached.
 #pragma once
 #include "dxmc/floating.hpp"
 
@@ -113,7 +114,7 @@ public:
                     m = std::max(m, d);
                     globalMax = std::max(globalMax, m);
                 }
-        const T scale = T { 255.0 } / globalMax;
+        const T scale = globalMax > 0 ? T { 255.0 } / globalMax : T { 0 }; // an all-zero buffer gives an all-zero image
         img->image.resize(mip.size());
         std::transform(mip.cbegin(), mip.cend(), img->image.begin(), [=](const T el) { return static_cast<std::uint8_t>(el * scale); });
         return img;

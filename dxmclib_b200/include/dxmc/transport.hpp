@@ -186,8 +186,10 @@ public:
         trace("run");
         if (completed)
             collect(world, source, result, useSourceDoseCalibration, progressbar);
-        else
-            result.numberOfHistories = 0; // cancelled: all zeros, like a cancelled reference run
+        else { // cancelled: all zeros, like a cancelled reference run (transport.hpp:176-185)
+            std::fill(result.dose.begin(), result.dose.end(), T { 0 }); // may hold a live preview of the partial dose
+            result.numberOfHistories = 0;
+        }
         trace("collect");
         release();
         trace("release");
@@ -281,15 +283,36 @@ public:
         }
         struct Progress {
             ProgressBar<T>* bar;
+            dxmcb200_ctx* ctx;
+            T* liveDose; // the buffer registered with ProgressBar::setDoseData, or null
+            std::size_t voxels;
             std::uint64_t reported = 0;
             volatile int cancel = 0;
-        } progress { progressbar };
+            std::chrono::steady_clock::time_point lastRefresh {};
+            std::vector<float> staging; // T = double only
+        } progress { progressbar, m_ctx.get(), (progressbar && result) ? result->dose.data() : nullptr, result ? result->dose.size() : 0 };
+        // Called by the runtime on this thread between waves. The reference's workers add into result.dose directly, so a
+        // GUI thread polling ProgressBar::computeDoseProgressImage sees the dose build up (progressbar.hpp:86-109); here the
+        // registered buffer is refreshed from the device accumulators (raw keV sums, like the reference's live buffer) at
+        // most four times a second: one decode pass + download, about 1 % of the run at 512x512x400.
         auto callback = [](std::uint64_t done, void* user) {
             auto* p = static_cast<Progress*>(user);
-            if (p->bar) {
-                p->bar->exposureCompleted(done - p->reported);
-                p->reported = done;
-                p->cancel = p->bar->cancel() ? 1 : 0;
+            if (!p->bar)
+                return;
+            p->bar->exposureCompleted(done - p->reported);
+            p->reported = done;
+            p->cancel = p->bar->cancel() ? 1 : 0;
+            const auto now = std::chrono::steady_clock::now();
+            if (p->liveDose && !p->cancel && now - p->lastRefresh >= std::chrono::milliseconds(250)) {
+                std::scoped_lock guard(p->bar->doseMutex());
+                if constexpr (std::is_same_v<T, float>) {
+                    dxmcb200_get_result(p->ctx, 2, 1, 1.0f, p->liveDose, nullptr, nullptr);
+                } else {
+                    p->staging.resize(p->voxels);
+                    if (dxmcb200_get_result(p->ctx, 2, 1, 1.0f, p->staging.data(), nullptr, nullptr) == DXMCB200_OK)
+                        std::copy(p->staging.begin(), p->staging.end(), p->liveDose);
+                }
+                p->lastRefresh = std::chrono::steady_clock::now();
             }
         };
         if (progressbar && progressbar->cancel())

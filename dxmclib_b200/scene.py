@@ -62,6 +62,11 @@ class ResultInfo(C.Structure):
     _fields_ = [("histories", C.c_uint64), ("seconds", C.c_double), ("units", C.c_char * 16)]
 
 
+class ProgressReport(C.Structure):
+    _fields_ = [("percent_seen", C.c_double), ("percent_final", C.c_double), ("images_polled", C.c_uint32), ("images_nonzero", C.c_uint32),
+                ("image_width", C.c_uint32), ("image_height", C.c_uint32), ("cancelled", C.c_int32), ("eta", C.c_char * 96)]
+
+
 # every symbol include/dxmcb200_scene.h declares (the CPU test suite checks the export list against this)
 SCENE_SYMBOLS = [
     "dxs_backend", "dxs_last_error", "dxs_create", "dxs_destroy", "dxs_world_geometry", "dxs_world_add_material",
@@ -72,7 +77,7 @@ SCENE_SYMBOLS = [
     "dxs_lut_max_inverse", "dxs_lut_scatter_factor", "dxs_lut_sample_form_factor", "dxs_lut_table",
     "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
-    "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport",
+    "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport", "dxs_transport_monitored",
     "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_run_strided", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
 ]
 
@@ -436,6 +441,20 @@ class Scene:
                                     dose.ctypes.data_as(_f32p), None if ev is None else ev.ctypes.data_as(_u32p),
                                     None if var is None else var.ctypes.data_as(_f32p), C.byref(info)), "dxs_transport")
         return Result(dose, ev, var, int(info.histories), float(info.seconds), info.units.decode())
+
+    def transport_monitored(self, model=MODEL_LIVERMORE, output=OUT_EV_PER_HISTORY, use_calibration=False, seed=0, workers=0,
+                            cancel_at_percent=0.0):
+        """Transport::operator() with a ProgressBar polled (and optionally cancelled) from a second thread; returns
+        (Result, report dict)."""
+        n = int(np.prod(self.dim))
+        dose, ev, var = np.zeros(n, np.float32), np.zeros(n, np.uint32), np.zeros(n, np.float32)
+        info, rep = ResultInfo(), ProgressReport()
+        _chk(self.lib.dxs_transport_monitored(self.h, model, output, int(use_calibration), C.c_uint64(seed), int(workers),
+                                              C.c_double(cancel_at_percent), dose.ctypes.data_as(_f32p), ev.ctypes.data_as(_u32p),
+                                              var.ctypes.data_as(_f32p), C.byref(info), C.byref(rep)), "dxs_transport_monitored")
+        report = {k: getattr(rep, k) for k, _ in ProgressReport._fields_}
+        report["eta"] = rep.eta.decode(errors="replace")
+        return Result(dose, ev, var, int(info.histories), float(info.seconds), info.units.decode()), report
 
     # ---- B200 extensions (product library only)
     def b200_prepare(self, device=0, model=MODEL_LIVERMORE, seed=0, total_histories_all_ranks=0):

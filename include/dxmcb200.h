@@ -138,6 +138,9 @@ int dxmcb200_set_fixed_point(dxmcb200_ctx*, int energy_bits, int energy_sq_bits)
 int dxmcb200_clear(dxmcb200_ctx*);
 
 /* ---- the hot path ------------------------------------------------------------------------- */
+/* called on the calling thread after every wave with the number of exposures of the run whose histories have all been
+ * issued so far (the value repeats while a long exposure is in flight), and once with the full count at the end; the
+ * callee may set the run's cancel flag, which is polled right after the call */
 typedef void (*dxmcb200_progress_cb)(uint64_t exposures_done, void* user);
 
 /* Counter-based per-history stream (replaces the per-thread std::random_device seeding of

@@ -202,6 +202,23 @@ typedef struct dxs_result_info {
 int dxs_transport(dxs_scene*, int model, int output_mode, int use_calibration, uint64_t seed, int n_workers,
     float* dose, uint32_t* n_events, float* variance, dxs_result_info* info);
 
+/* Transport::operator() WITH a ProgressBar, driven the way the reference's callers drive it (validation.cpp:269-290):
+ * the call runs on this thread while a second thread polls ProgressBar::getETA and computeDoseProgressImage every 2 ms
+ * and, when cancel_at_percent > 0, calls setCancel(true) once the reported progress reaches it. A cancelled run returns
+ * an all-zero result with histories == 0 (transport.hpp:176-185). Both implementations export it. */
+typedef struct dxs_progress_report {
+    double percent_seen;      /* largest progress the monitor saw in getETA() while the run was in flight */
+    double percent_final;     /* progress in getETA() after the call returned */
+    uint32_t images_polled;   /* computeDoseProgressImage() calls that returned an image */
+    uint32_t images_nonzero;  /* ... of the right size with at least one non-zero pixel (the live dose is visible) */
+    uint32_t image_width, image_height;
+    int32_t cancelled;        /* the monitor called setCancel(true) */
+    char eta[96];             /* last getETA() string */
+} dxs_progress_report;
+int dxs_transport_monitored(dxs_scene*, int model, int output_mode, int use_calibration, uint64_t seed, int n_workers,
+    double cancel_at_percent, float* dose, uint32_t* n_events, float* variance, dxs_result_info* info,
+    dxs_progress_report* report);
+
 /* ---- B200 extensions: the phases of Transport::operator() kept apart so a caller can hold the world,
  * tables and exposures resident on the GPU (bench.py device-resident timing, multi-GPU sharding).
  * The reference harness answers DXS_ERR_UNSUPPORTED. -------------------------------------------------- */
