@@ -1,4 +1,4 @@
-"""AAPM TG-195 Case 2 and Case 4.1 (the second further down). Case 2 (radiography of a soft-tissue slab with nine volumes of interest) as the reference's validation
+"""AAPM TG-195 Case 2, and further down Cases 4.1, 4.2 and 3 (all the reference ships except Case 5, whose voxel phantom is a data file of the reference). Case 2 (radiography of a soft-tissue slab with nine volumes of interest) as the reference's validation
 program sets it up (validation/validation.cpp:318-393 world, :425-471 source, :496-512 published values): 80x200x360
 voxels of 5 mm, 390x390x200 mm soft tissue at z = 1550 mm, isotropic point source at the origin collimated to the slab,
 56.4 keV, 0 degrees, forced interactions in the VOIs.
@@ -180,3 +180,179 @@ def test_tg195_case41_against_reference_and_published(gpu, product, reference, w
     print(f"TG-195 case 4.1, 56.4 keV, {'80' if wide else '10'} mm: slabs product/published eV per history "
           + ", ".join(f"{g:.1f}/{p:.1f}" for g, p in zip(mean_a, pub)) + f"; worst z vs reference {z.max():.2f}")
     assert np.all(np.abs(mean_a - pub) / pub < 0.15)
+
+
+# ---- Case 4.2: computed tomography, 320 mm PMMA cylinder with a central and a peripheral 10 mm rod --------------------
+# validation/validation.cpp:1054-1108 (world), :1111-1277 (sources, scoring, published values): 1200x1200x60 voxels of
+# 1x1x50 mm, PMMA cylinder of 160 mm radius, two rods of 5 mm radius (material indices 2: centre, 3: at x = -150 mm)
+# scored over the central 100 mm; simulation 0 is a full rotation (IsotropicCTSource), simulations 1..36 are single
+# projections with the source rotated by -(i-1)*10 degrees about z from (-600, 0, 0); 56.4 keV, 10 mm beam.
+TG195_CASE42 = {0: (12.11, 34.70), 1: (12.168675, 101.29375), 10: (12.149575, 12.166625)}  # (centre, periphery), :1137-1138
+
+
+def case42_arrays():
+    dim, sp = (1200, 1200, 60), (1.0, 1.0, 50.0)
+    x = np.arange(dim[0]) * sp[0] - dim[0] * sp[0] / 2  # circleIndices tests the voxel's lower corner (:556-574)
+    y = np.arange(dim[1]) * sp[1] - dim[1] * sp[1] / 2
+
+    def disc(cx, cy, r):
+        return ((x[None, :] - cx) ** 2 + (y[:, None] - cy) ** 2) <= r * r
+
+    body, centre, periphery = disc(0.0, 0.0, 160.0), disc(0.0, 0.0, 5.0), disc(-150.0, 0.0, 5.0)
+    zc = np.arange(dim[2]) * sp[2] - dim[2] * sp[2] / 2 + sp[2] / 2
+    scored = (zc >= -50) & (zc < 50)
+    mat = np.zeros((dim[2], dim[1], dim[0]), np.uint8)
+    mat[:, body] = 1
+    for k in np.nonzero(scored)[0]:
+        mat[k][centre] = 2
+        mat[k][periphery] = 3
+    dens = np.where(mat > 0, np.float32(1.19), np.float32(0.001205)).astype(np.float32)
+    return dim, sp, mat, dens
+
+
+def case42_scene(lib, arrays, simulation, histories, exposures):
+    dim, sp, mat, dens = arrays
+    sc = S.Scene(lib)
+    sc.world(dim, sp)
+    sc.add_material(T.AIR, 0.001205)
+    for _ in range(3):
+        sc.add_material(PMMA, 1.19)
+    sc.arrays(dens, mat)
+    assert sc.validate()
+    fan, beam = math.atan(160.0 / 600.0), math.atan(5.0 / 600.0)
+    angle = 0.0 if simulation == 0 else -math.radians((simulation - 1) * 10.0)
+    c, s = math.cos(angle), math.sin(angle)
+    rot = lambda v: (c * v[0] - s * v[1], s * v[0] + c * v[1], v[2])  # noqa: E731  rotation about z (vectormath::rotate)
+    pos, cos_x, cos_y = rot((-600.0, 0.0, 0.0)), rot((0.0, 1.0, 0.0)), rot((0.0, 0.0, 1.0))
+    sc.source_isotropic(pos, cos_x + cos_y, (-fan, fan, -beam, beam), np.array([1.0], np.float32), np.array([56.4], np.float32),
+                        histories, exposures, ct=(simulation == 0))
+    return sc
+
+
+@pytest.mark.parametrize("simulation", [0, 1, 10])
+def test_tg195_case42_against_reference_and_published(gpu, product, reference, simulation):
+    arrays = case42_arrays()
+    mat = arrays[2].ravel()
+    correction = math.pi * 5 * 5 * 100 / (float(np.prod(arrays[1])) * np.count_nonzero(mat == 2))  # :1232-1234
+    rods = [np.flatnonzero(mat == 2), np.flatnonzero(mat == 3)]
+
+    def rod_ev(result):
+        d = result.dose
+        return np.array([correction * d[idx].astype(np.float64).sum() for idx in rods]), float(d.astype(np.float64).sum())
+
+    replicas, exposures = 6, 36
+    hist_product, hist_reference = 600_000, 220_000  # per exposure: 2.16e7 histories per replica, 7.9e6 for the reference
+    got, total = [], []
+    for r in range(replicas):
+        sc = case42_scene(product, arrays, simulation, hist_product, exposures)
+        res = sc.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 41 * r)
+        v, t = rod_ev(res)
+        got.append(v)
+        total.append(t)
+        sc.close()
+    got = np.array(got)
+    mean_a, sigma_a = got.mean(axis=0), got.std(axis=0, ddof=1)
+    sb = case42_scene(reference, arrays, simulation, hist_reference, exposures)
+    rb = sb.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 9, workers=S.WORKERS_COUNTER_STREAMS)
+    mean_b, total_b = rod_ev(rb)
+    sb.close()
+    # (1) same inputs, two implementations: energy deposited in the whole phantom within 0.5 %, both rods within 3.5
+    # sigma of the combined uncertainty (sigma of one product replica from the replicas, scaled by the history counts)
+    assert abs(np.mean(total) - total_b) / total_b < 5e-3
+    sigma = sigma_a * math.sqrt(1.0 / replicas + hist_product / hist_reference)
+    z = np.abs(mean_a - mean_b) / sigma
+    assert np.all(z < 3.5), (mean_a, mean_b, sigma, z)
+    # (2) published TG-195 values, informational bound (approximate cross-section data on both sides)
+    pub = np.array(TG195_CASE42[simulation])
+    print(f"TG-195 case 4.2, 56.4 keV, 10 mm, simulation {simulation}: centre / periphery product {mean_a[0]:.2f} / {mean_a[1]:.2f}, "
+          f"reference {mean_b[0]:.2f} / {mean_b[1]:.2f}, published {pub[0]:.2f} / {pub[1]:.2f} eV per history; worst z {z.max():.2f}")
+    assert np.all(np.abs(mean_a - pub) / pub < 0.15)
+
+
+# ---- Case 3: mammography -------------------------------------------------------------------------------------------
+# validation/validation.cpp:576-711 (world), :713-790 (source), :806-823 (published values): 342x342x770 voxels of 1 mm,
+# compressed breast (semicircular, 5 cm thick, 2 mm skin) between two 2 mm PMMA plates in front of a water body, seven
+# 20x20x10 mm VOIs (material indices 5..11); isotropic point source 660 mm above the detector plane, collimated to the
+# 140 x 260 mm field; 16.8 keV, 0 degrees.
+TG195_CASE3_TOTAL = 4697.333
+TG195_CASE3_VOI = [17.692, 18.070, 17.865, 17.262, 17.768, 5.417, 56.017]
+BREAST = ("H61.9873215815672C25.2115870352038N0.812500094703561O11.959397097091P0.00826728025671175S0.00798629068764982"
+          "K0.00655039238754296Ca0.00639022810261801")
+SKIN = ("H61.6819253067427C9.42172044694575N2.26874188115669O26.5008052432356P0.0359095410401931S0.034689042139856"
+        "K0.02845211205691Ca0.027756426682265")
+WATER = "H66.6220373399527O33.3779626600473"
+
+
+def case3_arrays():
+    dim = (342, 342, 770)
+    z_lo = 660.0 - dim[2]
+    x = -dim[0] / 2 + np.arange(dim[0]) + 0.5
+    y = -dim[1] / 2 + np.arange(dim[1]) + 0.5
+    z = z_lo + np.arange(dim[2]) + 0.5
+    Z, Y, X = z[:, None, None], y[None, :, None], x[None, None, :]
+    centre = 40.0
+    mat = np.zeros((dim[2], dim[1], dim[0]), np.uint8)
+    filled = Z < 301  # nothing but air above
+    r2 = X * X + Y * Y
+    mat[filled & (Z > centre - 25) & (Z < centre + 25) & (X > 0) & (r2 < 100.0 ** 2)] = 3  # skin
+    mat[filled & (Z > centre - 23) & (Z < centre + 23) & (X > 0) & (r2 < 98.0 ** 2)] = 4  # breast tissue
+    boxes = [(1, (-170, 0, -150, 150, -150, 150)), (2, (0, 140, -130, 130, 25, 27)), (2, (0, 140, -130, 130, -27, -25)),
+             (7, (40, 60, -10, 10, -5, 5)), (6, (10, 30, -10, 10, -5, 5)), (8, (70, 90, -10, 10, -5, 5)),
+             (9, (40, 60, 20, 40, -5, 5)), (5, (40, 60, -40, -20, -5, 5)), (11, (40, 60, -10, 10, 10, 20)),
+             (10, (40, 60, -10, 10, -20, -10))]
+    for index, (x0, x1, y0, y1, z0, z1) in boxes:
+        mat[filled & (X > x0) & (X < x1) & (Y > y0) & (Y < y1) & (Z > z0 + centre) & (Z < z1 + centre)] = index
+    density = np.array([0.001205, 1.0, 1.19, 1.09] + [0.952] * 8, np.float32)
+    return dim, (1.0, 1.0, 1.0), (0.0, 0.0, (z_lo + 660.0) / 2), mat, density[mat]
+
+
+def case3_scene(lib, arrays, histories, exposures):
+    dim, sp, origin, mat, dens = arrays
+    sc = S.Scene(lib)
+    sc.world(dim, sp, origin)
+    sc.add_material(T.AIR, 0.001205).add_material(WATER, 1.0).add_material(PMMA, 1.19).add_material(SKIN, 1.09)
+    for _ in range(8):
+        sc.add_material(BREAST, 0.952)
+    sc.arrays(dens, mat)
+    assert sc.validate()
+    ax, ay = math.atan(140.0 / 660.0), math.atan(130.0 / 660.0)
+    sc.source_isotropic((0.0, 0.0, 660.0), (1, 0, 0, 0, -1, 0), (0.0, ax, -ay, ay), np.array([1.0], np.float32), np.array([16.8], np.float32),
+                        histories, exposures)
+    return sc
+
+
+def test_tg195_case3_against_reference_and_published(gpu, product, reference):
+    arrays = case3_arrays()
+    mat = arrays[3].ravel()
+    vois = [np.flatnonzero(mat == i) for i in range(5, 12)]
+    breast = np.flatnonzero(mat > 3)
+
+    def sums(result):
+        d = result.dose
+        return np.array([d[idx].astype(np.float64).sum() for idx in vois]), float(d[breast].astype(np.float64).sum())
+
+    replicas, exposures, hist_product, hist_reference = 6, 16, 1_000_000, 400_000
+    got, total = [], []
+    for r in range(replicas):
+        sc = case3_scene(product, arrays, hist_product, exposures)
+        res = sc.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 53 * r)
+        v, t = sums(res)
+        got.append(v)
+        total.append(t)
+        sc.close()
+    got = np.array(got)
+    mean_a, sigma_a = got.mean(axis=0), got.std(axis=0, ddof=1)
+    sb = case3_scene(reference, arrays, hist_reference, exposures)
+    rb = sb.transport(model=S.MODEL_LIVERMORE, output=S.OUT_EV_PER_HISTORY, seed=T.SEED + 13, workers=S.WORKERS_COUNTER_STREAMS)
+    mean_b, total_b = sums(rb)
+    sb.close()
+    # (1) same inputs, two implementations: energy deposited in the breast within 0.5 %, every VOI within 3.5 sigma
+    assert abs(np.mean(total) - total_b) / total_b < 5e-3
+    z = np.abs(mean_a - mean_b) / (sigma_a * math.sqrt(1.0 / replicas + hist_product / hist_reference))
+    assert np.all(z < 3.5), (mean_a, mean_b, sigma_a, z)
+    # (2) published TG-195 values, informational bound: at 16.8 keV the photoelectric data of xrl_lite matter most
+    print(f"TG-195 case 3, 16.8 keV, 0 deg: breast total {np.mean(total):.1f} eV/history (reference {total_b:.1f}, published "
+          f"{TG195_CASE3_TOTAL}); VOIs product/published " + ", ".join(f"{g:.2f}/{p:.2f}" for g, p in zip(mean_a, TG195_CASE3_VOI))
+          + f"; worst z vs reference {z.max():.2f}")
+    assert abs(np.mean(total) - TG195_CASE3_TOTAL) / TG195_CASE3_TOTAL < 0.15
+    assert np.all(np.abs(mean_a - np.array(TG195_CASE3_VOI)) / np.array(TG195_CASE3_VOI) < 0.20)
