@@ -34,8 +34,8 @@ from dxmclib_b200 import phantoms, sharding  # noqa: E402
 from dxmclib_b200 import scene as S  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size transportKernel launch, from the committed
-# `ncu --set full` capture (profiles/r1_v6_*), bytes
-TRAFFIC_PER_LAUNCH = 11.960e9  # profiles/r1_v6_transportKernel_ncu_summary.csv: 8.212 GB read + 3.748 GB written, 2^26-record wave
+# `ncu --set full` capture (profiles/r1_v7_*), bytes
+TRAFFIC_PER_LAUNCH = 9.441e9  # profiles/r1_v7_transportKernel_ncu_summary.csv: 5.713 GB read + 3.728 GB written, 2^26-record wave
 
 DIM = (512, 512, 400)
 SPACING = (1.0, 1.0, 1.0)
@@ -155,8 +155,8 @@ def workload_config(n_ranks, hist):
                     f"{DIM[0]}x{DIM[1]}x{DIM[2]} @1 mm, 10 materials, {EXPOSURES * n_ranks} exposures x {hist} histories",
         "voxels": int(np.prod(DIM)), "exposures": EXPOSURES * n_ranks, "histories_per_exposure": hist,
         "histories_per_step": EXPOSURES * n_ranks * hist, "sharding": f"exposures interleaved over {n_ranks} GPU(s) (rank r: r, r+N, ...), one all-reduce of the fixed-point grids",
-        "l2_note": "accumulators 3.4 GB + photon/event record streams (>20 GB per wave pair) exceed the 126 MB L2; the palette voxel "
-                   "grid is 105 MB; accumulators are cleared every step",
+        "l2_note": "accumulators 3.4 GB + photon/event record streams (>20 GB per wave pair) exceed the 126 MB L2; the 4-bit palette voxel "
+                   "grid is 52 MB; accumulators are cleared every step",
     }
 
 

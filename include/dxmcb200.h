@@ -11,7 +11,9 @@
  * dxmcb200_create fails with DXMCB200_ERR_NO_DEVICE.
  *
  * Threading: one ctx per device per host thread. dxmcb200_run is synchronous for the caller and
- * asynchronous on the ctx's own CUDA stream inside.
+ * asynchronous on the ctx's own CUDA streams inside (two wave pipelines). dxmcb200_set_world and
+ * dxmcb200_get_result move the caller's pageable arrays through pinned staging buffers on a few helper
+ * threads of their own; large device blocks are pooled per process (dxmcb200_trim_pool).
  */
 #ifndef DXMCB200_H
 #define DXMCB200_H
@@ -39,7 +41,8 @@ enum dxmcb200_status {
 
 /* World<T> as the hot loop sees it (reference world.hpp:37-68, transport.hpp:485-521, 643-645).
  * Voxel order is x fastest: idx = z*nx*ny + y*nx + x (transport.hpp:514). Arrays are HOST pointers
- * and are copied (packed into one 8-byte record per voxel on the device). measurement may be NULL. */
+ * and are copied (packed on the device: one 8-byte record per voxel, or one byte / half a byte per voxel
+ * plus a 256-entry record table when the grid holds at most 256 / 16 distinct records). measurement may be NULL. */
 typedef struct dxmcb200_world {
     uint64_t dim[3];
     float spacing[3];
