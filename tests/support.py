@@ -87,16 +87,17 @@ def tissue_block(lib, dim=(24, 20, 28), spacing=(4.0, 5.0, 3.0), origin=(3.0, -2
 
 def dx_slab_scene(lib, histories=500000, exposures=8):
     """BASELINE config #2 in small: a 120 kVp tungsten-anode DX source (the built-in tube model with heel effect, 2.5 mm Al)
-    onto a voxelised soft-tissue slab with a bone and a water insert, 5 mm voxels, tube 1 m above the isocentre (beam along -z)."""
-    dim, sp = (48, 48, 40), (5.0, 5.0, 5.0)
+    onto a voxelised soft-tissue slab with a bone and a water insert, 10 mm voxels, tube 1 m above the isocentre (beam
+    along -z)."""
+    dim, sp = (24, 24, 20), (10.0, 10.0, 10.0)
     sc = S.Scene(lib)
     sc.world(dim, sp)
     sc.add_material(AIR, 0.001205).add_material(SOFT, 1.03).add_material(BONE, 1.92).add_material("Water, Liquid", 1.0)
     nx, ny, nz = dim
     mat = np.zeros((nz, ny, nx), np.uint8)
-    mat[8:32, 4:44, 4:44] = 1  # 120 mm thick slab
-    mat[14:22, 12:24, 12:36] = 2  # bone insert
-    mat[14:26, 28:40, 12:36] = 3  # water insert
+    mat[4:16, 2:22, 2:22] = 1  # 120 mm thick slab
+    mat[7:11, 6:12, 6:18] = 2  # bone insert
+    mat[7:13, 14:20, 6:18] = 3  # water insert
     sc.arrays(np.array([0.001205, 1.03, 1.92, 1.0], np.float32)[mat], mat)
     assert sc.validate()
     sc.source_dx(voltage=120.0, al_mm=2.5, sdd=1000.0, field_size=(180.0, 180.0), source_angles_deg=(0.0, 90.0), tube_rotation_deg=0.0,

@@ -48,7 +48,7 @@ def test_against_committed_reference_streams(gpu, product, name, model):
     ("isotropic_ia", lambda lib: T.isotropic_scene(lib, histories=8000000, exposures=4), 2),
     ("ct_spiral", lambda lib: T.ct_scene(lib, histories=250000), 1),
     ("ct_axial_none", lambda lib: T.ct_scene(lib, spiral=False, histories=250000, xcare=False, tilt=0.0), 0),
-    ("dx_tube_slab", lambda lib: T.dx_slab_scene(lib, histories=1500000, exposures=8), 1),  # BASELINE config #2 in small
+    ("dx_tube_slab", lambda lib: T.dx_slab_scene(lib, histories=3000000, exposures=8), 1),  # BASELINE config #2 in small
 ])
 def test_live_reference_three_sigma(gpu, product, reference, name, builder, model):
     a = builder(product).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
