@@ -364,6 +364,8 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
         st[lane] = lane == IN_SHARD ? myShard : 0u;
     __syncwarp();
 
+    // The bookkeeping words in `st` are warp-uniform: every lane reads them, lane 0 alone writes them, with a __syncwarp
+    // between a write and the next read (compute-sanitizer racecheck runs clean on this kernel).
     // request the next group of records into the free half of the ring (no-op when both halves are in flight)
     auto issueGroup = [&]() {
         const unsigned issued = st[ISSUED];
@@ -373,8 +375,13 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
         if (tileNext >= tileEnd) { // claim the next tile: from the warp's own shard first, then round the others
             unsigned tried = st[SHARDS_TRIED], shard = st[IN_SHARD];
             for (;;) {
-                if (tried >= kShards)
+                if (tried >= kShards) { // every shard is drained: remember it, so that the next call returns at once
+                    __syncwarp(); // all lanes have read the words lane 0 is about to write
+                    if (lane == 0)
+                        st[SHARDS_TRIED] = tried;
+                    __syncwarp();
                     return;
+                }
                 const unsigned n = min(P.inCursors[shard].stored, P.photonRegion); // filled by completed kernels
                 unsigned t = n;
                 if (lane == 0 && n)
@@ -387,10 +394,13 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 }
                 shard = (shard + 1) % kShards;
                 ++tried;
+            }
+            __syncwarp(); // all lanes have read the words lane 0 is about to write
+            if (lane == 0) {
                 st[IN_SHARD] = shard;
                 st[SHARDS_TRIED] = tried;
+                st[TILE_END] = tileEnd;
             }
-            st[TILE_END] = tileEnd;
         }
         const unsigned half = issued & 1u;
         const unsigned cnt = min(kGroup, tileEnd - tileNext);
@@ -403,9 +413,13 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 cpAsync16(dst + piece * 16, src + piece * 16);
         }
         cpAsyncCommit();
-        st[COUNT0 + half] = cnt;
-        st[TILE_NEXT] = tileNext + kGroup;
-        st[ISSUED] = issued + 1;
+        __syncwarp(); // all lanes have read the words lane 0 is about to write
+        if (lane == 0) {
+            st[COUNT0 + half] = cnt;
+            st[TILE_NEXT] = tileNext + kGroup;
+            st[ISSUED] = issued + 1;
+        }
+        __syncwarp();
     };
     // make the oldest requested group the current one; false when the wave is drained
     auto openGroup = [&]() {
@@ -539,8 +553,11 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
             ringPos = min(ringEnd, ringPos + static_cast<unsigned>(__popc(deadMask)));
             deadMask = __ballot_sync(kFull, state == DEAD);
             if (ringPos == ringEnd) { // group handed out completely: recycle its half, move on to the next group
-                __syncwarp(); // every lane has read its record before the half is requested again
-                st[CONSUMED] = st[CONSUMED] + 1;
+                const unsigned consumed = st[CONSUMED];
+                __syncwarp(); // every lane has read its record (and the counter) before the half is requested again
+                if (lane == 0)
+                    st[CONSUMED] = consumed + 1;
+                __syncwarp();
                 issueGroup();
                 openGroup(); // leaves ringPos == ringEnd when the wave is drained
             }
