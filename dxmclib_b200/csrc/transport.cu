@@ -768,19 +768,33 @@ __global__ void paletteIndexKernel(const float* __restrict__ density, const uint
 
 // Per-material maximum density of the grid: the input of the Woodcock majorant (attenuationinterpolator.hpp:48-59,
 // where it is one transform_reduce over all voxels per material). Densities are non-negative (World::validate), so
-// their bit patterns order like unsigned integers; block maxima in shared memory, one atomicMax per material and block.
+// their bit patterns order like unsigned integers. Per trip a warp groups its lanes by material (match.any), takes each
+// group's maximum (redux.sync) and issues ONE shared-memory atomicMax per distinct material; block maxima go out with
+// one global atomicMax per material.
 __global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, unsigned* __restrict__ maxBits)
 {
-    __shared__ unsigned sMax[256];
-    sMax[threadIdx.x] = 0u;
+    __shared__ unsigned sMax[257]; // slot 256: lanes past the end of the grid
+    for (unsigned k = threadIdx.x; k < 257; k += blockDim.x)
+        sMax[k] = 0u;
     __syncthreads();
-    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
-        const uint2 r = records[i];
-        if (sMax[r.y & 0xffu] < r.x) // racy pre-check only saves atomics; the atomicMax decides
-            atomicMax(&sMax[r.y & 0xffu], r.x);
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t trips = (n + stride - 1) / stride; // the same for every thread: the warp stays converged
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    for (uint64_t t = 0; t < trips; ++t, i += stride) {
+        unsigned material = 256u, bits = 0u;
+        if (i < n) {
+            const uint2 r = records[i];
+            material = r.y & 0xffu;
+            bits = r.x;
+        }
+        const unsigned group = __match_any_sync(kFull, material);
+        const unsigned best = __reduce_max_sync(group, bits);
+        if (lane == static_cast<unsigned>(__ffs(group) - 1))
+            atomicMax(&sMax[material], best);
     }
     __syncthreads();
-    if (sMax[threadIdx.x])
+    if (threadIdx.x < 256 && sMax[threadIdx.x])
         atomicMax(maxBits + threadIdx.x, sMax[threadIdx.x]);
 }
 
