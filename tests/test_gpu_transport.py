@@ -99,15 +99,17 @@ def test_bit_reproducible_and_shard_invariant(gpu, product):
 def test_schedule_and_layout_invariance(gpu, product, monkeypatch):
     """The grids do not depend on how the wavefront is scheduled or how the voxel grid is stored: wave size (down to
     1024 photons, i.e. hundreds of waves and drains), re-fill batch, one to three wave pipelines, 4-bit palette (the automatic
-    choice for this grid), byte palette ("8") or 8-byte voxel records ("0") all give bit-identical accumulators."""
+    choice for this grid), byte palette ("8") or 8-byte voxel records ("0"), per-lane or warp-aggregated scoring all give
+    bit-identical accumulators."""
     sc = T.isotropic_scene(product, histories=40000, exposures=6, forced=True)
     flat = T.flatten_scene(sc)
     exps = T.exposures_of(sc)
 
-    def run(batch, palette, pipes):
+    def run(batch, palette, pipes, aggregate="-1"):
         monkeypatch.setenv("DXMCB200_BATCH", batch)
         monkeypatch.setenv("DXMCB200_PALETTE", palette)
         monkeypatch.setenv("DXMCB200_PIPES", pipes)
+        monkeypatch.setenv("DXMCB200_AGGREGATE", aggregate)
         ctx = cabi.Context(0)  # the switches are read when the context is created
         T.load_context(ctx, flat)
         ctx.set_fixed_point(20, 10)
@@ -118,10 +120,11 @@ def test_schedule_and_layout_invariance(gpu, product, monkeypatch):
 
     base = run("4,25", "1", "2")
     assert base[2].sum() > 50000
-    for setting in [("1,10", "1", "2"), ("32,12", "1", "1"), ("8,14", "0", "2"), ("4,25", "0", "1"), ("8,13", "8", "3"), ("8,26", "8", "2")]:
+    for setting in [("1,10", "1", "2"), ("32,12", "1", "1"), ("8,14", "0", "2"), ("4,25", "0", "1"), ("8,13", "8", "3"), ("8,26", "8", "2"), ("8,26", "1", "2", "1"),
+                    ("4,12", "0", "2", "1"), ("8,26", "1", "2", "0")]:
         other = run(*setting)
         for x, y in zip(base, other):
-            assert T.bit_equal(x, y), f"grids differ for DXMCB200_BATCH/PALETTE/PIPES = {setting}"
+            assert T.bit_equal(x, y), f"grids differ for DXMCB200_BATCH/PALETTE/PIPES/AGGREGATE = {setting}"
 
 
 def test_fixed_point_grid_against_oracle(gpu, product):
