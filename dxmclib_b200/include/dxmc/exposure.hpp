@@ -9,162 +9,125 @@
 #pragma once
 #include "dxmc/beamfilters.hpp"
 #include "dxmc/dxmcrandom.hpp"
-#include "dxmc/floating.hpp"
-#include "dxmc/particle.hpp"
+#include "dxmc/types.hpp"
 #include "dxmc/vectormath.hpp"
 
+#include <algorithm>
 #include <array>
 #include <cstdint>
+#include <functional>
 
 namespace dxmc {
 
 template <Floating T = double>
 class Exposure {
+    using Vec3 = std::array<T, 3>;
+    using Cosines = std::array<T, 6>; // x axis then y axis of the beam frame
+
 public:
-    Exposure(const std::array<T, 3>& position, const std::array<T, 6>& directionCosines, const std::array<T, 4>& collimationAngles,
-        std::uint64_t nHistories = 1000, T beamIntensityWeight = 1, const SpecterDistribution<T>* specterDistribution = nullptr,
-        const HeelFilter<T>* heelFilter = nullptr, const BeamFilter<T>* filter = nullptr)
-        : m_position(position)
-        , m_directionCosines(directionCosines)
-        , m_collimationAngles(collimationAngles)
-        , m_beamIntensityWeight(beamIntensityWeight)
-        , m_beamFilter(filter)
-        , m_specterDistribution(specterDistribution)
-        , m_heelFilter(heelFilter)
-        , m_nHistories(nHistories)
-    {
-        normalizeCosines();
-    }
-    // symmetric collimation: full opening angles {x, y}
-    Exposure(const std::array<T, 3>& position, const std::array<T, 6>& directionCosines, const std::array<T, 2>& collimationAngles,
-        std::uint64_t nHistories = 1000, T beamIntensityWeight = 1, const SpecterDistribution<T>* specterDistribution = nullptr,
-        const HeelFilter<T>* heelFilter = nullptr, const BeamFilter<T>* filter = nullptr)
-        : m_position(position)
-        , m_directionCosines(directionCosines)
-        , m_beamIntensityWeight(beamIntensityWeight)
-        , m_beamFilter(filter)
-        , m_specterDistribution(specterDistribution)
-        , m_heelFilter(heelFilter)
-        , m_nHistories(nHistories)
+    // collimation: {x0, x1, y0, y1} half-plane angles, or {x, y} full opening angles (symmetric)
+    template <std::size_t N>
+        requires(N == 2 || N == 4)
+    Exposure(const Vec3& position, const Cosines& directionCosines, const std::array<T, N>& collimationAngles, std::uint64_t nHistories = 1000,
+        T beamIntensityWeight = 1, const SpecterDistribution<T>* specterDistribution = nullptr, const HeelFilter<T>* heelFilter = nullptr,
+        const BeamFilter<T>* filter = nullptr)
+        : m_nHistories(nHistories)
+        , m_weight(beamIntensityWeight)
+        , m_spectrum(specterDistribution)
+        , m_heel(heelFilter)
+        , m_fanFilter(filter)
+        , m_origin(position)
     {
         setCollimationAngles(collimationAngles);
-        normalizeCosines();
+        setDirectionCosines(directionCosines);
     }
 
-    void setPosition(T x, T y, T z) { m_position = { x, y, z }; }
-    void setPosition(const T pos[3]) { m_position = { pos[0], pos[1], pos[2] }; }
-    void setPosition(const std::array<T, 3>& pos) { m_position = pos; }
-    void setPositionZ(const T posZ) { m_position[2] = posZ; }
-    const std::array<T, 3>& position() const { return m_position; }
-    void addPosition(const std::array<T, 3>& pos)
-    {
-        for (std::size_t i = 0; i < 3; ++i)
-            m_position[i] += pos[i];
-    }
-    void subtractPosition(const std::array<T, 3>& pos)
-    {
-        for (std::size_t i = 0; i < 3; ++i)
-            m_position[i] -= pos[i];
-    }
-
-    void setDirectionCosines(T x1, T x2, T x3, T y1, T y2, T y3)
-    {
-        m_directionCosines = { x1, x2, x3, y1, y2, y3 };
-        normalizeCosines();
-    }
-    void setDirectionCosines(const T cosines[6])
-    {
-        for (std::size_t i = 0; i < 6; ++i)
-            m_directionCosines[i] = cosines[i];
-        normalizeCosines();
-    }
-    void setDirectionCosines(const std::array<T, 6>& cosines)
-    {
-        m_directionCosines = cosines;
-        normalizeCosines();
-    }
-    void setDirectionCosines(const std::array<T, 3>& cosinesX, const std::array<T, 3>& cosinesY)
-    {
-        for (std::size_t i = 0; i < 3; ++i) {
-            m_directionCosines[i] = cosinesX[i];
-            m_directionCosines[i + 3] = cosinesY[i];
-        }
-        normalizeCosines();
-    }
-    const std::array<T, 6>& directionCosines() const { return m_directionCosines; }
-    const std::array<T, 3>& beamDirection() const { return m_beamDirection; }
-
-    void setCollimationAngles(const std::array<T, 4>& angles) { m_collimationAngles = angles; }
-    void setCollimationAngles(const std::array<T, 2>& angles) { setCollimationAngles(angles[0], angles[1]); }
-    void setCollimationAngles(const T angleX, const T angleY) { m_collimationAngles = { -angleX / 2, angleX / 2, -angleY / 2, angleY / 2 }; }
-    const std::array<T, 4>& collimationAngles() const { return m_collimationAngles; } // x0 x1 y0 y1
-    T collimationAngleX() const { return m_collimationAngles[1] - m_collimationAngles[0]; }
-    T collimationAngleY() const { return m_collimationAngles[3] - m_collimationAngles[2]; }
-
-    void setBeamIntensityWeight(T weight) { m_beamIntensityWeight = weight; }
-    T beamIntensityWeight() const { return m_beamIntensityWeight; }
-
-    void setBeamFilter(const BeamFilter<T>* filter) { m_beamFilter = filter; }
-    void setSpecterDistribution(const SpecterDistribution<T>* specter) { m_specterDistribution = specter; }
-    void setHeelFilter(const HeelFilter<T>* filter) { m_heelFilter = filter; }
-    // non-owning views used when the exposure is flattened for the device
-    const BeamFilter<T>* beamFilter() const { return m_beamFilter; }
-    const SpecterDistribution<T>* specterDistribution() const { return m_specterDistribution; }
-    const HeelFilter<T>* heelFilter() const { return m_heelFilter; }
-
-    void setMonoenergeticPhotonEnergy(T energy) { m_monoenergeticPhotonEnergy = std::clamp(energy, T { 0.0 }, T { 500.0 }); }
-    T monoenergeticPhotonEnergy() const { return m_monoenergeticPhotonEnergy; }
-
-    void setNumberOfHistories(std::size_t nHistories) { m_nHistories = nHistories; }
-    std::size_t numberOfHistories() const { return m_nHistories; }
-
-    // express position and orientation in the basis (x, y, x cross y) of a world
-    void alignToDirectionCosines(const std::array<T, 6>& directionCosines) noexcept
-    {
-        const T* b1 = directionCosines.data();
-        const T* b2 = b1 + 3;
-        T b3[3];
-        vectormath::cross(b1, b2, b3);
-        vectormath::changeBasisInverse(b1, b2, b3, m_position.data());
-        vectormath::changeBasisInverse(b1, b2, b3, m_directionCosines.data());
-        vectormath::changeBasisInverse(b1, b2, b3, m_directionCosines.data() + 3);
-        vectormath::changeBasisInverse(b1, b2, b3, m_beamDirection.data());
-    }
-
-    // host-side photon draw: fan angle about the y cosine, cone angle about the x cosine
+    // ---- the draw itself (host equivalent of the device birth stage): fan angle about the y cosine, cone angle
+    // about the x cosine, energy from the spectrum (or the mono-energetic value), weight from the filters
     Particle<T> sampleParticle(RandomState& state) const noexcept
     {
-        const T theta = state.randomUniform(m_collimationAngles[0], m_collimationAngles[1]);
-        const T phi = state.randomUniform(m_collimationAngles[2], m_collimationAngles[3]);
-        Particle<T> p { .pos = m_position, .dir = m_beamDirection, .weight = m_beamIntensityWeight };
-        vectormath::rotate(p.dir.data(), &m_directionCosines[3], theta);
-        vectormath::rotate(p.dir.data(), &m_directionCosines[0], phi);
-        p.energy = m_specterDistribution ? m_specterDistribution->sampleValue(state) : m_monoenergeticPhotonEnergy;
-        if (m_beamFilter)
-            p.weight *= m_beamFilter->sampleIntensityWeight(theta);
-        if (m_heelFilter)
-            p.weight *= m_heelFilter->sampleIntensityWeight(phi, p.energy);
-        return p;
+        const T fan = state.randomUniform(m_angles[0], m_angles[1]);
+        const T cone = state.randomUniform(m_angles[2], m_angles[3]);
+        Particle<T> photon { .pos = m_origin, .dir = m_beam, .weight = m_weight };
+        vectormath::rotate(photon.dir.data(), m_frame.data() + 3, fan);
+        vectormath::rotate(photon.dir.data(), m_frame.data(), cone);
+        photon.energy = m_spectrum ? m_spectrum->sampleValue(state) : m_monoEnergy;
+        if (m_fanFilter)
+            photon.weight *= m_fanFilter->sampleIntensityWeight(fan);
+        if (m_heel)
+            photon.weight *= m_heel->sampleIntensityWeight(cone, photon.energy);
+        return photon;
     }
 
-protected:
-    void normalizeCosines()
+    // express position and orientation in the basis (x, y, x cross y) of a world
+    void alignToDirectionCosines(const Cosines& worldCosines) noexcept
     {
-        vectormath::normalize(&m_directionCosines[0]);
-        vectormath::normalize(&m_directionCosines[3]);
-        vectormath::cross(m_directionCosines.data(), m_beamDirection.data());
+        const T* ex = worldCosines.data();
+        const T* ey = ex + 3;
+        T ez[3];
+        vectormath::cross(ex, ey, ez);
+        for (T* v : { m_origin.data(), m_frame.data(), m_frame.data() + 3, m_beam.data() })
+            vectormath::changeBasisInverse(ex, ey, ez, v);
     }
+
+    // ---- how many, how strong, which tables (non-owning views; the source outlives its exposures)
+    std::size_t numberOfHistories() const { return m_nHistories; }
+    void setNumberOfHistories(std::size_t nHistories) { m_nHistories = nHistories; }
+    T beamIntensityWeight() const { return m_weight; }
+    void setBeamIntensityWeight(T weight) { m_weight = weight; }
+    T monoenergeticPhotonEnergy() const { return m_monoEnergy; }
+    void setMonoenergeticPhotonEnergy(T energy) { m_monoEnergy = std::clamp(energy, T { 0.0 }, T { 500.0 }); }
+    const SpecterDistribution<T>* specterDistribution() const { return m_spectrum; }
+    void setSpecterDistribution(const SpecterDistribution<T>* specter) { m_spectrum = specter; }
+    const HeelFilter<T>* heelFilter() const { return m_heel; }
+    void setHeelFilter(const HeelFilter<T>* filter) { m_heel = filter; }
+    const BeamFilter<T>* beamFilter() const { return m_fanFilter; }
+    void setBeamFilter(const BeamFilter<T>* filter) { m_fanFilter = filter; }
+
+    // ---- collimation, stored as {x0, x1, y0, y1}
+    const std::array<T, 4>& collimationAngles() const { return m_angles; }
+    T collimationAngleX() const { return m_angles[1] - m_angles[0]; }
+    T collimationAngleY() const { return m_angles[3] - m_angles[2]; }
+    void setCollimationAngles(const std::array<T, 4>& angles) { m_angles = angles; }
+    void setCollimationAngles(const T angleX, const T angleY) { m_angles = { -angleX / 2, angleX / 2, -angleY / 2, angleY / 2 }; }
+    void setCollimationAngles(const std::array<T, 2>& angles) { setCollimationAngles(angles[0], angles[1]); }
+
+    // ---- beam frame: two cosines, normalised on every change; the beam runs along their cross product
+    const Cosines& directionCosines() const { return m_frame; }
+    const Vec3& beamDirection() const { return m_beam; }
+    void setDirectionCosines(const Cosines& cosines)
+    {
+        m_frame = cosines;
+        vectormath::normalize(m_frame.data());
+        vectormath::normalize(m_frame.data() + 3);
+        vectormath::cross(m_frame.data(), m_beam.data());
+    }
+    void setDirectionCosines(const T cosines[6]) { setDirectionCosines(Cosines { cosines[0], cosines[1], cosines[2], cosines[3], cosines[4], cosines[5] }); }
+    void setDirectionCosines(T x1, T x2, T x3, T y1, T y2, T y3) { setDirectionCosines(Cosines { x1, x2, x3, y1, y2, y3 }); }
+    void setDirectionCosines(const Vec3& cosinesX, const Vec3& cosinesY)
+    {
+        setDirectionCosines(Cosines { cosinesX[0], cosinesX[1], cosinesX[2], cosinesY[0], cosinesY[1], cosinesY[2] });
+    }
+
+    // ---- focal spot
+    const Vec3& position() const { return m_origin; }
+    void setPosition(const Vec3& pos) { m_origin = pos; }
+    void setPosition(const T pos[3]) { m_origin = { pos[0], pos[1], pos[2] }; }
+    void setPosition(T x, T y, T z) { m_origin = { x, y, z }; }
+    void setPositionZ(const T posZ) { m_origin[2] = posZ; }
+    void addPosition(const Vec3& shift) { std::transform(m_origin.begin(), m_origin.end(), shift.begin(), m_origin.begin(), std::plus<T>()); }
+    void subtractPosition(const Vec3& shift) { std::transform(m_origin.begin(), m_origin.end(), shift.begin(), m_origin.begin(), std::minus<T>()); }
 
 private:
-    std::array<T, 3> m_position;
-    std::array<T, 6> m_directionCosines;
-    std::array<T, 3> m_beamDirection;
-    std::array<T, 4> m_collimationAngles; // x0 x1 y0 y1
-    T m_beamIntensityWeight;
-    const BeamFilter<T>* m_beamFilter = nullptr;
-    const SpecterDistribution<T>* m_specterDistribution = nullptr;
-    const HeelFilter<T>* m_heelFilter = nullptr;
-    T m_monoenergeticPhotonEnergy { 0 };
     std::uint64_t m_nHistories;
+    T m_weight;
+    T m_monoEnergy { 0 };
+    const SpecterDistribution<T>* m_spectrum = nullptr;
+    const HeelFilter<T>* m_heel = nullptr;
+    const BeamFilter<T>* m_fanFilter = nullptr;
+    std::array<T, 4> m_angles {};
+    Vec3 m_origin;
+    Cosines m_frame {};
+    Vec3 m_beam {};
 };
 }

@@ -1,9 +1,3 @@
-// floating.hpp — the Floating concept every dxmc template is constrained on
-// (API of reference include/dxmc/floating.hpp:24-25).
+// floating.hpp — forwarding header: the Floating concept lives in dxmc/types.hpp.
 #pragma once
-#include <concepts>
-
-namespace dxmc {
-template <typename T>
-concept Floating = std::floating_point<T>;
-}
+#include "dxmc/types.hpp"

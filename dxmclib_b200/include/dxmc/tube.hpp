@@ -2,18 +2,20 @@
 //
 // Public surface of the reference's Tube<T> (include/dxmc/tube.hpp:35-299). The spectrum feeds the
 // alias table (SpecterDistribution) and the heel-effect table (HeelFilter) that Transport uploads
-// to the GPU; generation itself is host-side and runs once per source.
+// to the GPU; generation itself is host-side, runs once per source, and spreads its energy bins over
+// all host cores.
 #pragma once
 #include "dxmc/betheHeitlerCrossSection.hpp"
 #include "dxmc/constants.hpp"
-#include "dxmc/floating.hpp"
 #include "dxmc/hostparallel.hpp"
 #include "dxmc/material.hpp"
+#include "dxmc/types.hpp"
 
 #include <algorithm>
 #include <cmath>
 #include <execution>
 #include <numeric>
+#include <optional>
 #include <utility>
 #include <vector>
 
@@ -21,154 +23,136 @@ namespace dxmc {
 
 template <Floating T = double>
 class Tube {
+    using Filtration = std::vector<std::pair<Material, T>>; // material, thickness [mm]
+
+    // the half-value layer is expensive (a full spectrum); remembered until a setter changes the tube, never copied
+    struct HvlMemo {
+        std::optional<T> mmAl;
+        HvlMemo() = default;
+        HvlMemo(const HvlMemo&) { }
+        HvlMemo& operator=(const HvlMemo&)
+        {
+            mmAl.reset();
+            return *this;
+        }
+    };
+
 public:
+    static constexpr T minVoltage() { return T { 50 }; }
+    static constexpr T maxVoltage() { return T { 150 }; }
+
     Tube(T tubeVoltage = 120.0, T anodeAngleDeg = 12.0, T energyResolution = 1.0)
-        : m_voltage(tubeVoltage)
-        , m_energyResolution(energyResolution)
+        : m_kV(tubeVoltage)
+        , m_binWidth(energyResolution)
     {
         setAnodeAngleDeg(anodeAngleDeg);
     }
-    Tube(const Tube<T>& other)
-        : m_voltage(other.m_voltage)
-        , m_energyResolution(other.m_energyResolution)
-        , m_anodeAngle(other.m_anodeAngle)
-        , m_filtrationMaterials(other.m_filtrationMaterials)
-    {
-    }
-    Tube& operator=(const Tube<T>& other)
-    {
-        m_voltage = other.m_voltage;
-        m_energyResolution = other.m_energyResolution;
-        m_anodeAngle = other.m_anodeAngle;
-        m_filtrationMaterials = other.m_filtrationMaterials;
-        m_hasCachedHVL = false;
-        return *this;
-    }
 
-    static constexpr T maxVoltage() { return T { 150 }; }
-    static constexpr T minVoltage() { return T { 50 }; }
-
-    T voltage() const { return m_voltage; }
-    void setVoltage(T voltage)
-    {
-        m_voltage = std::min(std::max(voltage, minVoltage()), maxVoltage());
-        m_hasCachedHVL = false;
-    }
-
-    T anodeAngle() const { return m_anodeAngle; }
-    T anodeAngleDeg() const { return m_anodeAngle * RAD_TO_DEG<T>(); }
-    void setAnodeAngle(T angle)
-    {
-        m_anodeAngle = std::min(std::abs(angle), PI_VAL<T>() * T { 0.5 });
-        m_hasCachedHVL = false;
-    }
-    void setAnodeAngleDeg(T angle) { setAnodeAngle(angle * DEG_TO_RAD<T>()); }
-
-    void addFiltrationMaterial(const Material& filtrationMaterial, T mm)
-    {
-        m_filtrationMaterials.emplace_back(filtrationMaterial, std::abs(mm));
-        m_hasCachedHVL = false;
-    }
-    std::vector<std::pair<Material, T>>& filtrationMaterials() { return m_filtrationMaterials; }
-    const std::vector<std::pair<Material, T>>& filtrationMaterials() const { return m_filtrationMaterials; }
-    void clearFiltrationMaterials() { m_filtrationMaterials.clear(); }
-
-    void setAlFiltration(T mm) { setElementFiltration(13, "Al", mm); }
-    void setCuFiltration(T mm) { setElementFiltration(29, "Cu", mm); }
-    void setSnFiltration(T mm) { setElementFiltration(50, "Sn", mm); }
-    T AlFiltration() const { return elementFiltration("Al"); }
-    T CuFiltration() const { return elementFiltration("Cu"); }
-    T SnFiltration() const { return elementFiltration("Sn"); }
-
-    void setEnergyResolution(T energyResolution) { m_energyResolution = energyResolution; }
-    T energyResolution() const { return m_energyResolution; }
-
+    // ---- spectrum
     // bin energies: resolution, 2*resolution, ... <= voltage
     std::vector<T> getEnergy() const
     {
-        std::vector<T> energies;
-        energies.reserve(static_cast<std::size_t>(std::ceil(m_voltage / m_energyResolution)));
-        for (T hv = m_energyResolution; hv <= m_voltage; hv = hv + m_energyResolution)
-            energies.push_back(hv);
-        return energies;
-    }
-
-    std::vector<std::pair<T, T>> getSpecter(bool normalize = true) const
-    {
-        const auto energies = getEnergy();
-        const auto specter = getSpecter(energies, normalize);
-        std::vector<std::pair<T, T>> out;
-        out.reserve(specter.size());
-        for (std::size_t i = 0; i < specter.size(); ++i)
-            out.emplace_back(energies[i], specter[i]);
-        return out;
+        std::vector<T> bins;
+        bins.reserve(static_cast<std::size_t>(std::ceil(m_kV / m_binWidth)));
+        for (T hv = m_binWidth; hv <= m_kV; hv = hv + m_binWidth)
+            bins.push_back(hv);
+        return bins;
     }
     // bremsstrahlung + tungsten K lines, filtered by the added materials, at a given take-off angle
     std::vector<T> getSpecter(const std::vector<T>& energies, const T anodeAngle, bool normalize = true) const
     {
-        std::vector<T> specter(energies.size());
+        std::vector<T> fluence(energies.size());
         // one Bethe-Heitler depth integral per energy bin, independent of each other (reference tube.hpp:191-208)
         detail::parallelFor(energies.size(),
-            [&](std::size_t i) { specter[i] = BetheHeitlerCrossSection::betheHeitlerSpectra(m_voltage, energies[i], anodeAngle); });
-        addCharacteristicLines(energies, specter);
-        applyFiltration(energies, specter);
+            [&](std::size_t i) { fluence[i] = BetheHeitlerCrossSection::betheHeitlerSpectra(m_kV, energies[i], anodeAngle); });
+        // a K line goes into the first bin at or above its energy when that bin is within 2 keV
+        for (const auto& [lineEnergy, lineYield] : BetheHeitlerCrossSection::characteristicTungstenKedge(m_kV, m_takeOff)) {
+            const auto bin = std::lower_bound(energies.begin(), energies.end(), lineEnergy);
+            if (bin != energies.end() && std::abs(lineEnergy - *bin) <= T { 2.0 })
+                fluence[std::distance(energies.begin(), bin)] += lineYield;
+        }
+        for (const auto& [material, mm] : m_filters) {
+            const T cm = mm * T { 0.1 };
+            for (std::size_t i = 0; i < fluence.size(); ++i) {
+                const T n = fluence[i];
+                fluence[i] = n * std::exp(-material.getTotalAttenuation(energies[i]) * material.standardDensity() * cm);
+            }
+        }
         if (normalize) {
-            const auto sum = std::reduce(std::execution::par_unseq, specter.begin(), specter.end());
-            for (auto& n : specter)
+            const auto sum = std::reduce(std::execution::par_unseq, fluence.begin(), fluence.end());
+            for (auto& n : fluence)
                 n = n / sum;
         }
-        return specter;
+        return fluence;
     }
-    std::vector<T> getSpecter(const std::vector<T>& energies, bool normalize = true) const { return getSpecter(energies, m_anodeAngle, normalize); }
+    std::vector<T> getSpecter(const std::vector<T>& energies, bool normalize = true) const { return getSpecter(energies, m_takeOff, normalize); }
+    std::vector<std::pair<T, T>> getSpecter(bool normalize = true) const
+    {
+        const auto energies = getEnergy();
+        const auto fluence = getSpecter(energies, normalize);
+        std::vector<std::pair<T, T>> pairs(fluence.size());
+        for (std::size_t i = 0; i < fluence.size(); ++i)
+            pairs[i] = { energies[i], fluence[i] };
+        return pairs;
+    }
 
+    [[nodiscard]] T mmAlHalfValueLayer() const { return m_hvl.mmAl ? *m_hvl.mmAl : computeHalfValueLayer(); }
     T mmAlHalfValueLayer()
     {
-        if (!m_hasCachedHVL) {
-            m_cachedHVL = computeHalfValueLayer();
-            m_hasCachedHVL = true;
-        }
-        return m_cachedHVL;
+        if (!m_hvl.mmAl)
+            m_hvl.mmAl = computeHalfValueLayer();
+        return *m_hvl.mmAl;
     }
-    [[nodiscard]] T mmAlHalfValueLayer() const { return m_hasCachedHVL ? m_cachedHVL : computeHalfValueLayer(); }
+
+    // ---- added filtration
+    void addFiltrationMaterial(const Material& filtrationMaterial, T mm)
+    {
+        m_filters.emplace_back(filtrationMaterial, std::abs(mm));
+        m_hvl.mmAl.reset();
+    }
+    Filtration& filtrationMaterials() { return m_filters; }
+    const Filtration& filtrationMaterials() const { return m_filters; }
+    void clearFiltrationMaterials() { m_filters.clear(); }
+    T AlFiltration() const { return elementFiltration("Al"); }
+    T CuFiltration() const { return elementFiltration("Cu"); }
+    T SnFiltration() const { return elementFiltration("Sn"); }
+    void setAlFiltration(T mm) { setElementFiltration(13, "Al", mm); }
+    void setCuFiltration(T mm) { setElementFiltration(29, "Cu", mm); }
+    void setSnFiltration(T mm) { setElementFiltration(50, "Sn", mm); }
+
+    // ---- tube settings
+    T voltage() const { return m_kV; }
+    void setVoltage(T voltage)
+    {
+        m_kV = std::clamp(voltage, minVoltage(), maxVoltage());
+        m_hvl.mmAl.reset();
+    }
+    T anodeAngle() const { return m_takeOff; }
+    T anodeAngleDeg() const { return m_takeOff * RAD_TO_DEG<T>(); }
+    void setAnodeAngle(T angle)
+    {
+        m_takeOff = std::min(std::abs(angle), PI_VAL<T>() * T { 0.5 });
+        m_hvl.mmAl.reset();
+    }
+    void setAnodeAngleDeg(T angle) { setAnodeAngle(angle * DEG_TO_RAD<T>()); }
+    T energyResolution() const { return m_binWidth; }
+    void setEnergyResolution(T energyResolution) { m_binWidth = energyResolution; }
 
 protected:
-    void setElementFiltration(int Z, const char* symbol, T mm)
-    {
-        for (auto& [material, thickness] : m_filtrationMaterials)
-            if (material.name().compare(symbol) == 0) {
-                thickness = std::abs(mm);
-                m_hasCachedHVL = false;
-                return;
-            }
-        addFiltrationMaterial(Material(Z), std::abs(mm));
-    }
     T elementFiltration(const char* symbol) const
     {
-        for (const auto& [material, thickness] : m_filtrationMaterials)
-            if (material.name().compare(symbol) == 0)
-                return thickness;
-        return T { 0 };
+        const auto it = std::find_if(m_filters.begin(), m_filters.end(), [&](const auto& f) { return f.first.name().compare(symbol) == 0; });
+        return it != m_filters.end() ? it->second : T { 0 };
     }
-
-    // a line is added to the first bin at or above its energy when that bin is within 2 keV
-    void addCharacteristicLines(const std::vector<T>& energy, std::vector<T>& specter) const
+    void setElementFiltration(int Z, const char* symbol, T mm)
     {
-        const auto lines = BetheHeitlerCrossSection::characteristicTungstenKedge(m_voltage, m_anodeAngle);
-        for (const auto& [e, n] : lines) {
-            const auto bin = std::lower_bound(energy.begin(), energy.end(), e);
-            if (bin != energy.end() && std::abs(e - *bin) <= T { 2.0 })
-                specter[std::distance(energy.begin(), bin)] += n;
+        const auto it = std::find_if(m_filters.begin(), m_filters.end(), [&](const auto& f) { return f.first.name().compare(symbol) == 0; });
+        if (it == m_filters.end()) {
+            addFiltrationMaterial(Material(Z), std::abs(mm));
+            return;
         }
-    }
-    void applyFiltration(const std::vector<T>& energies, std::vector<T>& specter) const
-    {
-        for (const auto& [material, mm] : m_filtrationMaterials) {
-            const T cm = mm * T { 0.1 };
-            for (std::size_t i = 0; i < specter.size(); ++i) {
-                const T n = specter[i];
-                specter[i] = n * std::exp(-material.getTotalAttenuation(energies[i]) * material.standardDensity() * cm);
-            }
-        }
+        it->second = std::abs(mm);
+        m_hvl.mmAl.reset();
     }
     // fixed-point iteration x <- x + (transmission(x) - 1/2) on the aluminium thickness in cm
     T computeHalfValueLayer() const
@@ -191,9 +175,8 @@ protected:
     }
 
 private:
-    T m_voltage, m_energyResolution, m_anodeAngle;
-    T m_cachedHVL = 0;
-    bool m_hasCachedHVL = false;
-    std::vector<std::pair<Material, T>> m_filtrationMaterials;
+    T m_kV, m_binWidth, m_takeOff;
+    Filtration m_filters;
+    HvlMemo m_hvl;
 };
 }
