@@ -4,6 +4,7 @@
 #pragma once
 #include <array>
 #include <concepts>
+#include <cstddef>
 
 namespace dxmc {
 
@@ -21,6 +22,15 @@ template <Floating T = double>
 struct Particle {
     std::array<T, 3> pos, dir;
     T energy, weight;
+
+    // move `distance` [mm] along the direction, component by component in the order the transport loop uses
+    constexpr void translate(T distance) noexcept
+    {
+        for (std::size_t axis = 0; axis < 3; ++axis)
+            pos[axis] += dir[axis] * distance;
+    }
+    // what Russian roulette looks at (transport.hpp:684): energy carried, in keV
+    constexpr T weightedEnergy() const noexcept { return energy * weight; }
 };
 
 }
