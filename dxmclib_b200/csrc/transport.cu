@@ -1425,7 +1425,9 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
         return DXMCB200_ERR_CUDA;
     }
     c->pipes[0].stream = c->stream;
-    for (int i = 0; i < kMaxPipes; ++i) {
+    if (const char* env = std::getenv("DXMCB200_PIPES"))
+        c->nPipes = std::clamp(std::atoi(env), 1, kMaxPipes);
+    for (int i = 0; i < c->nPipes; ++i) { // only the pipelines that will run get streams, events and (pinned) cursor blocks
         auto& pipe = c->pipes[i];
         if ((i > 0 && cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking) != cudaSuccess)
             || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&pipe.mark[0]) != cudaSuccess
@@ -1435,8 +1437,6 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
             return DXMCB200_ERR_CUDA;
         }
     }
-    if (const char* env = std::getenv("DXMCB200_PIPES"))
-        c->nPipes = std::clamp(std::atoi(env), 1, kMaxPipes);
     const char* stats = std::getenv("DXMCB200_STATS");
     c->collectStats = stats && stats[0] == '1';
     if (const char* env = std::getenv("DXMCB200_PALETTE")) { // 0: 8-byte records, 8: byte indices only, else automatic
