@@ -143,6 +143,35 @@ public:
     {
     }
 
+    // Copyable like the reference's Transport (validation.cpp passes it by value): a copy takes the settings and the
+    // look-up tables, never the device context or the prepared run of the original.
+    Transport(const Transport& other)
+        : m_attenuationLut(other.m_attenuationLut)
+        , m_nThreads(other.m_nThreads)
+        , m_outputmode(other.m_outputmode)
+        , m_lowenergyCorrection(other.m_lowenergyCorrection)
+        , m_device(other.m_device)
+        , m_seed(other.m_seed)
+    {
+    }
+    Transport& operator=(const Transport& other)
+    {
+        if (this != &other) {
+            release();
+            m_attenuationLut = other.m_attenuationLut;
+            m_nThreads = other.m_nThreads;
+            m_outputmode = other.m_outputmode;
+            m_lowenergyCorrection = other.m_lowenergyCorrection;
+            m_device = other.m_device;
+            m_seed = other.m_seed;
+            m_flat = detail::FlatTables {};
+            m_totalExposures = m_histories = 0;
+        }
+        return *this;
+    }
+    Transport(Transport&&) = default;
+    Transport& operator=(Transport&&) = default;
+
     // kept for source compatibility; the B200 path has no host workers
     void setNumberOfWorkers(std::uint64_t n) { m_nThreads = std::max(n, std::uint64_t { 1 }); }
     std::size_t numberOfWorkers() const { return m_nThreads; }

@@ -1,5 +1,5 @@
-"""Source compatibility of the drop-in headers, checked with the reference's OWN programs: its example and the unit-test
-programs that stay on the public API are compiled and linked UNCHANGED (from /root/reference, nothing is copied) against
+"""Source compatibility of the drop-in headers, checked with the reference's OWN programs: its example, its TG-195
+validation program and the unit-test programs that stay on the public API are compiled and linked UNCHANGED (from /root/reference, nothing is copied) against
 dxmclib_b200/include and libdxmcb200.so. Not covered: testtransport.cpp, which subclasses Transport to call the per-thread
 interaction samplers (computeInteractions, comptonScatter, ...: protected internals of the CPU hot path that are CUDA
 kernels here, tested through the C ABI instead), and testdxmclib.cpp / validatedxmclib.cpp, which include headers
@@ -14,7 +14,7 @@ import pytest
 import support as T
 
 REF = os.environ.get("DXMC_REFERENCE", "/root/reference")
-PROGRAMS = ["examples/pencilbeam/pencilbeam.cpp", "tests/testattenuationlut.cpp", "tests/testbeamfilters.cpp", "tests/testexposure.cpp",
+PROGRAMS = ["examples/pencilbeam/pencilbeam.cpp", "validation/validation.cpp", "tests/testattenuationlut.cpp", "tests/testbeamfilters.cpp", "tests/testexposure.cpp",
             "tests/testinterpolation.cpp", "tests/testmaterial.cpp", "tests/testrandom.cpp", "tests/testsource.cpp", "tests/testtube.cpp",
             "tests/testvectormath.cpp", "tests/testworld.cpp"]
 
