@@ -297,6 +297,7 @@ __device__ __forceinline__ void attenuationAt(const LutView& l, uint32_t materia
     asm("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
         : "=f"(pb), "=f"(pa), "=f"(cb), "=f"(ca), "=f"(rb), "=f"(ra), "=f"(pad0), "=f"(pad1)
         : "l"(c));
+    (void)pad0, (void)pad1;
     photo = fastExp10(__fadd_rn(pb, __fmul_rn(pa, logE)));
     compton = fastExp10(__fadd_rn(cb, __fmul_rn(ca, logE)));
     rayleigh = fastExp10(__fadd_rn(rb, __fmul_rn(ra, logE)));

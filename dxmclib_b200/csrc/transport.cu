@@ -147,7 +147,6 @@ template <bool kStats>
 __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant__ KernelParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned laneLt = (1u << lane) - 1u;
     uint32_t cHist = 0, cWorld = 0;
     const uint32_t rounded = (P.chunkCount + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < rounded; i += gridDim.x * kThreads) {
@@ -644,7 +643,6 @@ template <int L, bool kStats, bool kAggregate>
 __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_constant__ KernelParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    const unsigned laneLt = (1u << lane) - 1u;
     uint32_t cInter = 0, cScores = 0;
     // block b works on event shard b % kShards together with the other blocks of the same residue
     const unsigned blocksPerShard = gridDim.x / kShards; // the grid is a multiple of kShards
