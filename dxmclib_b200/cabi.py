@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
     "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_trim_pool",
-    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point",
+    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident", "dxmcb200_run_strided",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
     "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
@@ -61,7 +61,8 @@ class Exposure(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("histories", C.c_uint64), ("histories_in_world", C.c_uint64), ("steps", C.c_uint64), ("lookups", C.c_uint64),
-                ("interactions", C.c_uint64), ("score_events", C.c_uint64), ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_double)]
+                ("interactions", C.c_uint64), ("score_events", C.c_uint64), ("kernel_launches", C.c_uint64), ("kernel_ms", C.c_double),
+                ("air_walks", C.c_uint64), ("bricks_crossed", C.c_uint64)]
 
 
 def lib() -> C.CDLL:
@@ -93,6 +94,15 @@ def device_count() -> int:
     n = C.c_int(0)
     lib().dxmcb200_device_count(C.byref(n))
     return int(n.value)
+
+
+def suggest_fixed_point(total_histories: int, max_energy_weight: float):
+    """(energy_bits, energy_sq_bits) that cannot overflow for a job of this size (dxmcb200_suggest_fixed_point)."""
+    a, b = C.c_int(), C.c_int()
+    rc = lib().dxmcb200_suggest_fixed_point(C.c_uint64(int(total_histories)), C.c_double(float(max_energy_weight)), C.byref(a), C.byref(b))
+    if rc != 0:
+        raise CabiError(f"dxmcb200_suggest_fixed_point failed with status {rc}")
+    return int(a.value), int(b.value)
 
 
 class Context:
@@ -246,12 +256,25 @@ class Context:
         return {k: getattr(s, k) for k, _ in Stats._fields_}
 
     def kernel_times(self) -> dict:
-        """Device milliseconds and launch counts of generate / transport / interact kernels since clear()."""
-        ms = (C.c_double * 3)()
-        n = (C.c_uint64 * 3)()
+        """Device milliseconds and launch counts of generate / transport / air walk / interact kernels since clear()."""
+        ms = (C.c_double * 4)()
+        n = (C.c_uint64 * 4)()
         self._chk(self.l.dxmcb200_get_kernel_times(self.h, ms, n), "dxmcb200_get_kernel_times")
-        names = ("generate", "transport", "interact")
+        names = ("generate", "transport", "airwalk", "interact")
         return {k: {"ms": float(ms[i]), "launches": int(n[i])} for i, k in enumerate(names)}
+
+    def set_tracking(self, tracking: int, brick_mm: float = 0.0):
+        """0: the reference's Woodcock loop everywhere; 1: + empty-space traversal through air bricks (default)."""
+        self._chk(self.l.dxmcb200_set_tracking(self.h, int(tracking), C.c_float(brick_mm)), "dxmcb200_set_tracking")
+
+    def bricks(self, n_materials: int) -> dict:
+        shift, nb, f_air = (C.c_uint32 * 3)(), (C.c_uint32 * 3)(), C.c_float()
+        self._chk(self.l.dxmcb200_get_bricks(self.h, shift, nb, C.byref(f_air), None, None, None), "dxmcb200_get_bricks")
+        n = int(nb[0]) * int(nb[1]) * int(nb[2])
+        ratio, bmax, air = np.zeros(n_materials, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self._chk(self.l.dxmcb200_get_bricks(self.h, shift, nb, C.byref(f_air), ratio.ctypes.data_as(_f32p), bmax.ctypes.data_as(_f32p),
+                                             air.ctypes.data_as(_u8p)), "dxmcb200_get_bricks")
+        return {"shift": list(shift), "nb": list(nb), "f_air": float(f_air.value), "ratio": ratio, "brick_max": bmax, "air": air}
 
     def enable_stats(self, on=True):
         self._chk(self.l.dxmcb200_enable_stats(self.h, int(on)), "dxmcb200_enable_stats")

@@ -1,9 +1,11 @@
 // physics.cuh — device-side primitives of the photon transport hot path (sm_100a).
 //
 // Every function states the reference function whose arithmetic it reproduces. Float expressions
-// keep the reference's operation order; the translation unit is compiled with -fmad=false so
-// nvcc does not fuse a*b+c (the CPU checkers are built with -ffp-contract=off), and geometry uses
-// explicit round-to-nearest intrinsics, which makes voxel-index sequences bit-exact.
+// keep the reference's operation order. The translation unit is compiled with nvcc's default FMA
+// contraction (dxmclib_b200/build.py passes no -fmad=false): what must be bit-exact — geometry, voxel
+// and brick indices, LUT segment and exponent arguments, the RNG — is written with explicit
+// round-to-nearest intrinsics (__fmul_rn, __fadd_rn, ...), which nvcc never fuses; the interaction
+// samplers may be contracted and agree with the CPU checkers statistically, not bit by bit.
 #pragma once
 
 #include "../../include/dxmcb200.h"
@@ -89,6 +91,18 @@ struct WorldView {
     const uint8_t* palette; // palette form: index per voxel into paletteTable (grids with <= 256 distinct records)
     const uint2* paletteTable; // [256] records as in `voxels`
     uint32_t paletteNibbles; // 1: at most 16 distinct records, two 4-bit indices per byte (voxel i in byte i/2, low nibble first)
+};
+
+// Brick grid of the empty-space traversal: the voxel grid cut into bricks of 2^shift voxels per
+// axis, one bit per brick: set when the brick is "air" (rho * mu_total(E) <= f_air * majorant(E) for every voxel and energy,
+// no measurement voxel).
+struct BrickView {
+    uint32_t shift[3];
+    uint32_t nb[3]; // bricks per axis
+    float size[3]; // brick edge [mm]
+    float invFAir; // 1 / f_air: free paths in air bricks are the global-majorant ones times this
+    uint32_t nWords; // 32-bit words of the bitmap; 0: no air bricks, plain Woodcock tracking everywhere
+    const uint32_t* air; // bit b: brick b = (bz * nb[1] + by) * nb[0] + bx is air
 };
 
 struct SpectrumView {
@@ -202,9 +216,8 @@ __device__ __forceinline__ bool insideWorld(const WorldView& w, float x, float y
     return (x > w.ext[0] && x < w.ext[1]) && (y > w.ext[2] && y < w.ext[3]) && (z > w.ext[4] && z < w.ext[5]);
 }
 
-__device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, float y, float z)
+__device__ __forceinline__ void voxelCoords(const WorldView& w, float x, float y, float z, uint32_t& ix, uint32_t& iy, uint32_t& iz)
 {
-    uint32_t ix, iy, iz;
     if (w.exactInverse) { // uniform branch: scaling by a power of two is exact, so is the truncated quotient
         ix = __float2uint_rz(__fmul_rn(__fsub_rn(x, w.ext[0]), w.invSpacing[0]));
         iy = __float2uint_rz(__fmul_rn(__fsub_rn(y, w.ext[2]), w.invSpacing[1]));
@@ -214,6 +227,12 @@ __device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, floa
         iy = truncDiv(__fsub_rn(y, w.ext[2]), w.spacing[1], w.invSpacing[1]);
         iz = truncDiv(__fsub_rn(z, w.ext[4]), w.spacing[2], w.invSpacing[2]);
     }
+}
+
+__device__ __forceinline__ uint32_t voxelIndex(const WorldView& w, float x, float y, float z)
+{
+    uint32_t ix, iy, iz;
+    voxelCoords(w, x, y, z, ix, iy, iz);
     return (iz * w.dim[1] + iy) * w.dim[0] + ix;
 }
 
@@ -223,6 +242,14 @@ __device__ __forceinline__ uint32_t paletteIndex(const WorldView& w, uint32_t vo
     if (w.paletteNibbles)
         return (static_cast<uint32_t>(__ldcg(w.palette + (voxel >> 1))) >> ((voxel & 1u) * 4u)) & 15u;
     return __ldcg(w.palette + voxel);
+}
+
+// {density bits, material | measurement << 8} of a voxel, whatever form the grid is stored in
+__device__ __forceinline__ uint2 voxelRecord(const WorldView& w, uint32_t voxel)
+{
+    if (w.palette)
+        return __ldg(w.paletteTable + paletteIndex(w, voxel));
+    return __ldcg(w.voxels + voxel);
 }
 
 __device__ __forceinline__ void advance(Photon& p, float step)
@@ -257,6 +284,85 @@ __device__ __forceinline__ bool transportToWorld(const WorldView& w, Photon& p)
         return true;
     }
     return false;
+}
+
+// ---- empty-space traversal: brick look-up and ray / brick-grid traversal ----------------------
+__device__ __forceinline__ uint32_t brickOfVoxel(const BrickView& b, uint32_t ix, uint32_t iy, uint32_t iz)
+{
+    return ((iz >> b.shift[2]) * b.nb[1] + (iy >> b.shift[1])) * b.nb[0] + (ix >> b.shift[0]);
+}
+
+// voxel coordinate along one axis, clamped into the grid: also defined for points on (or a rounding error outside) the
+// faces of the world, where photons stand after transportToWorld
+__device__ __forceinline__ uint32_t axisVoxelClamped(const WorldView& w, int axis, float x)
+{
+    const float rel = __fsub_rn(x, w.ext[2 * axis]);
+    if (!(rel > 0.0f))
+        return 0u;
+    const uint32_t v = w.exactInverse ? __float2uint_rz(__fmul_rn(rel, w.invSpacing[axis])) : truncDiv(rel, w.spacing[axis], w.invSpacing[axis]);
+    return min(v, w.dim[axis] - 1u);
+}
+
+__device__ __forceinline__ bool airBit(const uint32_t* __restrict__ bitmap, uint32_t brick) { return (__ldg(bitmap + (brick >> 5)) >> (brick & 31u)) & 1u; }
+
+__device__ __forceinline__ bool inAirBrick(const WorldView& w, const BrickView& b, float x, float y, float z)
+{
+    const uint32_t ix = axisVoxelClamped(w, 0, x), iy = axisVoxelClamped(w, 1, y), iz = axisVoxelClamped(w, 2, z);
+    return airBit(b.air, brickOfVoxel(b, ix, iy, iz));
+}
+
+// Ray parameter at which the photon's ray leaves the run of air bricks it starts in (parametric ray / grid traversal,
+// Siddon 1985, Amanatides & Woo 1987, over the brick grid); `exits`: the ray leaves the grid there. Round-to-nearest
+// intrinsics throughout: the CPU restatement (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
+__device__ __forceinline__ float airRunLength(const WorldView& w, const BrickView& b, const Photon& p, bool& exits, uint32_t& crossed)
+{
+    const float pos[3] = { p.px, p.py, p.pz };
+    const float dir[3] = { p.dx, p.dy, p.dz };
+    int brick[3], step[3];
+    float tMax[3], tDelta[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        brick[i] = static_cast<int>(axisVoxelClamped(w, i, pos[i]) >> b.shift[i]);
+        if (fabsf(dir[i]) > kDirEpsilon) {
+            const float inv = __fdiv_rn(1.0f, dir[i]);
+            step[i] = dir[i] > 0.0f ? 1 : -1;
+            const float face = __fadd_rn(w.ext[2 * i], __fmul_rn(static_cast<float>(brick[i] + (dir[i] > 0.0f ? 1 : 0)), b.size[i]));
+            tMax[i] = fmaxf(__fmul_rn(__fsub_rn(face, pos[i]), inv), 0.0f);
+            tDelta[i] = __fmul_rn(b.size[i], fabsf(inv));
+        } else {
+            step[i] = 0;
+            tMax[i] = __int_as_float(0x7f800000);
+            tDelta[i] = 0.0f;
+        }
+    }
+    exits = false;
+    for (;;) {
+        const int a = tMax[0] <= tMax[1] ? (tMax[0] <= tMax[2] ? 0 : 2) : (tMax[1] <= tMax[2] ? 1 : 2);
+        const float t = a == 0 ? tMax[0] : a == 1 ? tMax[1] : tMax[2];
+        const int st = a == 0 ? step[0] : a == 1 ? step[1] : step[2];
+        if (st == 0) { // zero direction: the photon never leaves
+            exits = true;
+            return t;
+        }
+        const int moved = (a == 0 ? brick[0] : a == 1 ? brick[1] : brick[2]) + st;
+        ++crossed;
+        if (moved < 0 || moved >= static_cast<int>(a == 0 ? b.nb[0] : a == 1 ? b.nb[1] : b.nb[2])) {
+            exits = true;
+            return t;
+        }
+        if (a == 0) {
+            brick[0] = moved;
+            tMax[0] = __fadd_rn(tMax[0], tDelta[0]);
+        } else if (a == 1) {
+            brick[1] = moved;
+            tMax[1] = __fadd_rn(tMax[1], tDelta[1]);
+        } else {
+            brick[2] = moved;
+            tMax[2] = __fadd_rn(tMax[2], tDelta[2]);
+        }
+        if (!airBit(b.air, (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])))
+            return t;
+    }
 }
 
 // ---- attenuation tables (attenuationinterpolator.hpp:207-248) -------------------------------

@@ -16,6 +16,12 @@
 //                    Rayleigh sampling against the LUTs, 64-bit fixed-point scoring, Russian roulette; surviving
 //                    photons are compacted into the NEXT wave's photon buffer.
 //
+//   airWalkKernel    (b') empty-space traversal: photons that a Woodcock step left in an "air" brick
+//                    are walked through the run of air bricks on their ray (Siddon / Amanatides-Woo traversal of the
+//                    brick grid) against the regional majorant of air, then rejoin the next wave. Births take the same
+//                    walk inside generateKernel. Not part of the reference's algorithm; dxmcb200_set_tracking(ctx, 0)
+//                    switches it off and leaves the reference's Woodcock loop everywhere.
+//
 // One wave = births + survivors of the previous wave, at most `waveRecords` photons; the host tops every wave up
 // with new births until all histories are issued and then drains. Scoring is integer atomics and every history
 // carries its own random stream, so results do not depend on the wave size, scheduling or GPU partition.
@@ -39,10 +45,10 @@ namespace {
 constexpr int kThreads = 256;
 constexpr unsigned kFull = 0xffffffffu;
 
-enum LaneState : uint32_t { DEAD = 0, STEP = 1, EVENT = 2, EXHAUSTED = 3 };
+enum LaneState : uint32_t { DEAD = 0, STEP = 1, EVENT = 2, EXHAUSTED = 3, AIRBORNE = 4 };
 
 struct Counters {
-    unsigned long long histories, inWorld, steps, lookups, interactions, scores;
+    unsigned long long histories, inWorld, steps, lookups, interactions, scores, airWalks, bricksCrossed;
 };
 
 // one in-flight photon between kernels: 4 x 16 bytes
@@ -72,6 +78,7 @@ struct alignas(128) ShardCursor {
 struct WaveCursors {
     ShardCursor photons[2][kShards];
     ShardCursor events[kShards];
+    ShardCursor air[kShards];
     ShardCursor overflow; // .stored != 0: a region was too small, the run is invalid
 };
 
@@ -79,6 +86,7 @@ struct KernelParams {
     WorldView world;
     LutView lut;
     BeamView beams;
+    BrickView bricks;
     const dxmcb200_exposure* exposures; // absolute indexing
     const uint64_t* prefix; // [nExp+1] cumulative histories of the run's exposure range
     uint64_t expBegin; // first exposure of the run's range
@@ -97,6 +105,8 @@ struct KernelParams {
     ShardCursor* outCursors;
     EventRecord* events; // kShards regions of eventRegion slots, claimed in tiles of kEventTile
     ShardCursor* eventCursors;
+    PhotonRecord* airborne; // photons a Woodcock step left in an air brick: kShards regions of photonRegion records
+    ShardCursor* airCursors;
     unsigned int* overflow;
     uint32_t photonRegion, eventRegion;
     unsigned long long* acc; // [nVoxels][4]
@@ -112,25 +122,33 @@ __device__ __forceinline__ unsigned long long warpSum(uint32_t v)
     return s;
 }
 
-// Append the photons of the lanes in `mask` to the warp's shard of the output wave; returns the record to write
-// (nullptr for lanes outside the mask, or when the region is full, which invalidates the run).
-__device__ __forceinline__ PhotonRecord* appendPhotons(const KernelParams& P, unsigned mask, unsigned lane)
+// Append one record per lane in `mask` to the warp's shard region of a buffer; returns the slot index inside the buffer
+// (kNoSlot for lanes outside the mask, or when the region is full, which invalidates the run).
+constexpr size_t kNoSlot = ~static_cast<size_t>(0);
+__device__ __forceinline__ size_t appendSlots(ShardCursor* cursors, uint32_t region, unsigned int* overflow, unsigned mask, unsigned lane)
 {
     const unsigned shard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
     unsigned base = 0;
     const int leader = __ffs(mask) - 1;
     const unsigned n = __popc(mask);
     if (static_cast<int>(lane) == leader)
-        base = atomicAdd(&P.outCursors[shard].stored, n);
+        base = atomicAdd(&cursors[shard].stored, n);
     base = __shfl_sync(kFull, base, leader);
-    if (base + n > P.photonRegion) {
+    if (base + n > region) {
         if (static_cast<int>(lane) == leader)
-            atomicExch(P.overflow, 1u);
-        return nullptr;
+            atomicExch(overflow, 1u);
+        return kNoSlot;
     }
     if (!((mask >> lane) & 1u))
-        return nullptr;
-    return P.photonsOut + (static_cast<size_t>(shard) * P.photonRegion + base + __popc(mask & ((1u << lane) - 1u)));
+        return kNoSlot;
+    return static_cast<size_t>(shard) * region + base + __popc(mask & ((1u << lane) - 1u));
+}
+
+// the photons of the lanes in `mask` go to the output wave
+__device__ __forceinline__ PhotonRecord* appendPhotons(const KernelParams& P, unsigned mask, unsigned lane)
+{
+    const size_t slot = appendSlots(P.outCursors, P.photonRegion, P.overflow, mask, lane);
+    return slot == kNoSlot ? nullptr : P.photonsOut + slot;
 }
 
 // everything about a photon that only changes with its energy: log10(E) correctly rounded, the LUT segment it
@@ -142,17 +160,133 @@ __device__ __forceinline__ void energyDependent(const LutView& lut, float energy
     maxAttInv = maxAttenuationInverse(lut, logE);
 }
 
-// ---- (a) exposure-to-photon generation -------------------------------------------------------------
+// ---- photon records <-> registers ---------------------------------------------------------------------
+__device__ __forceinline__ void storePhoton(PhotonRecord* r, const Photon& p, const Rng& rng, float logE, float maxAttInv, uint32_t seg, float extra)
+{
+    r->posE = make_float4(p.px, p.py, p.pz, p.energy);
+    r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
+    r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+        static_cast<uint32_t>(rng.inc >> 32));
+    r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), extra);
+}
+
+__device__ __forceinline__ void loadPhoton(const PhotonRecord* r, Photon& p, Rng& rng, float& logE, float& maxAttInv, uint32_t& seg, float& extra)
+{
+    const float4 a = r->posE, b = r->dirW, d = r->lut;
+    const uint4 c = r->rng;
+    p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
+    p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
+    rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
+    rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
+    logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z), extra = d.w;
+}
+
+// -ln(r) * maxAttInv * 10 (transport.hpp:655-657) is evaluated as lg2(r) * kStepScale * maxAttInv; cm -> mm is the factor 10
+constexpr float kStepScale = -6.931471805599453f;
+
+// ---- (b') empty-space traversal ------------------------------------------------------------------------
+// A photon standing in an air brick is walked to the end of the run of air bricks on its ray. Collision candidates on
+// that stretch are sampled against the regional majorant f_air * majorant(E) (free paths are the global-majorant ones
+// times 1/f_air); what happens AT a candidate is the reference's step body (transport.hpp:659-693): look-up, accept /
+// reject (or forced interaction in a measurement voxel), Russian roulette after a virtual collision.
+enum WalkOutcome : uint32_t {
+    WALK_DENSE = 0, // the photon stands on the face of a non-air brick: back to Woodcock steps
+    WALK_GONE = 1, // left the world or lost Russian roulette
+    WALK_EVENT = 2 // an interaction is due at the photon's position
+};
+struct WalkEvent {
+    uint32_t voxel = 0, material = 0;
+    float eventProbability = 0.0f;
+};
+
 template <bool kStats>
+__device__ __forceinline__ uint32_t airWalk(const KernelParams& P, Photon& p, Rng& rng, float logE, uint32_t seg, float maxAttInv, WalkEvent& ev, uint32_t& cSteps,
+    uint32_t& cLookups, uint32_t& cBricks)
+{
+    bool exits = false;
+    uint32_t crossed = 0;
+    float remaining = airRunLength(P.world, P.bricks, p, exits, crossed);
+    if constexpr (kStats)
+        cBricks += crossed;
+    bool lowWeight = p.energy * p.weight < kRouletteThreshold;
+    for (;;) {
+        const float r1 = rng.uniform();
+        const float s = __fmul_rn(__fmul_rn(__fmul_rn(fastLog2(r1), kStepScale), maxAttInv), P.bricks.invFAir);
+        if (!(s < remaining)) { // no candidate before the end of the run
+            advance(p, remaining);
+            return exits ? WALK_GONE : WALK_DENSE;
+        }
+        advance(p, s);
+        remaining = __fsub_rn(remaining, s);
+        if constexpr (kStats)
+            ++cSteps;
+        if (!insideWorld(P.world, p.px, p.py, p.pz))
+            return WALK_GONE;
+        const uint32_t voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+        const uint2 rec = voxelRecord(P.world, voxel);
+        if constexpr (kStats)
+            ++cLookups;
+        float aP, aC, aR;
+        attenuationAt(P.lut, rec.y & 0xffu, seg, logE, aP, aC, aR);
+        const float attTotal = ((aP + aC) + aR) * __uint_as_float(rec.x);
+        const float eventProbability = fminf(__fmul_rn(__fmul_rn(attTotal, maxAttInv), P.bricks.invFAir), 1.0f);
+        bool event = (rec.y & 0xff00u) != 0;
+        if (!event)
+            event = rng.uniform() < eventProbability;
+        if (event) {
+            ev.voxel = voxel;
+            ev.material = rec.y;
+            ev.eventProbability = eventProbability;
+            return WALK_EVENT;
+        }
+        if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
+            const float r4 = rng.uniform();
+            if (r4 < kRouletteProbability)
+                return WALK_GONE;
+            constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+            p.weight *= factor;
+            lowWeight = p.energy * p.weight < kRouletteThreshold;
+        }
+    }
+}
+
+// hand the outcome of a walk on: photons on the face of a non-air brick join `photons` / `photonCursors`, photons with an
+// interaction due get an event record (claimed with an exact count: the consumer skips nothing but kNoEvent slots)
+__device__ __forceinline__ void emitWalked(const KernelParams& P, PhotonRecord* photons, ShardCursor* photonCursors, uint32_t outcome, bool valid, const Photon& p,
+    const Rng& rng, float logE, float maxAttInv, uint32_t seg, const WalkEvent& ev, unsigned lane)
+{
+    const unsigned denseMask = __ballot_sync(kFull, valid && outcome == WALK_DENSE);
+    const unsigned eventMask = __ballot_sync(kFull, valid && outcome == WALK_EVENT);
+    if (denseMask) {
+        const size_t slot = appendSlots(photonCursors, P.photonRegion, P.overflow, denseMask, lane);
+        if (slot != kNoSlot)
+            storePhoton(photons + slot, p, rng, logE, maxAttInv, seg, 0.0f);
+    }
+    if (eventMask) {
+        const size_t slot = appendSlots(P.eventCursors, P.eventRegion, P.overflow, eventMask, lane);
+        if (slot != kNoSlot) {
+            EventRecord* e = P.events + slot;
+            storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, ev.eventProbability);
+            e->where = make_uint4(ev.voxel, ev.material, 0u, 0u);
+        }
+    }
+}
+
+// ---- (a) exposure-to-photon generation -------------------------------------------------------------
+template <bool kStats, bool kAir>
 __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant__ KernelParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
-    uint32_t cHist = 0, cWorld = 0;
+    uint32_t cHist = 0, cWorld = 0, cSteps = 0, cLookups = 0, cBricks = 0, cWalks = 0;
     const uint32_t rounded = (P.chunkCount + 31u) & ~31u;
     for (uint32_t i = blockIdx.x * kThreads + threadIdx.x; i < rounded; i += gridDim.x * kThreads) {
         bool keep = false;
         Photon p {};
         Rng rng { 0, 1 };
+        float logE = 0.0f, maxAttInv = 0.0f;
+        uint32_t seg = 0;
+        uint32_t outcome = WALK_DENSE;
+        WalkEvent ev;
         if (i < P.chunkCount) {
             uint32_t e;
             uint64_t history;
@@ -182,27 +316,78 @@ __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant
                 ++cHist;
                 cWorld += keep ? 1u : 0u;
             }
+            if (keep) {
+                energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+                if constexpr (kAir) { // born into (or onto the face of) an air brick: walk to the first non-air brick
+                    if (inAirBrick(P.world, P.bricks, p.px, p.py, p.pz)) {
+                        outcome = airWalk<kStats>(P, p, rng, logE, seg, maxAttInv, ev, cSteps, cLookups, cBricks);
+                        if constexpr (kStats)
+                            ++cWalks;
+                    }
+                }
+            }
         }
-        const unsigned keepMask = __ballot_sync(kFull, keep);
-        if (keepMask == 0)
-            continue;
-        PhotonRecord* r = appendPhotons(P, keepMask, lane);
-        if (r) {
-            float logE, maxAttInv;
-            uint32_t seg;
-            energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
-            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
-            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
-                static_cast<uint32_t>(rng.inc >> 32));
-            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
+        if constexpr (kAir) {
+            emitWalked(P, P.photonsOut, P.outCursors, outcome, keep, p, rng, logE, maxAttInv, seg, ev, lane);
+        } else {
+            const unsigned keepMask = __ballot_sync(kFull, keep);
+            if (keepMask == 0)
+                continue;
+            PhotonRecord* r = appendPhotons(P, keepMask, lane);
+            if (r)
+                storePhoton(r, p, rng, logE, maxAttInv, seg, 0.0f);
         }
     }
     if constexpr (kStats) {
-        const unsigned long long h = warpSum(cHist), w = warpSum(cWorld);
+        const unsigned long long h = warpSum(cHist), w = warpSum(cWorld), st = warpSum(cSteps), l = warpSum(cLookups), b = warpSum(cBricks),
+                                 wk = warpSum(cWalks);
         if (lane == 0) {
             atomicAdd(&P.counters->histories, h);
             atomicAdd(&P.counters->inWorld, w);
+            if constexpr (kAir) {
+                atomicAdd(&P.counters->steps, st);
+                atomicAdd(&P.counters->lookups, l);
+                atomicAdd(&P.counters->bricksCrossed, b);
+                atomicAdd(&P.counters->airWalks, wk);
+            }
+        }
+    }
+}
+
+// photons the transport kernel left in air bricks: walk them, survivors join the NEXT wave
+template <bool kStats>
+__global__ void __launch_bounds__(kThreads) airWalkKernel(const __grid_constant__ KernelParams P)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    uint32_t cSteps = 0, cLookups = 0, cBricks = 0, cWalks = 0;
+    const unsigned blocksPerShard = gridDim.x / kShards; // the grid is a multiple of kShards
+    const unsigned shard = blockIdx.x % kShards;
+    const unsigned nSlots = min(P.airCursors[shard].stored, P.photonRegion);
+    const PhotonRecord* const region = P.airborne + static_cast<size_t>(shard) * P.photonRegion;
+    for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
+        const unsigned i = base + threadIdx.x;
+        const bool valid = i < nSlots;
+        Photon p {};
+        Rng rng { 0, 1 };
+        float logE = 0.0f, maxAttInv = 0.0f, extra = 0.0f;
+        uint32_t seg = 0;
+        uint32_t outcome = WALK_GONE;
+        WalkEvent ev;
+        if (valid) {
+            loadPhoton(region + i, p, rng, logE, maxAttInv, seg, extra);
+            outcome = airWalk<kStats>(P, p, rng, logE, seg, maxAttInv, ev, cSteps, cLookups, cBricks);
+            if constexpr (kStats)
+                ++cWalks;
+        }
+        emitWalked(P, P.photonsOut, P.outCursors, outcome, valid, p, rng, logE, maxAttInv, seg, ev, lane);
+    }
+    if constexpr (kStats) {
+        const unsigned long long st = warpSum(cSteps), l = warpSum(cLookups), b = warpSum(cBricks), wk = warpSum(cWalks);
+        if (lane == 0) {
+            atomicAdd(&P.counters->steps, st);
+            atomicAdd(&P.counters->lookups, l);
+            atomicAdd(&P.counters->bricksCrossed, b);
+            atomicAdd(&P.counters->airWalks, wk);
         }
     }
 }
@@ -379,24 +564,31 @@ __device__ __forceinline__ void cpAsyncWait()
 }
 
 // ---- (b) Woodcock delta tracking (transport.hpp:640-700) -------------------------------------------
-template <bool kStats>
+constexpr unsigned kMaxBrickWords = 512; // bitmap of the brick grid in shared memory: at most 16384 bricks
+
+template <bool kStats, bool kAir>
 __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_constant__ KernelParams P)
 {
     __shared__ PhotonRecord ring[kThreads / 32][2 * kGroup];
     __shared__ unsigned stage[kThreads / 32][8];
     __shared__ uint2 sPalette[256];
+    __shared__ unsigned sAir[kAir ? kMaxBrickWords : 1];
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
     const unsigned myShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
     PhotonRecord* const myRing = ring[threadIdx.x >> 5];
     const bool paletteForm = P.world.palette != nullptr;
-    if (paletteForm) {
+    if (paletteForm)
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
-        __syncthreads();
+    if constexpr (kAir) {
+        for (unsigned k = threadIdx.x; k < P.bricks.nWords; k += kThreads)
+            sAir[k] = P.bricks.air[k];
     }
+    __syncthreads();
     // shared-state-space address of the table: the look-up below is one LEA + LDS instead of a generic-window address
     const unsigned paletteBase = static_cast<unsigned>(__cvta_generic_to_shared(sPalette));
+    const unsigned airBase = static_cast<unsigned>(__cvta_generic_to_shared(sAir));
 
     Rng rng { 0, 1 };
     Photon p {};
@@ -405,9 +597,6 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     bool lowWeight = false; // E*w below the Russian-roulette threshold (transport.hpp:684)
     uint32_t state = DEAD;
     uint32_t cSteps = 0, cLookups = 0;
-
-    // -ln(r)*maxAttInv*10 (transport.hpp:655-657) is evaluated as lg2(r) * kStepScale * maxAttInv; cm -> mm is the factor 10
-    constexpr float kStepScale = -6.931471805599453f;
 
     // ---- staging, all warp-uniform. Input: the warp claims tiles of kTile records from the shards of the wave and
     // streams them through its ring in groups of kGroup records (group k lives in ring half k & 1); empty lanes take
@@ -509,7 +698,9 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
             if (!insideWorld(P.world, p.px, p.py, p.pz)) {
                 state = DEAD;
             } else {
-                voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+                uint32_t ix, iy, iz;
+                voxelCoords(P.world, p.px, p.py, p.pz, ix, iy, iz);
+                voxel = (iz * P.world.dim[1] + iy) * P.world.dim[0] + ix;
                 uint2 rec;
                 // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
                 if (paletteForm) {
@@ -530,14 +721,23 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                     event = rng.uniform() < eventProbability;
                 if (event) {
                     state = EVENT;
-                } else if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
-                    const float r4 = rng.uniform();
-                    if (r4 < kRouletteProbability) {
-                        state = DEAD;
-                    } else {
-                        constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
-                        p.weight *= factor;
-                        lowWeight = p.energy * p.weight < kRouletteThreshold;
+                } else {
+                    if (lowWeight) { // Russian roulette after a virtual collision (transport.hpp:684-693)
+                        const float r4 = rng.uniform();
+                        if (r4 < kRouletteProbability) {
+                            state = DEAD;
+                        } else {
+                            constexpr float factor = 1.0f / (1.0f - kRouletteProbability);
+                            p.weight *= factor;
+                            lowWeight = p.energy * p.weight < kRouletteThreshold;
+                        }
+                    }
+                    if constexpr (kAir) { // a virtual collision in an air brick: the photon leaves for the air walk
+                        const unsigned brick = brickOfVoxel(P.bricks, ix, iy, iz);
+                        unsigned word;
+                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(airBase + 4u * (brick >> 5)));
+                        if (state == STEP && ((word >> (brick & 31u)) & 1u))
+                            state = AIRBORNE;
                     }
                 }
             }
@@ -584,6 +784,17 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 state = DEAD;
             }
             deadMask |= eventMask;
+        }
+        if constexpr (kAir) { // ---- lanes whose photon stands in an air brick hand it to the air walk
+            const unsigned airMask = __ballot_sync(kFull, state == AIRBORNE);
+            if (airMask) {
+                const size_t slot = appendSlots(P.airCursors, P.photonRegion, P.overflow, airMask, lane);
+                if (slot != kNoSlot)
+                    storePhoton(P.airborne + slot, p, rng, logE, maxAttInv, seg, 0.0f);
+                if (state == AIRBORNE)
+                    state = DEAD;
+                deadMask |= airMask;
+            }
         }
 
         // ---- re-fill empty lanes from the ring (a second pass when the current group runs out half-way)
@@ -830,9 +1041,46 @@ __global__ void paletteIndexKernel(const float* __restrict__ density, const uint
     }
 }
 
+// Brick grid of the empty-space traversal: per brick, the maximum over its voxels of density * ratio[material] (ratio[m] =
+// the largest mu_total,m(E) / majorant(E) over the table energies, computed on the host), and whether it holds a measurement
+// voxel. One coalesced pass over the grid; a warp covers 32 consecutive voxels of a row, i.e. one or two bricks: lanes are
+// grouped by brick (match.any) and each group issues one atomicMax. Positive floats order like their bit patterns; negative
+// and NaN products never win (they count as 0, like the oracle's `f > max` test).
+__global__ void brickMaxKernel(WorldView w, BrickView b, const float* __restrict__ ratio, uint64_t n, unsigned* __restrict__ brickMaxBits,
+    unsigned* __restrict__ brickMeasured)
+{
+    const unsigned lane = threadIdx.x & 31u;
+    const uint64_t stride = static_cast<uint64_t>(gridDim.x) * blockDim.x;
+    const uint64_t trips = (n + stride - 1) / stride; // the same for every thread: the warp stays converged
+    const uint64_t plane = static_cast<uint64_t>(w.dim[0]) * w.dim[1];
+    uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    for (uint64_t t = 0; t < trips; ++t, i += stride) {
+        unsigned brick = 0xffffffffu, bits = 0u, measured = 0u;
+        if (i < n) {
+            const uint32_t iz = static_cast<uint32_t>(i / plane);
+            const uint32_t rem = static_cast<uint32_t>(i - iz * plane);
+            const uint32_t iy = rem / w.dim[0], ix = rem - iy * w.dim[0];
+            const uint2 r = voxelRecord(w, static_cast<uint32_t>(i));
+            const float f = __fmul_rn(__uint_as_float(r.x), ratio[r.y & 0xffu]);
+            bits = f > 0.0f ? __float_as_uint(f) : 0u;
+            measured = (r.y & 0xff00u) ? 1u : 0u;
+            brick = brickOfVoxel(b, ix, iy, iz);
+        }
+        const unsigned group = __match_any_sync(kFull, brick);
+        const unsigned best = __reduce_max_sync(group, bits);
+        const unsigned any = __reduce_or_sync(group, measured);
+        if (brick != 0xffffffffu && lane == static_cast<unsigned>(__ffs(group) - 1)) {
+            atomicMax(brickMaxBits + brick, best);
+            if (any)
+                atomicOr(brickMeasured + brick, 1u);
+        }
+    }
+}
+
 // Per-material maximum density of the grid: the input of the Woodcock majorant (attenuationinterpolator.hpp:48-59,
-// where it is one transform_reduce over all voxels per material). Densities are non-negative (World::validate), so
-// their bit patterns order like unsigned integers. Per trip a warp groups its lanes by material (match.any), takes each
+// where it is one transform_reduce(init 0, max) over all voxels per material). Positive floats order like their bit
+// patterns; a negative, -0.0f or NaN density (nothing upstream rejects them) counts as 0, exactly like std::max(0, x)
+// leaves the reference's running maximum untouched. Per trip a warp groups its lanes by material (match.any), takes each
 // group's maximum (redux.sync) and issues ONE shared-memory atomicMax per distinct material; block maxima go out with
 // one global atomicMax per material.
 __global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, unsigned* __restrict__ maxBits)
@@ -850,7 +1098,7 @@ __global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, 
         if (i < n) {
             const uint2 r = records[i];
             material = r.y & 0xffu;
-            bits = r.x;
+            bits = __uint_as_float(r.x) > 0.0f ? r.x : 0u; // sign bit or NaN: ignored
         }
         const unsigned group = __match_any_sync(kFull, material);
         const unsigned best = __reduce_max_sync(group, bits);
@@ -1021,6 +1269,17 @@ struct dxmcb200_ctx {
     uint2* dPaletteTable = nullptr; // ... into this 256-entry record table
     bool allowPalette = true;
     bool allowNibbles = true;
+    // tracking: 1 = Woodcock + empty-space traversal through air bricks (default), 0 = the reference's Woodcock loop with the
+    // global majorant everywhere (DXMCB200_TRACKING, dxmcb200_set_tracking)
+    int tracking = 1;
+    float brickMm = 16.0f; // target brick edge (DXMCB200_BRICK_MM)
+    bool bricksValid = false;
+    BrickView bricks {};
+    uint32_t* dBrickBits = nullptr;
+    std::vector<float> hRatio, hBrickMax; // what the brick grid was built from, for dxmcb200_get_bricks
+    std::vector<uint8_t> hAir;
+    float fAir = 0.0f;
+    std::vector<float> hKnots, hCoeff, hMaxCoeff; // host copies of the attenuation fits (brick classification)
     int aggregateScores = -1; // warp-aggregated scoring: -1 automatic (narrow beams), 0 never, 1 always (DXMCB200_AGGREGATE)
     bool aggregateThisRun = false;
     unsigned long long* dAcc = nullptr;
@@ -1047,9 +1306,10 @@ struct dxmcb200_ctx {
     struct Pipe {
         cudaStream_t stream = nullptr;
         cudaEvent_t done = nullptr;
-        cudaEvent_t mark[4] = { nullptr, nullptr, nullptr, nullptr }; // around generate / transport / interact of the wave in flight
+        cudaEvent_t mark[5] = { nullptr, nullptr, nullptr, nullptr, nullptr }; // around generate / transport / air walk / interact of the wave in flight
         bool generated = false;
         PhotonRecord* dPhotons[2] = { nullptr, nullptr };
+        PhotonRecord* dAir = nullptr; // photons left in air bricks by the transport kernel (empty-space traversal)
         EventRecord* dEvents = nullptr;
         WaveCursors* dCursors = nullptr;
         WaveCursors* hCursors = nullptr; // pinned host copy for the per-wave read-back
@@ -1058,8 +1318,8 @@ struct dxmcb200_ctx {
         bool pending = false;
     } pipes[kMaxPipes];
     int nPipes = 2;
-    double kernelMs[3] = { 0, 0, 0 }; // summed device time of generate / transport / interact launches since clear
-    uint64_t kernelLaunches[3] = { 0, 0, 0 };
+    double kernelMs[4] = { 0, 0, 0, 0 }; // summed device time of generate / transport / air walk / interact launches since clear
+    uint64_t kernelLaunches[4] = { 0, 0, 0, 0 };
     uint64_t photonRegion = 0, eventRegion = 0; // slots per shard region of the photon / event buffers
     Counters* dCounters = nullptr;
 
@@ -1145,10 +1405,129 @@ cudaError_t launchInteract(const dxmcb200_ctx* c, cudaStream_t stream, const Ker
 
 unsigned maxTransportBlocks(const dxmcb200_ctx* c)
 {
-    int a = 0, b = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, transportKernel<false>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, transportKernel<true>, kThreads, 0);
-    return static_cast<unsigned>(c->smCount) * static_cast<unsigned>(std::max({ a, b, 1 }));
+    int occ[4] = { 0, 0, 0, 0 };
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], transportKernel<false, false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], transportKernel<true, false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], transportKernel<false, true>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], transportKernel<true, true>, kThreads, 0);
+    return static_cast<unsigned>(c->smCount) * static_cast<unsigned>(std::max({ occ[0], occ[1], occ[2], occ[3], 1 }));
+}
+
+// Layout of the brick grid (shared rule with the CPU restatement, oracle/dxmc_oracle.cpp buildBricks): the brick edge per axis
+// is the power of two (in voxels) closest to brickMm; while the grid has more than kMaxBricks bricks the axis with the
+// shortest brick edge in mm is doubled (ties: z before y before x).
+constexpr uint64_t kMaxBricks = static_cast<uint64_t>(kMaxBrickWords) * 32;
+constexpr double kAirThreshold = 0.02;
+
+void brickLayout(const uint64_t dim[3], const float spacing[3], float brickMm, uint32_t shift[3], uint32_t nb[3])
+{
+    for (int i = 0; i < 3; ++i) {
+        const double k = std::round(std::log2(static_cast<double>(brickMm) / static_cast<double>(spacing[i])));
+        shift[i] = static_cast<uint32_t>(std::clamp(k, 0.0, 10.0));
+    }
+    for (;;) {
+        uint64_t n = 1;
+        for (int i = 0; i < 3; ++i) {
+            nb[i] = static_cast<uint32_t>((dim[i] + (1ull << shift[i]) - 1) >> shift[i]);
+            n *= nb[i];
+        }
+        if (n <= kMaxBricks)
+            break;
+        int grow = 2;
+        for (int i = 1; i >= 0; --i)
+            if (static_cast<double>(1u << shift[i]) * spacing[i] < static_cast<double>(1u << shift[grow]) * spacing[grow])
+                grow = i;
+        ++shift[grow];
+    }
+}
+
+// Classify the bricks of the uploaded grid against the uploaded attenuation fits (once per world / table pair).
+int ensureBricks(dxmcb200_ctx* c)
+{
+    if (c->bricksValid)
+        return DXMCB200_OK;
+    c->bricks = BrickView {};
+    c->fAir = 0.0f;
+    c->hRatio.clear();
+    c->hBrickMax.clear();
+    c->hAir.clear();
+    if (c->tracking == 0) {
+        c->bricksValid = true;
+        return DXMCB200_OK;
+    }
+    const uint32_t nMat = c->lut.nMaterials, nSeg = c->lut.nSegments;
+    // per material: the largest mu_total(E) * majorantInverse(E) over the table. Inside a segment it is a sum of exponentials
+    // in log10 E (convex), so the maximum sits at a segment end; evaluated in double from the float fits.
+    std::vector<float> ratio(256, 0.0f);
+    for (uint32_t m = 0; m < nMat; ++m) {
+        double best = 0;
+        for (uint32_t k = 0; k < nSeg; ++k) {
+            const double ends[2] = { k == 0 ? 0.0 : static_cast<double>(c->hKnots[k - 1]), static_cast<double>(c->hKnots[k]) };
+            const float* fit = c->hCoeff.data() + (static_cast<size_t>(m) * nSeg + k) * 6;
+            for (const double x : ends) {
+                double total = 0;
+                for (int i = 0; i < 3; ++i)
+                    total += std::pow(10.0, static_cast<double>(fit[2 * i]) + static_cast<double>(fit[2 * i + 1]) * x);
+                best = std::max(best, total * std::pow(10.0, static_cast<double>(c->hMaxCoeff[2 * k]) + static_cast<double>(c->hMaxCoeff[2 * k + 1]) * x));
+            }
+        }
+        ratio[m] = static_cast<float>(best);
+    }
+    BrickView b {};
+    const uint64_t dim[3] = { c->world.dim[0], c->world.dim[1], c->world.dim[2] };
+    brickLayout(dim, c->world.spacing, c->brickMm, b.shift, b.nb);
+    for (int i = 0; i < 3; ++i)
+        b.size[i] = static_cast<float>(1u << b.shift[i]) * c->world.spacing[i];
+    const size_t nBricks = static_cast<size_t>(b.nb[0]) * b.nb[1] * b.nb[2];
+    float* dRatio = nullptr;
+    unsigned* dMax = nullptr; // [nBricks] maxima, then [nBricks] measurement flags
+    CU_CHECK(c, cudaMalloc(&dRatio, 256 * sizeof(float)));
+    cudaError_t e = cudaMalloc(&dMax, 2 * nBricks * sizeof(unsigned));
+    std::vector<unsigned> host(2 * nBricks, 0u);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dRatio, ratio.data(), 256 * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(dMax, 0, 2 * nBricks * sizeof(unsigned), c->stream);
+    if (e == cudaSuccess) {
+        brickMaxKernel<<<gridFor(c, c->nVoxels), 256, 0, c->stream>>>(c->world, b, dRatio, c->nVoxels, dMax, dMax + nBricks);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(host.data(), dMax, host.size() * sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(dRatio);
+    cudaFree(dMax);
+    CU_CHECK(c, e);
+    c->hRatio.assign(ratio.begin(), ratio.begin() + nMat);
+    c->hBrickMax.resize(nBricks);
+    std::memcpy(c->hBrickMax.data(), host.data(), nBricks * sizeof(float));
+    c->hAir.assign(nBricks, 0);
+    std::vector<uint32_t> bitmap((nBricks + 31) / 32, 0u);
+    double fAir = 0;
+    size_t nAir = 0;
+    for (size_t k = 0; k < nBricks; ++k) {
+        const double f = 1.001 * static_cast<double>(c->hBrickMax[k]);
+        if (f <= kAirThreshold && !host[nBricks + k]) {
+            c->hAir[k] = 1;
+            bitmap[k >> 5] |= 1u << (k & 31);
+            fAir = std::max(fAir, f);
+            ++nAir;
+        }
+    }
+    if (nAir > 0) {
+        c->fAir = static_cast<float>(std::max(fAir, 1.0e-6));
+        b.invFAir = 1.0f / c->fAir;
+        b.nWords = static_cast<uint32_t>(bitmap.size());
+        cudaFree(c->dBrickBits);
+        c->dBrickBits = nullptr;
+        CU_CHECK(c, cudaMalloc(&c->dBrickBits, bitmap.size() * sizeof(uint32_t)));
+        CU_CHECK(c, cudaMemcpy(c->dBrickBits, bitmap.data(), bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        b.air = c->dBrickBits;
+    }
+    c->bricks = b; // nWords == 0: no air bricks, the kernels without the traversal run
+    c->bricksValid = true;
+    return DXMCB200_OK;
 }
 
 // transports exposures expBegin + k * stride, k in [0, nExp)
@@ -1163,6 +1542,12 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     c->lastRunMs = 0;
     if (nExp == 0)
         return DXMCB200_OK;
+    {
+        const int st = ensureBricks(c);
+        if (st != DXMCB200_OK)
+            return st;
+    }
+    const bool air = c->bricks.nWords > 0; // empty-space traversal on and the grid has air bricks
     if (nExp >= (1ULL << 32)) {
         c->error = "more than 2^32 exposures in one run";
         return DXMCB200_ERR_ARG;
@@ -1210,7 +1595,8 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             hostio::poolFree(pipe.dPhotons[0]);
             hostio::poolFree(pipe.dPhotons[1]);
             hostio::poolFree(pipe.dEvents);
-            pipe.dPhotons[0] = pipe.dPhotons[1] = nullptr;
+            hostio::poolFree(pipe.dAir);
+            pipe.dPhotons[0] = pipe.dPhotons[1] = pipe.dAir = nullptr;
             pipe.dEvents = nullptr;
         }
         c->photonRegion = std::max(photonRegion, c->photonRegion);
@@ -1223,12 +1609,15 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dPhotons[1], c->photonRegion * kShards * sizeof(PhotonRecord)));
             CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dEvents, c->eventRegion * kShards * sizeof(EventRecord)));
         }
+        if (air && !pipe.dAir)
+            CU_CHECK(c, hostio::poolAlloc(c->device, &pipe.dAir, c->photonRegion * kShards * sizeof(PhotonRecord)));
     }
 
     KernelParams base {};
     base.world = c->world;
     base.lut = c->lut;
     base.beams = c->beams;
+    base.bricks = c->bricks;
     base.exposures = devExposures;
     base.prefix = c->dPrefix;
     base.expBegin = expBegin;
@@ -1260,7 +1649,13 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         const int cur = pipe.cur, nxt = cur ^ 1;
         P.events = pipe.dEvents;
         P.eventCursors = pipe.dCursors->events;
+        P.airborne = pipe.dAir;
+        P.airCursors = pipe.dCursors->air;
         P.overflow = &pipe.dCursors->overflow.stored;
+        // every kernel of the wave may append events (air walks included), so the event cursors are reset first
+        resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->events, 1);
+        if (air)
+            resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->air, 1);
         // (a) births
         const uint64_t births = std::min<uint64_t>(wave - pipe.survivors, total - issuedHistories);
         P.photonsOut = pipe.dPhotons[cur];
@@ -1274,8 +1669,12 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
                 P.chunkFirstExposure = static_cast<uint32_t>(issuedHistories / P.uniformHistories);
                 P.chunkFirstOffset = static_cast<uint32_t>(issuedHistories % P.uniformHistories);
             }
-            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, generateKernel<true>, P, births)
-                                        : launchPersistent(c, pipe.stream, generateKernel<false>, P, births));
+            if (air)
+                CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, generateKernel<true, true>, P, births)
+                                            : launchPersistent(c, pipe.stream, generateKernel<false, true>, P, births));
+            else
+                CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, generateKernel<true, false>, P, births)
+                                            : launchPersistent(c, pipe.stream, generateKernel<false, false>, P, births));
             issuedHistories += births;
             ++c->launches;
         }
@@ -1284,18 +1683,27 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         P.photonsIn = pipe.dPhotons[cur];
         P.inCursors = pipe.dCursors->photons[cur];
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[cur], 0);
-        resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->events, 1);
         CU_CHECK(c, cudaEventRecord(pipe.mark[1], pipe.stream));
-        CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true>, P, records)
-                                    : launchPersistent(c, pipe.stream, transportKernel<false>, P, records));
+        if (air)
+            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true, true>, P, records)
+                                        : launchPersistent(c, pipe.stream, transportKernel<false, true>, P, records));
+        else
+            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true, false>, P, records)
+                                        : launchPersistent(c, pipe.stream, transportKernel<false, false>, P, records));
         CU_CHECK(c, cudaEventRecord(pipe.mark[2], pipe.stream));
-        // (c)+(d) interactions and scoring; survivors open the next wave
+        // (b') photons left in air bricks take the air walk; (c)+(d) interactions and scoring; the survivors of both open the next wave
         P.photonsOut = pipe.dPhotons[nxt];
         P.outCursors = pipe.dCursors->photons[nxt];
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[nxt], 1);
+        if (air) {
+            CU_CHECK(c, c->collectStats ? launchSharded(c, pipe.stream, airWalkKernel<true>, P, records)
+                                        : launchSharded(c, pipe.stream, airWalkKernel<false>, P, records));
+            ++c->launches;
+        }
+        CU_CHECK(c, cudaEventRecord(pipe.mark[3], pipe.stream));
         CU_CHECK(c, model == 0 ? launchInteract<0>(c, pipe.stream, P, records)
                                : model == 1 ? launchInteract<1>(c, pipe.stream, P, records) : launchInteract<2>(c, pipe.stream, P, records));
-        CU_CHECK(c, cudaEventRecord(pipe.mark[3], pipe.stream));
+        CU_CHECK(c, cudaEventRecord(pipe.mark[4], pipe.stream));
         c->launches += 2;
         CU_CHECK(c, cudaMemcpyAsync(pipe.hCursors->photons[nxt], pipe.dCursors->photons[nxt], sizeof(ShardCursor) * kShards, cudaMemcpyDeviceToHost,
                         pipe.stream));
@@ -1309,9 +1717,9 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         CU_CHECK(c, cudaEventSynchronize(pipe.done));
         pipe.pending = false;
         const int nxt = pipe.cur ^ 1;
-        for (int k = 0; k < 3; ++k) { // device time of the wave's kernels (mark[1] is recorded after the tiny cursor resets)
+        for (int k = 0; k < 4; ++k) { // device time of the wave's kernels (mark[1] is recorded after the tiny cursor resets)
             float ms = 0;
-            if ((k > 0 || pipe.generated) && cudaEventElapsedTime(&ms, pipe.mark[k], pipe.mark[k + 1]) == cudaSuccess) {
+            if ((k > 0 || pipe.generated) && (k != 2 || air) && cudaEventElapsedTime(&ms, pipe.mark[k], pipe.mark[k + 1]) == cudaSuccess) {
                 c->kernelMs[k] += ms;
                 ++c->kernelLaunches[k];
             }
@@ -1430,6 +1838,7 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
         if ((i > 0 && cudaStreamCreateWithFlags(&pipe.stream, cudaStreamNonBlocking) != cudaSuccess)
             || cudaEventCreateWithFlags(&pipe.done, cudaEventDisableTiming) != cudaSuccess || cudaEventCreate(&pipe.mark[0]) != cudaSuccess
             || cudaEventCreate(&pipe.mark[1]) != cudaSuccess || cudaEventCreate(&pipe.mark[2]) != cudaSuccess || cudaEventCreate(&pipe.mark[3]) != cudaSuccess
+            || cudaEventCreate(&pipe.mark[4]) != cudaSuccess
             || cudaMalloc(&pipe.dCursors, sizeof(WaveCursors)) != cudaSuccess || cudaMallocHost(&pipe.hCursors, sizeof(WaveCursors)) != cudaSuccess) {
             dxmcb200_destroy(c);
             return DXMCB200_ERR_CUDA;
@@ -1443,6 +1852,13 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     }
     if (const char* env = std::getenv("DXMCB200_AGGREGATE"))
         c->aggregateScores = std::clamp(std::atoi(env), -1, 1);
+    if (const char* env = std::getenv("DXMCB200_TRACKING")) // 0: the reference's Woodcock loop everywhere, 1: + empty-space traversal
+        c->tracking = std::clamp(std::atoi(env), 0, 1);
+    if (const char* env = std::getenv("DXMCB200_BRICK_MM")) {
+        const double mm = std::atof(env);
+        if (mm > 0)
+            c->brickMm = static_cast<float>(mm);
+    }
     if (const char* env = std::getenv("DXMCB200_BATCH")) { // experiments: <refill batch>[,<log2 wave records>]
         int r = 8, lg = 26;
         std::sscanf(env, "%d,%d", &r, &lg);
@@ -1483,6 +1899,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
+    cudaFree(c->dBrickBits);
     lap("world, tables");
     for (int i = 0; i < kMaxPipes; ++i) {
         auto& pipe = c->pipes[i];
@@ -1492,6 +1909,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
         hostio::poolFree(pipe.dPhotons[0]);
         hostio::poolFree(pipe.dPhotons[1]);
         hostio::poolFree(pipe.dEvents);
+        hostio::poolFree(pipe.dAir);
         if (pipe.done)
             cudaEventDestroy(pipe.done);
         for (auto& m : pipe.mark)
@@ -1651,6 +2069,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     c->world.voxels = c->dVoxels;
     c->world.palette = c->dPalette;
     c->world.paletteTable = c->dPaletteTable;
+    c->bricksValid = false;
 
     // Optional (DXMCB200_L2PERSIST=1): pin the voxel grid in L2 with a persisting carve-out + access-policy window.
     // Measured on B200 with the 105 MB palette grid it LOWERS throughput (1.64e9 vs 2.00e9 histories/s): the carve-out
@@ -1731,6 +2150,10 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
     c->lut.rita = c->dLutBlob + oRita;
     c->lut.spline = c->dLutBlob + oSpline;
     c->lut.shells = c->dLutBlob + oShell;
+    c->hKnots.assign(l->knots, l->knots + nKnots);
+    c->hCoeff.assign(l->coefficients, l->coefficients + nCoeffIn);
+    c->hMaxCoeff.assign(l->max_coefficients, l->max_coefficients + nMax);
+    c->bricksValid = false;
     return DXMCB200_OK;
 }
 
@@ -1848,7 +2271,7 @@ int dxmcb200_clear(dxmcb200_ctx* c)
     c->totalMs = 0;
     c->lastRunMs = 0;
     c->launches = 0;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
         c->kernelMs[k] = 0;
         c->kernelLaunches[k] = 0;
     }
@@ -2049,17 +2472,52 @@ int dxmcb200_get_stats(dxmcb200_ctx* c, dxmcb200_stats* s)
     s->score_events = h.scores;
     s->kernel_launches = c->launches;
     s->kernel_ms = c->totalMs;
+    s->air_walks = h.airWalks;
+    s->bricks_crossed = h.bricksCrossed;
     return DXMCB200_OK;
 }
 
-int dxmcb200_get_kernel_times(dxmcb200_ctx* c, double ms[3], uint64_t launches[3])
+int dxmcb200_get_kernel_times(dxmcb200_ctx* c, double ms[4], uint64_t launches[4])
 {
     if (!c || !ms || !launches)
         return DXMCB200_ERR_ARG;
-    for (int k = 0; k < 3; ++k) {
+    for (int k = 0; k < 4; ++k) {
         ms[k] = c->kernelMs[k];
         launches[k] = c->kernelLaunches[k];
     }
+    return DXMCB200_OK;
+}
+
+int dxmcb200_set_tracking(dxmcb200_ctx* c, int tracking, float brickMm)
+{
+    if (!c || tracking < 0 || tracking > 1 || (brickMm != 0.0f && !(brickMm > 0.0f)))
+        return DXMCB200_ERR_ARG;
+    c->tracking = tracking;
+    if (brickMm > 0.0f)
+        c->brickMm = brickMm;
+    c->bricksValid = false;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_bricks(dxmcb200_ctx* c, uint32_t shift[3], uint32_t nb[3], float* fAir, float* ratio, float* brickMax, uint8_t* air)
+{
+    if (!c || !shift || !nb || !fAir || (!c->dVoxels && !c->dPalette) || !c->dLutBlob)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const int st = ensureBricks(c);
+    if (st != DXMCB200_OK)
+        return st;
+    for (int i = 0; i < 3; ++i) {
+        shift[i] = c->bricks.shift[i];
+        nb[i] = c->bricks.nb[i];
+    }
+    *fAir = c->bricks.nWords ? c->fAir : 0.0f;
+    if (ratio)
+        std::copy(c->hRatio.begin(), c->hRatio.end(), ratio);
+    if (brickMax)
+        std::copy(c->hBrickMax.begin(), c->hBrickMax.end(), brickMax);
+    if (air)
+        std::copy(c->hAir.begin(), c->hAir.end(), air);
     return DXMCB200_OK;
 }
 

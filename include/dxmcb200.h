@@ -137,6 +137,24 @@ int dxmcb200_set_beam_tables(dxmcb200_ctx*, uint32_t n_spectra, const dxmcb200_s
 int dxmcb200_suggest_fixed_point(uint64_t total_histories, double max_energy_weight, int* energy_bits, int* energy_sq_bits);
 int dxmcb200_set_fixed_point(dxmcb200_ctx*, int energy_bits, int energy_sq_bits);
 
+/* Tracking algorithm of subsequent runs.
+ *   0  the reference's Woodcock loop (transport.hpp:640-700) with the global majorant everywhere: draw for draw the
+ *      reference's algorithm, what the stream-identical parity tests run;
+ *   1  (default) the same loop plus EMPTY-SPACE TRAVERSAL: the grid is cut into bricks of about brick_mm (0 keeps the
+ *      current value, default 16 mm; powers of two in voxels, at most 16384 bricks); a brick is "air" when
+ *      rho * mu_total(E) <= f_air * majorant(E) for all its voxels and all table energies (f_air <= 0.02) and it holds no
+ *      measurement voxel; a photon standing in an air brick (at birth, or after a virtual collision) is walked through the run
+ *      of air bricks on its ray (Siddon / Amanatides-Woo traversal of the brick grid) with collision candidates sampled
+ *      against f_air * majorant. Delta tracking with any valid majorant samples the same collision density, so results
+ *      are statistically equivalent to mode 0 (not draw for draw); the CPU restatement implements the same scheme
+ *      (oracle/dxmc_oracle.cpp) and agrees with the kernels stream by stream.
+ * Also settable with DXMCB200_TRACKING / DXMCB200_BRICK_MM in the environment at create time. */
+int dxmcb200_set_tracking(dxmcb200_ctx*, int tracking, float brick_mm);
+/* The brick grid of mode 1 for the uploaded world and tables (built on first use): shift[3] (brick edge = 2^shift voxels),
+ * nb[3] bricks per axis, f_air (0: no air bricks); optional (may be NULL) ratio [n_materials] = max_E mu_total,m(E) /
+ * majorant(E), brick_max [nb2*nb1*nb0] = max over the brick's voxels of density * ratio[material], air [nb2*nb1*nb0] flags. */
+int dxmcb200_get_bricks(dxmcb200_ctx*, uint32_t shift[3], uint32_t nb[3], float* f_air, float* ratio, float* brick_max, uint8_t* air);
+
 /* zero the accumulators and counters */
 int dxmcb200_clear(dxmcb200_ctx*);
 
@@ -199,12 +217,14 @@ typedef struct dxmcb200_stats {
     uint64_t score_events;     /* scoring events (S of the roofline model) */
     uint64_t kernel_launches;
     double kernel_ms;          /* summed over all runs since dxmcb200_clear */
+    uint64_t air_walks;        /* empty-space traversal: walks through runs of air bricks */
+    uint64_t bricks_crossed;   /* ... and brick faces crossed on them */
 } dxmcb200_stats;
 int dxmcb200_get_stats(dxmcb200_ctx*, dxmcb200_stats*);
-/* Device time (CUDA events on the launching streams) and launch counts of the three wave kernels since
- * dxmcb200_clear: [0] generateKernel, [1] transportKernel (includes two one-block cursor resets), [2] interactKernel.
- * With two pipelines the kernels of both overlap on the GPU, so the three sums can exceed the wall time. */
-int dxmcb200_get_kernel_times(dxmcb200_ctx*, double ms[3], uint64_t launches[3]);
+/* Device time (CUDA events on the launching streams) and launch counts of the wave kernels since dxmcb200_clear:
+ * [0] generateKernel, [1] transportKernel, [2] airWalkKernel (incl. a one-block cursor reset), [3] interactKernel.
+ * With two pipelines the kernels of both overlap on the GPU, so the sums can exceed the wall time. */
+int dxmcb200_get_kernel_times(dxmcb200_ctx*, double ms[4], uint64_t launches[4]);
 /* The per-history work counters (histories .. score_events) cost registers, so the transport kernel is
  * compiled twice; on != 0 selects the counting variant for subsequent runs (default off, or
  * DXMCB200_STATS=1 in the environment at create time). kernel_launches / kernel_ms are always kept. */

@@ -684,6 +684,281 @@ struct Oracle {
         }
     }
 
+    // =====================================================================================================
+    // Empty-space traversal (NOT in the reference; restated from the product's design, DESIGN.md section 4b, so that
+    // the CUDA kernels can be checked stream by stream). The voxel grid is cut into bricks of 2^k voxels per axis.
+    // A brick is "air" when rho * mu_total(E) <= fAir * majorant(E) holds for all its voxels and all table energies
+    // (fAir <= kAirThreshold) and it holds no measurement voxel. Photons are tracked with the reference's Woodcock
+    // loop (global majorant) everywhere else. Whenever a photon stands in an air brick — at birth, after
+    // transportParticleToWorld, or after a virtual collision — it is walked through the run of air bricks on its ray
+    // by a parametric ray/grid traversal (Siddon 1985 / Amanatides & Woo 1987) up to the first non-air brick or the
+    // edge of the grid; collision candidates on that stretch are sampled against the regional majorant
+    // fAir * majorant(E) (delta tracking with any valid majorant gives the same collision density). Everything
+    // that happens AT a candidate (look-up, accept / reject, forced interaction, roulette) is the reference's code.
+    // =====================================================================================================
+    static constexpr double kAirThreshold = 0.02;
+    struct Bricks {
+        bool enabled = false;
+        std::uint32_t shift[3] {}, nb[3] {};
+        T size[3] {}; // brick edge [mm]
+        std::vector<std::uint8_t> air; // [nb2][nb1][nb0]
+        std::vector<T> ratio; // per material: max over E of mu_total(E) / majorant(E)
+        std::vector<T> brickMax; // per brick: max over voxels of rho * ratio[material]
+        T fAir = 0, invFAir = 0;
+        std::uint64_t nAir = 0;
+    } bricks;
+    std::uint64_t brickSteps = 0, walks = 0, walkCandidates = 0; // instrumentation
+
+    // brick edge per axis: the power of two (in voxels) closest to `brickMm`; while the grid has more than kMaxBricks
+    // bricks the axis with the shortest brick edge in mm is doubled (ties: z before y before x)
+    static constexpr std::uint64_t kMaxBricks = 16384;
+    void buildBricks(T brickMm)
+    {
+        Bricks& b = bricks;
+        b = Bricks {};
+        for (int i = 0; i < 3; ++i) {
+            const double k = std::round(std::log2(static_cast<double>(brickMm) / static_cast<double>(spacing[i])));
+            b.shift[i] = static_cast<std::uint32_t>(std::clamp(k, 0.0, 10.0));
+        }
+        for (;;) {
+            std::uint64_t n = 1;
+            for (int i = 0; i < 3; ++i) {
+                b.nb[i] = static_cast<std::uint32_t>((dim[i] + (1ull << b.shift[i]) - 1) >> b.shift[i]);
+                n *= b.nb[i];
+            }
+            if (n <= kMaxBricks)
+                break;
+            int grow = 2;
+            for (int i = 1; i >= 0; --i)
+                if (static_cast<double>(1u << b.shift[i]) * spacing[i] < static_cast<double>(1u << b.shift[grow]) * spacing[grow])
+                    grow = i;
+            ++b.shift[grow];
+        }
+        for (int i = 0; i < 3; ++i)
+            b.size[i] = static_cast<T>(1u << b.shift[i]) * spacing[i];
+        // per material: the largest mu_total(E) * majorantInverse(E) over the table. Inside a segment it is a sum of
+        // exponentials in log10 E (convex), so the maximum sits at a segment end; evaluated in double.
+        b.ratio.assign(nMat, T { 0 });
+        for (std::size_t m = 0; m < nMat; ++m) {
+            double best = 0;
+            for (std::size_t k = 0; k < nSeg; ++k) {
+                const double ends[2] = { k == 0 ? 0.0 : static_cast<double>(knots[k - 1]), static_cast<double>(knots[k]) };
+                for (const double x : ends) {
+                    double total = 0;
+                    for (int i = 0; i < 3; ++i)
+                        total += std::pow(10.0, static_cast<double>(coeff[(m * nSeg + k) * 6 + 2 * i]) + static_cast<double>(coeff[(m * nSeg + k) * 6 + 2 * i + 1]) * x);
+                    best = std::max(best, total * std::pow(10.0, static_cast<double>(maxCoeff[2 * k]) + static_cast<double>(maxCoeff[2 * k + 1]) * x));
+                }
+            }
+            b.ratio[m] = static_cast<T>(best);
+        }
+        const std::size_t nBricks = static_cast<std::size_t>(b.nb[0]) * b.nb[1] * b.nb[2];
+        b.brickMax.assign(nBricks, T { 0 });
+        std::vector<std::uint8_t> measured(nBricks, 0);
+        for (std::size_t z = 0; z < dim[2]; ++z)
+            for (std::size_t y = 0; y < dim[1]; ++y)
+                for (std::size_t x = 0; x < dim[0]; ++x) {
+                    const std::size_t v = (z * dim[1] + y) * dim[0] + x;
+                    const std::size_t br = ((z >> b.shift[2]) * b.nb[1] + (y >> b.shift[1])) * b.nb[0] + (x >> b.shift[0]);
+                    const T f = density[v] * b.ratio[material[v]];
+                    if (f > b.brickMax[br]) // NaN and negative densities never win
+                        b.brickMax[br] = f;
+                    if (!measurement.empty() && measurement[v])
+                        measured[br] = 1;
+                }
+        b.air.assign(nBricks, 0);
+        double fAir = 0;
+        for (std::size_t br = 0; br < nBricks; ++br) {
+            const double f = 1.001 * static_cast<double>(b.brickMax[br]);
+            if (f <= kAirThreshold && !measured[br]) {
+                b.air[br] = 1;
+                ++b.nAir;
+                fAir = std::max(fAir, f);
+            }
+        }
+        b.fAir = static_cast<T>(std::max(fAir, 1.0e-6));
+        b.invFAir = T { 1 } / b.fAir;
+        b.enabled = b.nAir > 0;
+    }
+
+    void voxelCoordinates(const T pos[3], std::uint32_t out[3]) const // clamped: also valid on the faces of the world
+    {
+        for (int i = 0; i < 3; ++i) {
+            const T rel = (pos[i] - ext[2 * i]) / spacing[i];
+            const std::uint64_t v = rel > 0 ? static_cast<std::uint64_t>(rel) : 0;
+            out[i] = static_cast<std::uint32_t>(std::min<std::uint64_t>(v, dim[i] - 1));
+        }
+    }
+    bool airBrick(const std::uint32_t b[3]) const { return bricks.air[(static_cast<std::size_t>(b[2]) * bricks.nb[1] + b[1]) * bricks.nb[0] + b[0]] != 0; }
+    bool inAirBrick(const T pos[3]) const
+    {
+        std::uint32_t v[3];
+        voxelCoordinates(pos, v);
+        const std::uint32_t b[3] = { v[0] >> bricks.shift[0], v[1] >> bricks.shift[1], v[2] >> bricks.shift[2] };
+        return airBrick(b);
+    }
+
+    // Ray parameter at which the ray leaves the run of air bricks it starts in; `exits` when it leaves the grid there.
+    T airRunLength(const Particle& p, bool& exits)
+    {
+        std::uint32_t v[3];
+        voxelCoordinates(p.pos, v);
+        std::int64_t b[3];
+        T tMax[3], tDelta[3];
+        int step[3];
+        for (int i = 0; i < 3; ++i) {
+            b[i] = v[i] >> bricks.shift[i];
+            if (std::abs(p.dir[i]) > N_ERROR) {
+                const T inv = T { 1 } / p.dir[i];
+                step[i] = p.dir[i] > 0 ? 1 : -1;
+                const T face = ext[2 * i] + static_cast<T>(b[i] + (p.dir[i] > 0 ? 1 : 0)) * bricks.size[i];
+                tMax[i] = std::max((face - p.pos[i]) * inv, T { 0 });
+                tDelta[i] = bricks.size[i] * std::abs(inv);
+            } else {
+                step[i] = 0;
+                tMax[i] = std::numeric_limits<T>::infinity();
+                tDelta[i] = 0;
+            }
+        }
+        exits = false;
+        for (;;) {
+            const int a = tMax[0] <= tMax[1] ? (tMax[0] <= tMax[2] ? 0 : 2) : (tMax[1] <= tMax[2] ? 1 : 2);
+            const T t = tMax[a];
+            if (step[a] == 0) { // direction is zero along every axis: the photon never leaves
+                exits = true;
+                return t;
+            }
+            b[a] += step[a];
+            ++brickSteps;
+            if (b[a] < 0 || b[a] >= static_cast<std::int64_t>(bricks.nb[a])) {
+                exits = true;
+                return t;
+            }
+            tMax[a] += tDelta[a];
+            const std::uint32_t bb[3] = { static_cast<std::uint32_t>(b[0]), static_cast<std::uint32_t>(b[1]), static_cast<std::uint32_t>(b[2]) };
+            if (!airBrick(bb))
+                return t;
+        }
+    }
+
+    // Walk a photon standing in an air brick to the end of the air run. Returns false when the history ends
+    // (left the world, absorbed, roulette); `interacted` reports a real or forced interaction (the walk stops there).
+    template <int L>
+    bool airWalk(Particle& p, Rng& state, T maxAttenuationInv, bool& updateMaxAttenuation, bool& interacted)
+    {
+        interacted = false;
+        ++walks;
+        bool exits = false;
+        T remaining = airRunLength(p, exits);
+        for (;;) {
+            const auto r1 = state.uniform();
+            const auto stepLenght = (-std::log(r1) * maxAttenuationInv * T { 10 }) * bricks.invFAir;
+            if (!(stepLenght < remaining)) { // no candidate before the end of the run
+                for (std::size_t i = 0; i < 3; i++)
+                    p.pos[i] += p.dir[i] * remaining;
+                return !exits;
+            }
+            for (std::size_t i = 0; i < 3; i++)
+                p.pos[i] += p.dir[i] * stepLenght;
+            remaining -= stepLenght;
+            ++stats.steps;
+            ++walkCandidates;
+            if (!inside(p.pos))
+                return false;
+            const std::size_t bufferIdx = indexFromPosition(p.pos);
+            const auto matIdx = material[bufferIdx];
+            const auto dens = density[bufferIdx];
+            const auto meas = measurement.empty() ? std::uint8_t { 0 } : measurement[bufferIdx];
+            ++stats.lookups;
+            const auto att = attenuation(matIdx, p.energy);
+            const auto attenuationTotal = (((T { 0 } + att[0]) + att[1]) + att[2]) * dens;
+            const auto eventProbability = std::min((attenuationTotal * maxAttenuationInv) * bricks.invFAir, T { 1 });
+            bool alive = true;
+            if (meas == 0) {
+                const auto r2 = state.uniform();
+                if (r2 < eventProbability) {
+                    ++stats.interactions;
+                    interacted = true;
+                    alive = computeInteractions<L>(att, p, matIdx, bufferIdx, state, updateMaxAttenuation);
+                }
+            } else {
+                ++stats.interactions;
+                interacted = true;
+                alive = computeInteractionsForced<L>(eventProbability, att, p, matIdx, bufferIdx, state, updateMaxAttenuation);
+            }
+            if (alive && p.energy * p.weight < ROULETTE_THRESHOLD) {
+                const auto r4 = state.uniform();
+                if (r4 < ROULETTE_PROBABILITY)
+                    alive = false;
+                else
+                    p.weight *= T { 1 } / (T { 1 } - ROULETTE_PROBABILITY);
+            }
+            if (!alive || interacted)
+                return alive;
+        }
+    }
+
+    // woodcockParticleTracking<L> with the air walk hooked in (same statements as woodcock<L> above otherwise)
+    template <int L>
+    void woodcockEmptySpace(Particle& p, Rng& state)
+    {
+        T maxAttenuationInv = maxAttenuationInverse(p.energy);
+        bool updateMaxAttenuation = false;
+        bool interacted = false;
+        bool continueSampling = true;
+        if (inAirBrick(p.pos)) // birth in (or at the face of) an air brick
+            continueSampling = airWalk<L>(p, state, maxAttenuationInv, updateMaxAttenuation, interacted);
+        while (continueSampling) {
+            if (updateMaxAttenuation) {
+                maxAttenuationInv = maxAttenuationInverse(p.energy);
+                updateMaxAttenuation = false;
+            }
+            const auto r1 = state.uniform();
+            const auto stepLenght = -std::log(r1) * maxAttenuationInv * T { 10 };
+            for (std::size_t i = 0; i < 3; i++)
+                p.pos[i] += p.dir[i] * stepLenght;
+            ++stats.steps;
+            if (!inside(p.pos))
+                break;
+            const std::size_t bufferIdx = indexFromPosition(p.pos);
+            const auto matIdx = material[bufferIdx];
+            const auto dens = density[bufferIdx];
+            const auto meas = measurement.empty() ? std::uint8_t { 0 } : measurement[bufferIdx];
+            ++stats.lookups;
+            const auto att = attenuation(matIdx, p.energy);
+            const auto attenuationTotal = (((T { 0 } + att[0]) + att[1]) + att[2]) * dens;
+            const auto eventProbability = attenuationTotal * maxAttenuationInv;
+            interacted = false;
+            if (meas == 0) {
+                const auto r2 = state.uniform();
+                if (r2 < eventProbability) {
+                    ++stats.interactions;
+                    interacted = true;
+                    continueSampling = computeInteractions<L>(att, p, matIdx, bufferIdx, state, updateMaxAttenuation);
+                }
+            } else {
+                ++stats.interactions;
+                interacted = true;
+                continueSampling = computeInteractionsForced<L>(eventProbability, att, p, matIdx, bufferIdx, state, updateMaxAttenuation);
+            }
+            if (continueSampling && p.energy * p.weight < ROULETTE_THRESHOLD) {
+                const auto r4 = state.uniform();
+                if (r4 < ROULETTE_PROBABILITY)
+                    continueSampling = false;
+                else
+                    p.weight *= T { 1 } / (T { 1 } - ROULETTE_PROBABILITY);
+            }
+            // a virtual collision in an air brick: the photon is walked to the end of the air run, then Woodcock steps resume
+            if (continueSampling && !interacted && inAirBrick(p.pos)) {
+                if (updateMaxAttenuation) {
+                    maxAttenuationInv = maxAttenuationInverse(p.energy);
+                    updateMaxAttenuation = false;
+                }
+                continueSampling = airWalk<L>(p, state, maxAttenuationInv, updateMaxAttenuation, interacted);
+            }
+        }
+    }
+
     // ---- transport<L> over a range of exposures (transport.hpp:729-763)
     template <int L>
     void run(const dxmcb200_exposure* exposures, std::uint64_t begin, std::uint64_t end, std::uint64_t seed, bool perHistoryStreams)
@@ -700,7 +975,10 @@ struct Oracle {
                 ++stats.histories;
                 if (transportParticleToWorld(particle)) {
                     ++stats.histories_in_world;
-                    woodcock<L>(particle, state);
+                    if (bricks.enabled)
+                        woodcockEmptySpace<L>(particle, state);
+                    else
+                        woodcock<L>(particle, state);
                 }
             }
         }
@@ -813,6 +1091,7 @@ int dxmc_oracle_clear(dxmc_oracle* h)
     std::fill(o->fixedEnergy.begin(), o->fixedEnergy.end(), 0);
     std::fill(o->fixedEnergySq.begin(), o->fixedEnergySq.end(), 0u);
     o->stats = {};
+    o->walks = o->brickSteps = o->walkCandidates = 0;
     return DXMCB200_OK;
 }
 
@@ -829,6 +1108,53 @@ int dxmc_oracle_run(dxmc_oracle* h, const dxmcb200_exposure* exposures, uint64_t
         o->run<1>(exposures, begin, end, seed, per_history_streams != 0);
     else
         o->run<2>(exposures, begin, end, seed, per_history_streams != 0);
+    return DXMCB200_OK;
+}
+
+// tracking 0: the reference's Woodcock loop (global majorant) everywhere; 1: Woodcock + empty-space traversal through
+// air bricks of about brick_mm (the product's default tracking). Call after set_world and set_luts.
+int dxmc_oracle_set_tracking(dxmc_oracle* h, int tracking, float brick_mm)
+{
+    auto* o = reinterpret_cast<Oracle*>(h);
+    if (!o || tracking < 0 || tracking > 1 || (tracking == 1 && (!(brick_mm > 0) || o->nMat == 0 || o->density.empty())))
+        return DXMCB200_ERR_ARG;
+    if (tracking == 1)
+        o->buildBricks(brick_mm);
+    else
+        o->bricks = {};
+    return DXMCB200_OK;
+}
+
+// the brick grid of the empty-space traversal: shift[3], nb[3], f_air, and (any pointer may be NULL) the per-material ratios
+// [n_materials], the per-brick maxima [nb2*nb1*nb0] and the air flags [nb2*nb1*nb0]
+int dxmc_oracle_get_bricks(dxmc_oracle* h, uint32_t shift[3], uint32_t nb[3], float* f_air, float* ratio, float* brick_max, uint8_t* air)
+{
+    auto* o = reinterpret_cast<Oracle*>(h);
+    if (!o || !shift || !nb || !f_air)
+        return DXMCB200_ERR_ARG;
+    for (int i = 0; i < 3; ++i) {
+        shift[i] = o->bricks.shift[i];
+        nb[i] = o->bricks.nb[i];
+    }
+    *f_air = o->bricks.enabled ? o->bricks.fAir : 0.0f;
+    if (ratio)
+        std::copy(o->bricks.ratio.begin(), o->bricks.ratio.end(), ratio);
+    if (brick_max)
+        std::copy(o->bricks.brickMax.begin(), o->bricks.brickMax.end(), brick_max);
+    if (air)
+        std::copy(o->bricks.air.begin(), o->bricks.air.end(), air);
+    return DXMCB200_OK;
+}
+
+// instrumentation of the empty-space traversal: out[0] air walks, out[1] bricks crossed, out[2] collision candidates in air
+int dxmc_oracle_get_walk_stats(dxmc_oracle* h, uint64_t out[3])
+{
+    auto* o = reinterpret_cast<Oracle*>(h);
+    if (!o || !out)
+        return DXMCB200_ERR_ARG;
+    out[0] = o->walks;
+    out[1] = o->brickSteps;
+    out[2] = o->walkCandidates;
     return DXMCB200_OK;
 }
 

@@ -128,6 +128,25 @@ class Oracle:
         self._chk(self.l.dxmc_oracle_get_fixed(self.h, e.ctypes.data_as(_i64p), e2.ctypes.data_as(C.POINTER(C.c_uint64))), "dxmc_oracle_get_fixed")
         return e, e2
 
+    def set_tracking(self, tracking: int, brick_mm: float = 16.0):
+        """0: the reference's Woodcock loop; 1: Woodcock + empty-space traversal through air bricks (call after load)."""
+        self._chk(self.l.dxmc_oracle_set_tracking(self.h, int(tracking), C.c_float(brick_mm)), "dxmc_oracle_set_tracking")
+
+    def bricks(self) -> dict:
+        shift, nb, f_air = (C.c_uint32 * 3)(), (C.c_uint32 * 3)(), C.c_float()
+        self._chk(self.l.dxmc_oracle_get_bricks(self.h, shift, nb, C.byref(f_air), None, None, None), "dxmc_oracle_get_bricks")
+        n = int(nb[0]) * int(nb[1]) * int(nb[2])
+        n_mat = int(self._flat["luts"]["n_materials"])
+        ratio, bmax, air = np.zeros(n_mat, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
+        self._chk(self.l.dxmc_oracle_get_bricks(self.h, shift, nb, C.byref(f_air), ratio.ctypes.data_as(_f32p), bmax.ctypes.data_as(_f32p),
+                                                air.ctypes.data_as(_u8p)), "dxmc_oracle_get_bricks")
+        return {"shift": list(shift), "nb": list(nb), "f_air": float(f_air.value), "ratio": ratio, "brick_max": bmax, "air": air}
+
+    def walk_stats(self):
+        out = (C.c_uint64 * 3)()
+        self._chk(self.l.dxmc_oracle_get_walk_stats(self.h, out), "dxmc_oracle_get_walk_stats")
+        return [int(x) for x in out]
+
     def stats(self) -> dict:
         s = cabi.Stats()
         self._chk(self.l.dxmc_oracle_get_stats(self.h, C.byref(s)), "dxmc_oracle_get_stats")

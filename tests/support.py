@@ -140,6 +140,33 @@ def ct_scene(lib, spiral=True, histories=5000, aec=True, xcare=True, tilt=5.0, d
     return sc
 
 
+def air_gap_scene(lib, histories=20000, exposures=4, forced=False, dim=(40, 36, 44), spacing=(2.0, 2.5, 2.0)):
+    """A tissue body with a bone core, a lung-like insert and an internal air cavity, surrounded by a wide margin of air, lit by
+    a wide isotropic spectrum source from outside the world: most bricks of the empty-space traversal are air bricks, photons
+    are born into them, leave through them and cross the cavity. With forced=True a slab is flagged in the measurement map."""
+    sc = S.Scene(lib)
+    sc.world(dim, spacing)
+    sc.add_material(AIR, 0.001205).add_material(SOFT, 1.03).add_material(BONE, 1.92).add_material(SOFT, 0.26)
+    nx, ny, nz = dim
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    r2 = ((x - nx / 2 + 0.5) / (nx * 0.28)) ** 2 + ((y - ny / 2 + 0.5) / (ny * 0.30)) ** 2
+    body = (r2 <= 1.0) & (z >= nz // 6) & (z < nz - nz // 6)
+    mat = np.zeros((nz, ny, nx), np.uint8)
+    mat[body] = 1
+    mat[body & (r2 <= 0.08)] = 2
+    mat[body & (np.abs(x - nx * 0.62) < nx * 0.06) & (np.abs(y - ny / 2) < ny * 0.12)] = 3
+    mat[body & (np.abs(x - nx * 0.36) < nx * 0.05) & (np.abs(y - ny / 2) < ny * 0.08) & (np.abs(z - nz / 2) < nz * 0.2)] = 0  # cavity
+    dens = np.array([0.001205, 1.03, 1.92, 0.26], np.float32)[mat]
+    meas = None
+    if forced:
+        meas = np.zeros((nz, ny, nx), np.uint8)
+        meas[nz // 2 - 1: nz // 2 + 1, ny // 3: 2 * ny // 3, nx // 3: 2 * nx // 3] = 1
+    sc.arrays(dens, mat, meas)
+    assert sc.validate()
+    sc.source_isotropic((1.0, -260.0, 2.0), (-1, 0, 0, 0, 0, 1), (-0.16, 0.16, -0.17, 0.17), SPECTRUM_W, SPECTRUM_E, histories, exposures, ct=True)
+    return sc
+
+
 def ctdi_scene(lib, histories=4000, diameter=160):
     sc = S.Scene(lib)
     sc.ctdi_phantom(diameter)

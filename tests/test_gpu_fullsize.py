@@ -26,7 +26,8 @@ def test_full_size_ct_spiral_properties(gpu, product):
     st = ctx.stats()
     whole = ctx.get_raw()
     assert st["histories"] == total
-    assert 10 < st["lookups"] / total < 40 and 0.3 < st["score_events"] / total < 3
+    assert 5 < st["lookups"] / total < 40 and 0.3 < st["score_events"] / total < 3  # ~33 with plain Woodcock tracking, ~11 with the air walk
+    assert st["air_walks"] > total  # default tracking: every history is born into air, many leave through it
     # second run, split into three launches' worth of exposure blocks, must reproduce the grids bit for bit
     ctx.clear()
     for b, e in ((0, 1000), (1000, 1001), (1001, 3600)):

@@ -25,7 +25,8 @@ SCENES = {
 
 @pytest.mark.parametrize("name", list(SCENES))
 @pytest.mark.parametrize("model", [0, 1, 2])
-def test_against_committed_reference_streams(gpu, product, name, model):
+def test_against_committed_reference_streams(gpu, product, name, model, monkeypatch):
+    monkeypatch.setenv("DXMCB200_TRACKING", "0")  # the reference's own tracking: same draws as the committed vectors
     g = np.load(os.path.join(G, f"streams_{name}_m{model}.npz"))
     sc = SCENES[name](product)
     r = sc.transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
@@ -50,7 +51,13 @@ def test_against_committed_reference_streams(gpu, product, name, model):
     ("ct_axial_none", lambda lib: T.ct_scene(lib, spiral=False, histories=250000, xcare=False, tilt=0.0), 0),
     ("dx_tube_slab", lambda lib: T.dx_slab_scene(lib, histories=3000000, exposures=8), 1),  # BASELINE config #2 in small
 ])
-def test_live_reference_three_sigma(gpu, product, reference, name, builder, model):
+@pytest.mark.parametrize("tracking", ["0", "1"])
+def test_live_reference_three_sigma(gpu, product, reference, name, builder, model, tracking, monkeypatch):
+    """tracking 0 = the reference's Woodcock loop (identical streams on both sides), 1 = the product's default (empty-space
+    traversal: independent statistics in every scene with air bricks)."""
+    if tracking == "1" and name in ("pencil", "isotropic_forced", "isotropic_ia"):
+        pytest.skip("no air bricks at the default brick size: identical to tracking 0")
+    monkeypatch.setenv("DXMCB200_TRACKING", tracking)
     a = builder(product).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED)
     b = builder(reference).transport(model=model, output=S.OUT_EV_PER_HISTORY, seed=T.SEED, workers=S.WORKERS_COUNTER_STREAMS)
     n = a.histories
@@ -134,6 +141,7 @@ def test_fixed_point_grid_against_oracle(gpu, product):
     exps = T.exposures_of(sc)
     ctx = cabi.Context(0)
     T.load_context(ctx, flat)
+    ctx.set_tracking(0)
     ctx.set_fixed_point(22, 12)
     ctx.run(exps, 0, 3, model=1, seed=7)
     e, e2, ev = ctx.get_raw()
@@ -163,6 +171,7 @@ def test_continuous_density_takes_record_grid(gpu, product):
     exps = T.exposures_of(sc)
     ctx = cabi.Context(0)
     T.load_context(ctx, flat)
+    ctx.set_tracking(0)
     ctx.set_fixed_point(22, 12)
     ctx.run(exps, 0, 3, model=1, seed=11)
     e, e2, ev = ctx.get_raw()
@@ -186,6 +195,7 @@ def test_uneven_histories_and_empty_exposures(gpu, product):
         x.histories = h
     ctx = cabi.Context(0)
     T.load_context(ctx, flat)
+    ctx.set_tracking(0)
     ctx.enable_stats(True)
     ctx.run(exps, 0, 5, model=1, seed=3)
     assert ctx.stats()["histories"] == 3000 + 17 + 12001 + 1
@@ -208,6 +218,7 @@ def test_work_counters_match_oracle(gpu, product):
     exps = T.exposures_of(sc)
     ctx = cabi.Context(0)
     T.load_context(ctx, flat)
+    ctx.set_tracking(0)
     ctx.enable_stats(True)
     ctx.run(exps, 0, len(exps), model=1, seed=11)
     s = ctx.stats()
@@ -259,12 +270,13 @@ def test_ct_dose_calibration_second_pass(gpu, product, reference):
     assert a > 0 and abs(a - b) / b < 0.05, (a, b)
 
 
-def test_ctdi_phantom_hole_dose_identical_streams(gpu, product, reference):
+def test_ctdi_phantom_hole_dose_identical_streams(gpu, product, reference, monkeypatch):
     """The calibration run itself: CT axial source on the CTDI phantom, forced interactions in the five dosimeter bores,
     DOSE output without calibration (keV/kg). Same streams on both sides -> the bore doses that enter CTDIw agree to 1e-5."""
     def holes(sc, r):
         return np.array([r.dose[sc.ctdi_holes(p).astype(np.int64)].astype(np.float64).mean() for p in range(5)])
 
+    monkeypatch.setenv("DXMCB200_TRACKING", "0")  # the reference's own tracking, so that both sides draw the same numbers
     a, b = T.ctdi_scene(product, histories=30000, diameter=320), T.ctdi_scene(reference, histories=30000, diameter=320)
     ra = a.transport(model=1, output=S.OUT_DOSE, use_calibration=False, seed=5)
     rb = b.transport(model=1, output=S.OUT_DOSE, use_calibration=False, seed=5, workers=S.WORKERS_COUNTER_STREAMS)
