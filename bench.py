@@ -235,7 +235,7 @@ def main():
 
     kernel_ms = []
     launches = 0
-    per_kernel = {"generate": [0.0, 0], "transport": [0.0, 0], "interact": [0.0, 0]}
+    per_kernel = {"generate": [0.0, 0], "transport": [0.0, 0], "airwalk": [0.0, 0], "interact": [0.0, 0]}
 
     def step(record):
         nonlocal launches

@@ -29,6 +29,27 @@ CUDA_SOURCES = ["csrc/transport.cu"]
 HOST_SOURCES = ["host/xrl_lite.cpp", "host/matdb.cpp", "host/scene_capi.cpp"]
 
 
+def _xraylib():
+    """Compile and link flags of a real xraylib (the reference's element data library, CMakeLists.txt:47-55), when there is
+    one: DXMCB200_XRAYLIB=<prefix> (with include/xraylib/xraylib.h and lib/libxrl.so), or `pkg-config libxrl`. DXMCB200_XRAYLIB=0
+    forces the in-repo approximate xrl_lite. Returns (cflags, ldflags) or None."""
+    prefix = os.environ.get("DXMCB200_XRAYLIB", "")
+    if prefix == "0":
+        return None
+    if prefix:
+        for inc in (os.path.join(prefix, "include", "xraylib"), os.path.join(prefix, "include")):
+            if os.path.exists(os.path.join(inc, "xraylib.h")):
+                lib = os.path.join(prefix, "lib")
+                return [f"-I{inc}"], [f"-L{lib}", "-lxrl", "-Xlinker", f"-rpath={lib}"]
+        raise RuntimeError(f"DXMCB200_XRAYLIB={prefix}: no xraylib.h under it")
+    pc = shutil.which("pkg-config")
+    if pc and subprocess.run([pc, "--exists", "libxrl"]).returncode == 0:
+        cflags = subprocess.check_output([pc, "--cflags", "libxrl"], text=True).split()
+        libs = subprocess.check_output([pc, "--libs", "libxrl"], text=True).split()
+        return cflags, libs
+    return None
+
+
 def _newer(src_files, target):
     if not os.path.exists(target):
         return True
@@ -66,9 +87,12 @@ def build(force: bool = False, verbose: bool = False) -> str:
         _run([NVCC, *NVCC_FLAGS, *INCLUDES, "-c", os.path.join(HERE, s), "-o", o], log)
         objs.append(o)
     procs = []
+    xrl = _xraylib()
+    xrl_cflags = ["-DDXMCB200_USE_XRAYLIB", *xrl[0]] if xrl else []
+    xrl_ldflags = xrl[1] if xrl else []
     for s in HOST_SOURCES:
         o = os.path.join(OBJ, os.path.basename(s) + ".o")
-        procs.append((s, subprocess.Popen([CXX, *CXX_FLAGS, *INCLUDES, "-c", os.path.join(HERE, s), "-o", o], stdout=subprocess.PIPE,
+        procs.append((s, subprocess.Popen([CXX, *CXX_FLAGS, *xrl_cflags, *INCLUDES, "-c", os.path.join(HERE, s), "-o", o], stdout=subprocess.PIPE,
                                           stderr=subprocess.STDOUT, text=True)))
         objs.append(o)
     for s, p in procs:
@@ -76,7 +100,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         if p.returncode != 0:
             sys.stderr.write(out)
             raise RuntimeError(f"compiling {s} failed")
-    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-ldl", "-lpthread", "-Xlinker", "-Bsymbolic"], log)
+    _run([NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", OUT, *objs, "-ldl", "-lpthread", "-Xlinker", "-Bsymbolic", *xrl_ldflags], log)
     with open(os.path.join(OBJ, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:

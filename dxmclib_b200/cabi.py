@@ -20,7 +20,7 @@ _u64p = C.POINTER(C.c_uint64)
 
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
-    "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_trim_pool",
+    "dxmcb200_physics_backend", "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_trim_pool",
     "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_run_resident", "dxmcb200_run_strided",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
@@ -73,8 +73,9 @@ def lib() -> C.CDLL:
         l.dxmcb200_destroy.restype = None
         l.dxmcb200_destroy.argtypes = [C.c_void_p]
         l.dxmcb200_history_stream.restype = None
+        l.dxmcb200_physics_backend.restype = C.c_char_p
         for name in CABI_SYMBOLS:
-            if name not in ("dxmcb200_last_error", "dxmcb200_destroy", "dxmcb200_history_stream"):
+            if name not in ("dxmcb200_last_error", "dxmcb200_destroy", "dxmcb200_history_stream", "dxmcb200_physics_backend"):
                 getattr(l, name).restype = C.c_int
         l._cabi_ready = True
     return l
@@ -94,6 +95,13 @@ def device_count() -> int:
     n = C.c_int(0)
     lib().dxmcb200_device_count(C.byref(n))
     return int(n.value)
+
+
+def physics_backend():
+    """(name, approximate) of the element data the library's host-side table builders use."""
+    flag = C.c_int()
+    name = lib().dxmcb200_physics_backend(C.byref(flag))
+    return name.decode(), bool(flag.value)
 
 
 def suggest_fixed_point(total_histories: int, max_energy_weight: float):

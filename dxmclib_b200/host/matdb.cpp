@@ -11,12 +11,49 @@ using namespace xrl_lite;
 #endif
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <execution>
+#include <mutex>
 #include <numeric>
 
 namespace dxmcb200::matdb {
 
+bool backendIsApproximate()
+{
+#ifdef DXMCB200_USE_XRAYLIB
+    return false;
+#else
+    return true;
+#endif
+}
+
+const char* backendName()
+{
+#ifdef DXMCB200_USE_XRAYLIB
+    return "xraylib";
+#else
+    return "xrl_lite (approximate: analytic models + anchor tables, few % on mu/rho for Z <= 20 and 5-150 keV; H-Ca, I, W and a few "
+           "more elements; build with a real xraylib for dosimetry: dxmclib_b200/build.py, DXMCB200_XRAYLIB)";
+#endif
+}
+
 namespace {
+
+    // A dosimetry library that silently computes with approximate cross sections is a trap: say so once per process, on the
+    // first material that is looked up (DXMCB200_QUIET=1 silences it; dxmcb200_physics_backend() reports the same).
+    void announceBackendOnce()
+    {
+        if (!backendIsApproximate())
+            return;
+        static std::once_flag once;
+        std::call_once(once, [] {
+            const char* quiet = std::getenv("DXMCB200_QUIET");
+            if (quiet && quiet[0] == '1')
+                return;
+            std::fprintf(stderr, "[dxmcb200] physics data backend: %s\n", backendName());
+        });
+    }
 
     // mass fractions -> normalised number fractions (reference material.cpp:150-154, 347-353)
     void fillNumberFractions(Composition& c, int n, const int* Z, const double* massFractions)
@@ -96,6 +133,7 @@ namespace {
 
 Composition compositionFromString(const std::string& s)
 {
+    announceBackendOnce();
     Composition c;
     if (compoundDataNIST* n = GetCompoundDataNISTByName(s.c_str(), nullptr)) {
         c.name = n->name;
@@ -118,6 +156,7 @@ Composition compositionFromString(const std::string& s)
 
 Composition compositionFromAtomicNumber(int Z)
 {
+    announceBackendOnce();
     Composition c;
     if (char* sym = AtomicNumberToSymbol(Z, nullptr)) {
         c.name = sym;
@@ -291,3 +330,11 @@ std::array<Shell, 12> electronConfiguration(const std::string& name)
 }
 
 } // namespace dxmcb200::matdb
+
+// C ABI (include/dxmcb200.h): which element data the host-side table builders of this library were compiled against
+extern "C" const char* dxmcb200_physics_backend(int* approximate)
+{
+    if (approximate)
+        *approximate = dxmcb200::matdb::backendIsApproximate() ? 1 : 0;
+    return dxmcb200::matdb::backendName();
+}

@@ -26,6 +26,10 @@ struct Composition {
     bool hasDensity = false;
 };
 
+// the element data behind every function below: "xraylib", or the in-repo approximate xrl_lite
+const char* backendName();
+bool backendIsApproximate();
+
 // NIST compound name first, chemical formula second (reference material.cpp:83-97, 340-377)
 Composition compositionFromString(const std::string& nameOrFormula);
 // single element (reference material.cpp:324-338)

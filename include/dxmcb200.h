@@ -111,6 +111,14 @@ typedef struct dxmcb200_exposure {
     uint64_t histories;
 } dxmcb200_exposure;
 
+/* ---- physics data ----------------------------------------------------------------------- */
+/* Name of the element data source the host-side table builders (Material, AttenuationLut, Tube) of this library were
+ * compiled against: "xraylib" (what the reference uses, src/material.cpp:23-375) or the in-repo "xrl_lite (approximate ...)".
+ * *approximate (may be NULL) is 1 for the latter: absolute doses then carry the few-% error of that data (TG-195 totals
+ * within about 2-5 %); product-vs-reference parity is unaffected because both are built on the same source here. The
+ * library also prints this line once to stderr when approximate data is first used (DXMCB200_QUIET=1 silences it). */
+const char* dxmcb200_physics_backend(int* approximate);
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 int dxmcb200_device_count(int* count);
 int dxmcb200_create(int device, dxmcb200_ctx** out);
