@@ -12,6 +12,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <thread>
@@ -26,7 +27,20 @@ namespace hostio {
     // again to the next request of a similar size on the same device (the accumulators, wave buffers and staging
     // arrays of consecutive Transport calls have the same sizes). dxmcb200_trim_pool() gives everything back.
     constexpr size_t kPoolMinBytes = size_t { 16 } << 20;
-    constexpr size_t kPoolMaxParked = size_t { 96 } << 30; // per process; beyond this, releases go to the driver
+
+    // How many bytes may stay parked per process after their context is gone. Default 0: a library user gets all device
+    // memory back when Transport::operator() returns (a GUI host shares the GPU with other code). Callers that run many
+    // Transport calls back to back opt in with DXMCB200_POOL_GB=<n> in the environment or dxmcb200_set_pool_limit():
+    // at 1e10 histories a call then saves about 0.5-1 s of cudaMalloc / cudaFree of 40+ GB of wave buffers.
+    inline std::atomic<size_t>& poolLimit()
+    {
+        static std::atomic<size_t> limit { [] {
+            const char* env = std::getenv("DXMCB200_POOL_GB");
+            const double gb = env ? std::atof(env) : 0.0;
+            return gb > 0 ? static_cast<size_t>(gb * 1073741824.0) : size_t { 0 };
+        }() };
+        return limit;
+    }
 
     struct Pool {
         struct Block {
@@ -92,7 +106,7 @@ namespace hostio {
                 if (it != live.end()) {
                     const Block b = it->second;
                     live.erase(it);
-                    if (parkedBytes + b.bytes <= kPoolMaxParked) {
+                    if (parkedBytes + b.bytes <= poolLimit().load()) {
                         parked.push_back(b);
                         parkedBytes += b.bytes;
                         return;

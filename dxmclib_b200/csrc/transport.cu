@@ -27,10 +27,12 @@
 // carries its own random stream, so results do not depend on the wave size, scheduling or GPU partition.
 #include "hostio.cuh"
 #include "physics.cuh"
+#include "../include/dxmc/sourcemodel.hpp"
 
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <dlfcn.h>
@@ -858,11 +860,15 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     // block b works on event shard b % kShards together with the other blocks of the same residue
     const unsigned blocksPerShard = gridDim.x / kShards; // the grid is a multiple of kShards
     const unsigned shard = blockIdx.x % kShards;
-    const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion); // a multiple of kEventTile
+    // transportKernel claims slots in tiles of kEventTile, the walk kernels claim exact counts: any number of slots. The trip
+    // count is the same for all lanes of a warp (the loop body holds full-mask ballots and shuffles); slots past the end read
+    // as unused.
+    const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion);
     const EventRecord* const region = P.events + static_cast<size_t>(shard) * P.eventRegion;
-    for (unsigned i = (blockIdx.x / kShards) * kThreads + threadIdx.x; i < nSlots; i += blocksPerShard * kThreads) {
-        const EventRecord* e = region + i;
-        const uint4 where = e->where;
+    for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
+        const unsigned i = base + threadIdx.x;
+        const EventRecord* e = region + min(i, nSlots - 1u);
+        const uint4 where = i < nSlots ? e->where : make_uint4(0u, kNoEvent, 0u, 0u);
         bool alive = false;
         Photon p {};
         Rng rng { 0, 1 };
@@ -926,6 +932,39 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
             atomicAdd(&P.counters->scores, sc);
         }
     }
+}
+
+// ---- exposure table on the device: exposure i of a source is a pure function of its parameter block ----
+static_assert(sizeof(dxmcb200_source_params) == sizeof(dxmc::model::SourceParams<float>), "dxmcb200_source_params mirrors model::SourceParams<float>");
+static_assert(offsetof(dxmcb200_source_params, world_cosines) == offsetof(dxmc::model::SourceParams<float>, worldCosines), "layout of the parameter block");
+static_assert(offsetof(dxmcb200_source_params, sdd) == offsetof(dxmc::model::SourceParams<float>, sdd), "layout of the parameter block");
+static_assert(offsetof(dxmcb200_source_params, xcare_angle) == offsetof(dxmc::model::SourceParams<float>, xcareAngle), "layout of the parameter block");
+
+__global__ void exposureKernel(const __grid_constant__ dxmc::model::SourceParams<float> source, const float* __restrict__ tubeCurrent, uint64_t n,
+    dxmcb200_exposure* __restrict__ out)
+{
+    const uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (i >= n)
+        return;
+    dxmc::model::ExposureValues<float> v;
+    dxmc::model::evaluate(source, tubeCurrent, i, v);
+    dxmcb200_exposure e;
+    for (int k = 0; k < 3; ++k) {
+        e.position[k] = v.position[k];
+        e.beam_direction[k] = v.beam[k];
+    }
+    for (int k = 0; k < 6; ++k)
+        e.cosines[k] = v.cosines[k];
+    for (int k = 0; k < 4; ++k)
+        e.collimation[k] = v.collimation[k];
+    e.weight = v.weight;
+    e.mono_energy = v.monoEnergy;
+    e.spectrum = v.spectrum;
+    e.heel = v.heel;
+    e.bowtie = v.bowtie;
+    e.reserved = 0;
+    e.histories = v.histories;
+    out[i] = e;
 }
 
 // reset the cursors of one buffer between waves
@@ -1938,6 +1977,14 @@ int dxmcb200_trim_pool(int device)
     return DXMCB200_OK;
 }
 
+int dxmcb200_set_pool_limit(uint64_t bytes)
+{
+    hostio::poolLimit().store(static_cast<size_t>(bytes));
+    if (bytes == 0)
+        hostio::Pool::instance().trim(-1);
+    return DXMCB200_OK;
+}
+
 int dxmcb200_material_max_density(dxmcb200_ctx* c, uint32_t nMaterials, float* out)
 {
     if (!c || !out || nMaterials == 0 || nMaterials > 256 || (!c->dVoxels && !c->dPalette))
@@ -2301,6 +2348,55 @@ int dxmcb200_upload_exposures(dxmcb200_ctx* c, const dxmcb200_exposure* exposure
     c->nExposuresResident = n;
     c->hExposures.assign(exposures, exposures + n);
     return DXMCB200_OK;
+}
+
+int dxmcb200_generate_exposures(dxmcb200_ctx* c, const dxmcb200_source_params* params, const float* aecProfile, dxmcb200_exposure* out)
+{
+    if (!c || !params || params->exposures == 0 || params->motion > DXMCB200_SOURCE_GANTRY_TOPOGRAM || (params->aec_size && !aecProfile)
+        || (params->tubes != 1 && params->tubes != 2))
+        return DXMCB200_ERR_ARG;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const uint64_t n = params->exposures;
+    if (n > c->nExposuresResident) {
+        cudaFree(c->dExposures);
+        c->dExposures = nullptr;
+        c->nExposuresResident = 0;
+        CU_CHECK(c, cudaMalloc(&c->dExposures, n * sizeof(dxmcb200_exposure)));
+    }
+    float* dProfile = nullptr;
+    if (params->aec_size) {
+        CU_CHECK(c, cudaMalloc(&dProfile, params->aec_size * sizeof(float)));
+        cudaError_t e = cudaMemcpyAsync(dProfile, aecProfile, params->aec_size * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+        if (e != cudaSuccess) {
+            cudaFree(dProfile);
+            CU_CHECK(c, e);
+        }
+    }
+    dxmc::model::SourceParams<float> block;
+    std::memcpy(&block, params, sizeof(block));
+    exposureKernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, c->stream>>>(block, dProfile, n, c->dExposures);
+    cudaError_t e = cudaGetLastError();
+    c->hExposures.resize(n);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(c->hExposures.data(), c->dExposures, n * sizeof(dxmcb200_exposure), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(c->stream);
+    cudaFree(dProfile);
+    CU_CHECK(c, e);
+    c->nExposuresResident = n;
+    if (out)
+        std::memcpy(out, c->hExposures.data(), n * sizeof(dxmcb200_exposure));
+    return DXMCB200_OK;
+}
+
+int dxmcb200_run_range(dxmcb200_ctx* c, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb,
+    void* user)
+{
+    if (!c || !c->dExposures || expEnd > c->nExposuresResident || expEnd < expBegin)
+        return DXMCB200_ERR_STATE;
+    if (expEnd == expBegin)
+        return DXMCB200_OK;
+    return runRange(c, c->hExposures.data(), c->dExposures, expBegin, expEnd - expBegin, 1, model, seed, cancel, cb, user);
 }
 
 int dxmcb200_run_resident(dxmcb200_ctx* c, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed)

@@ -307,6 +307,11 @@ public:
         buildPositionTable(world.densityArray()->cbegin(), world.densityArray()->cend(), world.spacing(), world.dimensions(), world.origin());
     }
     bool isValid() const { return m_valid; }
+    // the table sampleIntensityWeight interpolates in: one intensity per slice between positionMin and positionMax
+    const std::vector<T>& positionIntensity() const { return m_positionIntensity; }
+    T positionMin() const { return m_positionMin; }
+    T positionMax() const { return m_positionMax; }
+    T positionStep() const { return m_positionStep; }
     const std::vector<T>& mass() const { return m_mass; }
     const std::vector<T>& massIntensity() const { return m_massIntensity; }
     const std::string& filterName() const { return m_filterName; }

@@ -1,7 +1,11 @@
 // ctsource.hpp — the CT source family: CTBaseSource -> CTSource -> CTAxialSource / CTSpiralSource, CTDualSource ->
-// CTAxialDualSource / CTSpiralDualSource, CTTopogramSource; reference include/dxmc/source.hpp:789-1700. getExposure(i)
-// is O(1) host code that Transport evaluates for every exposure up front; ctCalibration runs a second Transport on a
-// CTDIPhantom like the reference does, i.e. a second pass through the same CUDA path. Included by dxmc/source.hpp.
+// CTAxialDualSource / CTSpiralDualSource, CTTopogramSource. API of reference include/dxmc/source.hpp:789-1700.
+//
+// A CT scan is the GANTRY_* motion of the parameter block in dxmc/sourcemodel.hpp: per tube a focal-spot radius, field of
+// view, start angle and weight; a beam width, angular step, pitch or table step, gantry tilt; the two tube-current
+// modulations. The classes are setters over that block (names, defaults and clamps as in the reference); exposure i is
+// model::evaluate(block, i) on the host and exposureKernel on the device. The CTDI calibration (reference :925-988) is
+// a second Transport run over a CTDIPhantom, i.e. a second pass through the same CUDA path. Included by dxmc/source.hpp.
 #pragma once
 #include "dxmc/sourcebase.hpp"
 
@@ -16,19 +20,20 @@ class CTAxialDualSource;
 template <Floating T>
 class CTSpiralDualSource;
 
-// common CT state: gantry geometry, tube, bow-tie, CTDI calibration target
+// gantry geometry, tube A, bow-tie, CTDI calibration target
 template <Floating T>
 class CTBaseSource : public Source<T> {
 public:
     CTBaseSource()
     {
-        this->m_type = Source<T>::Type::None;
-        m_sdd = 1190.0;
-        m_collimation = 38.4;
-        m_fov = 500.0;
-        m_startAngle = 0.0;
-        m_scanLenght = 100.0;
-        tube().setAlFiltration(7.0);
+        auto& p = this->m_p;
+        p.motion = model::GANTRY_AXIAL;
+        p.sdd[0] = p.sdd[1] = 1190.0;
+        p.fov[0] = p.fov[1] = 500.0;
+        p.beamWidth = 38.4;
+        p.scanLength = 100.0;
+        p.spectrum[0] = 0;
+        m_tube.setAlFiltration(7.0);
         this->setDirectionCosines({ -1, 0, 0, 0, 0, 1 });
     }
 
@@ -46,31 +51,31 @@ public:
 
     void setSourceDetectorDistance(T sdd)
     {
-        m_sdd = std::abs(sdd);
+        this->m_p.sdd[0] = std::abs(sdd);
         m_specterValid = false;
     }
-    T sourceDetectorDistance() const { return m_sdd; }
+    T sourceDetectorDistance() const { return this->m_p.sdd[0]; }
     void setCollimation(T collimation)
     {
-        m_collimation = std::abs(collimation);
+        this->m_p.beamWidth = std::abs(collimation);
         m_specterValid = false;
     }
-    T collimation() const { return m_collimation; }
-    void setFieldOfView(T fov) { m_fov = std::abs(fov); }
-    T fieldOfView() const { return m_fov; }
+    T collimation() const { return this->m_p.beamWidth; }
+    void setFieldOfView(T fov) { this->m_p.fov[0] = std::abs(fov); }
+    T fieldOfView() const { return this->m_p.fov[0]; }
 
-    void setGantryTiltAngle(T angle) { m_gantryTiltAngle = std::clamp(angle, -PI_VAL<T>(), PI_VAL<T>()); }
-    T gantryTiltAngle() const { return m_gantryTiltAngle; }
+    void setGantryTiltAngle(T angle) { this->m_p.tilt = std::clamp(angle, -PI_VAL<T>(), PI_VAL<T>()); }
+    T gantryTiltAngle() const { return this->m_p.tilt; }
     void setGantryTiltAngleDeg(T angle) { setGantryTiltAngle(angle * DEG_TO_RAD<T>()); }
-    T gantryTiltAngleDeg() const { return m_gantryTiltAngle * RAD_TO_DEG<T>(); }
+    T gantryTiltAngleDeg() const { return this->m_p.tilt * RAD_TO_DEG<T>(); }
 
-    void setStartAngle(T angle) { m_startAngle = angle; }
-    T startAngle() const { return m_startAngle; }
-    T startAngleDeg() const { return RAD_TO_DEG<T>() * m_startAngle; }
-    void setStartAngleDeg(T angle) { m_startAngle = DEG_TO_RAD<T>() * angle; }
+    void setStartAngle(T angle) { this->m_p.startAngle[0] = angle; }
+    T startAngle() const { return this->m_p.startAngle[0]; }
+    T startAngleDeg() const { return RAD_TO_DEG<T>() * this->m_p.startAngle[0]; }
+    void setStartAngleDeg(T angle) { this->m_p.startAngle[0] = DEG_TO_RAD<T>() * angle; }
 
-    virtual void setScanLenght(T scanLenght) { m_scanLenght = std::abs(scanLenght); }
-    T scanLenght() const { return m_scanLenght; }
+    virtual void setScanLenght(T scanLenght) { this->m_p.scanLength = std::abs(scanLenght); }
+    T scanLenght() const { return this->m_p.scanLength; }
 
     void setCtdiVol(T ctdivol)
     {
@@ -91,81 +96,90 @@ public:
         updateSpecterDistribution();
         return m_specterValid;
     }
+    typename Source<T>::BeamTables beamTables(std::uint32_t) const override
+    {
+        return { m_specterDistribution.get(), m_heelFilter.get(), m_bowTieFilter.get() };
+    }
+    // take over what another CT source holds at this level (geometry of tube A, beam width, scan length, tilt, tube, bow-tie,
+    // spectrum state, CTDI target) and leave the rest of this source (motion, angular step, table step, modulation) alone
+    void adoptBaseOf(const CTBaseSource& other)
+    {
+        auto& p = this->m_p;
+        const auto& q = other.m_p;
+        std::copy(q.position, q.position + 3, p.position);
+        std::copy(q.cosines, q.cosines + 6, p.cosines);
+        p.histories = q.histories;
+        p.sdd[0] = q.sdd[0];
+        p.fov[0] = q.fov[0];
+        p.startAngle[0] = q.startAngle[0];
+        p.beamWidth = q.beamWidth;
+        p.scanLength = q.scanLength;
+        p.tilt = q.tilt;
+        m_ctdivol = other.m_ctdivol;
+        m_ctdiPhantomDiameter = other.m_ctdiPhantomDiameter;
+        m_bowTieFilter = other.m_bowTieFilter;
+        m_tube = other.m_tube;
+        m_specterDistribution = other.m_specterDistribution;
+        m_heelFilter = other.m_heelFilter;
+        m_modelHeelEffect = other.m_modelHeelEffect;
+        m_specterValid = other.m_specterValid;
+    }
+    bool describe(model::SourceParams<T>& block, const T*& tubeCurrent) const override
+    {
+        Source<T>::describe(block, tubeCurrent);
+        const auto a = this->beamTables(0);
+        block.spectrum[0] = a.specter ? 0 : -1;
+        block.heel[0] = a.heel ? 0 : -1;
+        block.bowtie[0] = a.fan ? 0 : -1;
+        if (block.tubes == 2) {
+            const auto b = this->beamTables(1);
+            block.spectrum[1] = b.specter ? 1 : -1;
+            block.heel[1] = b.heel ? 1 : -1;
+            block.bowtie[1] = b.fan ? 1 : -1;
+        }
+        return true;
+    }
 
 protected:
-    struct GantryFrame {
-        std::array<T, 3> position;
-        std::array<T, 6> cosines;
-    };
-    // Focal spot position and detector orientation for a gantry angle: start at (0, -sdd/2, 0), tilt the
-    // rotation axis (y cosine) about x, rotate about the tilted axis, then advance along z.
-    GantryFrame gantryFrame(T sdd, T angle, T zAdvance) const
-    {
-        GantryFrame f;
-        f.position = { 0, -sdd / T { 2 }, 0 };
-        f.cosines = this->m_directionCosines;
-        T* rotationAxis = &f.cosines[3];
-        T* otherAxis = &f.cosines[0];
-        const std::array<T, 3> tiltAxis = { 1, 0, 0 };
-        auto tiltCorrection = f.position;
-        vectormath::rotate(tiltCorrection.data(), tiltAxis.data(), m_gantryTiltAngle);
-        vectormath::rotate(rotationAxis, tiltAxis.data(), m_gantryTiltAngle);
-        vectormath::rotate(otherAxis, tiltAxis.data(), m_gantryTiltAngle);
-        vectormath::rotate(f.position.data(), rotationAxis, angle);
-        f.position[2] += zAdvance + tiltCorrection[2];
-        vectormath::rotate(otherAxis, rotationAxis, angle);
-        for (std::size_t i = 0; i < 3; ++i)
-            f.position[i] += this->m_position[i];
-        return f;
-    }
-    // full fan and cone opening angles; the focal spot is sdd/2 from the isocentre
-    std::array<T, 2> openingAngles(T fov, T sdd) const { return { std::atan(fov / sdd) * T { 2 }, std::atan(m_collimation / sdd) * T { 2 } }; }
-
-    // CTDIw of one axial rotation on a CTDI phantom -> factor that scales the run to the requested CTDIvol
+    // Dose calibration of a rotating CT source (reference source.hpp:925-988): the scan's axial twin, centred and untilted, makes
+    // one rotation over a CTDI phantom with at least CTDIPhantom::ctdiMinHistories() histories; CTDIw from the five chamber
+    // bores, scaled to 100 mm / beam width, against the requested CTDIvol and the mean beam weight of the twin.
     template <typename U>
         requires std::is_same_v<CTAxialSource<T>, U> || std::is_same_v<CTAxialDualSource<T>, U>
-    static T ctCalibration(U& sourceCopy, LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr)
+    static T ctCalibration(U& twin, LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr)
     {
-        T meanWeight = 0;
-        for (std::uint64_t i = 0; i < sourceCopy.totalExposures(); ++i)
-            meanWeight += sourceCopy.getExposure(i).beamIntensityWeight();
-        meanWeight /= sourceCopy.totalExposures();
-
-        sourceCopy.setDirectionCosines({ -1, 0, 0, 0, 0, 1 });
-        sourceCopy.setPosition({ 0, 0, 0 });
-        sourceCopy.setScanLenght(sourceCopy.collimation());
-        sourceCopy.setUseXCareFilter(false); // organ modulation would bias the CTDI statistics
-
-        std::size_t statCounter = CTDIPhantom<T>::ctdiMinHistories() / (sourceCopy.exposuresPerRotatition() * sourceCopy.historiesPerExposure());
-        statCounter = std::max(statCounter, std::size_t { 1 });
-
-        CTDIPhantom<T> world(sourceCopy.ctdiPhantomDiameter());
-        sourceCopy.updateFromWorld(world);
-        sourceCopy.setHistoriesPerExposure(sourceCopy.historiesPerExposure() * statCounter);
-        sourceCopy.validate();
+        const T meanWeight = twin.meanBeamWeight();
+        twin.setDirectionCosines({ -1, 0, 0, 0, 0, 1 });
+        twin.setPosition({ 0, 0, 0 });
+        twin.setScanLenght(twin.collimation());
+        twin.setUseXCareFilter(false); // organ modulation would bias the CTDI statistics
+        const std::size_t repeats = std::max<std::size_t>(CTDIPhantom<T>::ctdiMinHistories() / (twin.exposuresPerRotatition() * twin.historiesPerExposure()), 1);
+        CTDIPhantom<T> phantom(twin.ctdiPhantomDiameter());
+        twin.updateFromWorld(phantom);
+        twin.setHistoriesPerExposure(twin.historiesPerExposure() * repeats);
+        twin.validate();
         if (progressBar) {
             progressBar->setPlaneNormal(ProgressBar<T>::Axis::Z);
             progressBar->setPrefixMessage("CTDI calibration ");
         }
-
         Transport<T> transport;
         transport.setLowEnergyCorrectionModel(model);
-        const auto result = transport(world, &sourceCopy, progressBar, false);
+        const auto result = transport(phantom, &twin, progressBar, false);
 
-        using Hole = typename CTDIPhantom<T>::HolePosition;
-        const std::array<Hole, 5> holes = { Hole::Center, Hole::West, Hole::East, Hole::South, Hole::North };
-        std::array<T, 5> dose;
-        dose.fill(T { 0 });
-        for (std::size_t i = 0; i < 5; ++i) {
-            const auto& indices = world.holeIndices(holes[i]);
-            for (const auto idx : indices)
-                dose[i] += result.dose[idx];
-            dose[i] /= indices.size();
+        using Bore = typename CTDIPhantom<T>::HolePosition;
+        T bore[5];
+        int k = 0;
+        for (const Bore where : { Bore::Center, Bore::West, Bore::East, Bore::South, Bore::North }) {
+            const auto& voxels = phantom.holeIndices(where);
+            T sum = 0;
+            for (const auto v : voxels)
+                sum += result.dose[v];
+            bore[k++] = sum / voxels.size();
         }
-        const T periphery = (dose[1] + dose[2] + dose[3] + dose[4]) / T { 4 };
-        T ctdiw = (dose[0] + 2 * periphery) / 3;
-        ctdiw *= T { 100 } / sourceCopy.collimation();
-        return sourceCopy.ctdiVol() / ctdiw / meanWeight;
+        const T periphery = (bore[1] + bore[2] + bore[3] + bore[4]) / T { 4 };
+        T ctdiw = (bore[0] + 2 * periphery) / 3;
+        ctdiw *= T { 100 } / twin.collimation();
+        return twin.ctdiVol() / ctdiw / meanWeight;
     }
 
     virtual void updateSpecterDistribution()
@@ -173,20 +187,14 @@ protected:
         if (m_specterValid)
             return;
         const auto energies = m_tube.getEnergy();
-        const auto weights = m_tube.getSpecter(energies);
-        m_specterDistribution = std::make_shared<SpecterDistribution<T>>(weights, energies);
-        const T heelSpan = std::atan(m_collimation * T { 0.5 } / m_sdd) * T { 2.0 };
-        m_heelFilter = m_modelHeelEffect ? std::make_shared<HeelFilter<T>>(m_tube, heelSpan) : nullptr;
+        m_specterDistribution = std::make_shared<SpecterDistribution<T>>(m_tube.getSpecter(energies), energies);
+        m_heelFilter = m_modelHeelEffect ? std::make_shared<HeelFilter<T>>(m_tube, heelSpan()) : nullptr;
         m_specterValid = true;
     }
+    // take-off angle range the heel table covers: the cone angle of the beam width seen from the focal spot of tube A
+    T heelSpan() const { return std::atan(this->m_p.beamWidth * T { 0.5 } / this->m_p.sdd[0]) * T { 2.0 }; }
 
-    T m_sdd;
-    T m_collimation;
-    T m_fov;
-    T m_startAngle;
-    T m_scanLenght;
     T m_ctdivol = 1;
-    T m_gantryTiltAngle = 0;
     std::uint64_t m_ctdiPhantomDiameter = 320;
     std::shared_ptr<BowTieFilter<T>> m_bowTieFilter;
     Tube<T> m_tube;
@@ -196,23 +204,21 @@ protected:
     bool m_specterValid = false;
 };
 
-// rotating CT source: angular step between exposures, tube current modulation along z (AEC) and
-// around the patient (XCare)
+// rotating CT source: angular step between exposures, tube current modulation along z (AEC) and around the patient (XCare)
 template <Floating T>
 class CTSource : public CTBaseSource<T> {
 public:
-    CTSource() { m_exposureAngleStep = DEG_TO_RAD<T>(); }
-    virtual Exposure<T> getExposure(std::uint64_t i) const override = 0;
+    CTSource() { this->m_p.angleStep = DEG_TO_RAD<T>(); }
 
-    void setExposureAngleStep(T angleStep) { m_exposureAngleStep = std::clamp(std::abs(angleStep), DEG_TO_RAD<T>() / 10, PI_VAL<T>() / 2); }
-    T exposureAngleStep() const { return m_exposureAngleStep; }
+    void setExposureAngleStep(T angleStep) { this->m_p.angleStep = std::clamp(std::abs(angleStep), DEG_TO_RAD<T>() / 10, PI_VAL<T>() / 2); }
+    T exposureAngleStep() const { return this->m_p.angleStep; }
     void setExposureAngleStepDeg(T angleStep) { setExposureAngleStep(angleStep * DEG_TO_RAD<T>()); }
-    T exposureAngleStepDeg() const { return m_exposureAngleStep * RAD_TO_DEG<T>(); }
+    T exposureAngleStepDeg() const { return this->m_p.angleStep * RAD_TO_DEG<T>(); }
 
     void setAecFilter(std::shared_ptr<AECFilter<T>> filter) { m_aecFilter = filter; }
     std::shared_ptr<AECFilter<T>> aecFilter() { return m_aecFilter; }
-    bool useXCareFilter() const { return m_useXCareFilter; }
-    void setUseXCareFilter(bool use) { m_useXCareFilter = use; }
+    bool useXCareFilter() const { return this->m_p.xcare != 0; }
+    void setUseXCareFilter(bool use) { this->m_p.xcare = use ? 1 : 0; }
     XCareFilter<T>& xcareFilter() { return m_xcareFilter; }
     const XCareFilter<T>& xcareFilter() const { return m_xcareFilter; }
 
@@ -221,28 +227,86 @@ public:
         if (m_aecFilter)
             m_aecFilter->updateFromWorld(world);
     }
-    virtual std::uint64_t exposuresPerRotatition() const
-    {
-        constexpr T twoPi = 2 * PI_VAL<T>();
-        return static_cast<std::size_t>(twoPi / m_exposureAngleStep);
-    }
+    virtual std::uint64_t exposuresPerRotatition() const { return this->m_p.tubes * anglesPerRotation(); }
 
-    T m_exposureAngleStep = RAD_TO_DEG<T>();
-    std::shared_ptr<AECFilter<T>> m_aecFilter;
-    XCareFilter<T> m_xcareFilter;
-    bool m_useXCareFilter = false;
+    // the modulation objects are the caller's to change at any time: their current values go into the block when it is read
+    bool describe(model::SourceParams<T>& block, const T*& tubeCurrent) const override
+    {
+        CTBaseSource<T>::describe(block, tubeCurrent);
+        withModulation(block);
+        tubeCurrent = tubeCurrentProfile();
+        return true;
+    }
+    Exposure<T> getExposure(std::uint64_t i) const override
+    {
+        auto block = this->parameters();
+        withModulation(block);
+        model::ExposureValues<T> v;
+        model::evaluate(block, tubeCurrentProfile(), i, v);
+        const auto tables = this->beamTables(block.tubes == 2 ? static_cast<std::uint32_t>(i & 1u) : 0u);
+        return Exposure<T>::fromModel(v, tables.specter, tables.heel, tables.fan);
+    }
+    // mean beam weight over all exposures of the scan
+    T meanBeamWeight() const
+    {
+        auto block = this->parameters();
+        withModulation(block);
+        model::ExposureValues<T> v;
+        T sum = 0;
+        for (std::uint64_t i = 0; i < block.exposures; ++i) {
+            model::evaluate(block, tubeCurrentProfile(), i, v);
+            sum += v.weight;
+        }
+        return sum / block.exposures;
+    }
 
 protected:
-    // per-exposure weight from the two modulations
-    T modulationWeight(T weight, const std::array<T, 3>& pos, T angle) const
+    const T* tubeCurrentProfile() const override { return m_aecFilter ? m_aecFilter->positionIntensity().data() : nullptr; }
+    void withModulation(model::SourceParams<T>& block) const
     {
-        if (m_aecFilter)
-            weight *= m_aecFilter->sampleIntensityWeight(pos);
-        if (m_useXCareFilter)
-            weight *= m_xcareFilter.sampleIntensityWeight(angle);
-        return weight;
+        block.xcareAngle = m_xcareFilter.filterAngle();
+        block.xcareSpan = m_xcareFilter.spanAngle();
+        block.xcareRamp = m_xcareFilter.rampAngle();
+        block.xcareLow = m_xcareFilter.lowWeight();
+        block.aecSize = 0;
+        if (m_aecFilter) {
+            block.aecSize = static_cast<std::uint32_t>(m_aecFilter->positionIntensity().size());
+            block.aecMin = m_aecFilter->positionMin();
+            block.aecMax = m_aecFilter->positionMax();
+            block.aecStep = m_aecFilter->positionStep();
+        }
     }
-    std::uint64_t anglesPerRotation() const { return static_cast<std::uint64_t>(2 * PI_VAL<T>() / m_exposureAngleStep); }
+    std::uint64_t anglesPerRotation() const { return static_cast<std::uint64_t>(2 * PI_VAL<T>() / this->m_p.angleStep); }
+    // table positions of a step-and-shoot scan: the scan length is a whole number of steps, at least one
+    void setAxialStep(T step)
+    {
+        const T steps = this->m_p.scanLength / this->m_p.tableStep;
+        this->m_p.tableStep = std::max(std::abs(step), T { 0.01 });
+        setAxialScanLength(this->m_p.tableStep * steps);
+    }
+    void setAxialScanLength(T scanLenght)
+    {
+        this->m_p.scanLength = std::max(this->m_p.tableStep * std::ceil(std::abs(scanLenght) / this->m_p.tableStep), this->m_p.tableStep);
+    }
+    std::uint64_t axialExposures() const
+    {
+        const std::uint64_t rotations = static_cast<std::uint64_t>(std::round(this->m_p.scanLength / this->m_p.tableStep));
+        return static_cast<std::uint64_t>(PI_VAL<T>() * T { 2 } / this->m_p.angleStep) * rotations * this->m_p.tubes;
+    }
+    std::uint64_t spiralExposures() const
+    {
+        constexpr T twoPi = 2 * PI_VAL<T>();
+        return static_cast<std::uint64_t>(this->m_p.scanLength * twoPi / (this->m_p.beamWidth * this->m_p.pitch * this->m_p.angleStep)) * this->m_p.tubes;
+    }
+    void becomeAxialTwin(T scanLenght) // a spiral scan's parameters reinterpreted as step-and-shoot with step = beam width
+    {
+        this->m_p.motion = model::GANTRY_AXIAL;
+        this->m_p.tableStep = this->m_p.beamWidth;
+        setAxialScanLength(scanLenght);
+    }
+
+    std::shared_ptr<AECFilter<T>> m_aecFilter;
+    XCareFilter<T> m_xcareFilter;
 };
 
 // two tubes 90 degrees apart, exposures alternate A, B, A, B ...
@@ -251,10 +315,13 @@ class CTDualSource : public CTSource<T> {
 public:
     CTDualSource()
     {
-        this->m_type = Source<T>::Type::None;
-        m_sddB = this->m_sdd;
-        m_fovB = this->m_fov;
-        m_startAngleB = this->m_startAngle + PI_VAL<T>() * T { 0.5 };
+        auto& p = this->m_p;
+        p.tubes = 2;
+        p.sdd[1] = p.sdd[0];
+        p.fov[1] = p.fov[0];
+        p.startAngle[1] = p.startAngle[0] + PI_VAL<T>() * T { 0.5 };
+        p.tubeWeight[0] = p.tubeWeight[1] = -1.0;
+        p.spectrum[1] = 1;
         m_tubeB.setAlFiltration(this->m_tube.AlFiltration());
     }
 
@@ -278,78 +345,63 @@ public:
     const Tube<T>& tubeB() const { return m_tubeB; }
 
     T maxPhotonEnergyProduced() const override { return std::max(this->m_tube.voltage(), m_tubeB.voltage()); }
-    std::uint64_t exposuresPerRotatition() const override { return 2 * static_cast<std::size_t>((2 * PI_VAL<T>()) / this->m_exposureAngleStep); }
     void setBowTieFilterB(std::shared_ptr<BowTieFilter<T>> filter) { m_bowTieFilterB = filter; }
     std::shared_ptr<BowTieFilter<T>> bowTieFilterB() { return m_bowTieFilterB; }
     const std::shared_ptr<BowTieFilter<T>> bowTieFilterB() const { return m_bowTieFilterB; }
     void setSourceDetectorDistanceB(T sdd)
     {
         this->m_specterValid = false;
-        m_sddB = std::abs(sdd);
+        this->m_p.sdd[1] = std::abs(sdd);
     }
-    T sourceDetectorDistanceB() const { return m_sddB; }
-    void setFieldOfViewB(T fov) { m_fovB = std::abs(fov); }
-    T fieldOfViewB() const { return m_fovB; }
-    void setStartAngleB(T angle) { m_startAngleB = angle; }
-    T startAngleB() const { return m_startAngleB; }
-    void setStartAngleDegB(T angle) { m_startAngleB = DEG_TO_RAD<T>() * angle; }
-    T startAngleDegB() const { return RAD_TO_DEG<T>() * m_startAngleB; }
+    T sourceDetectorDistanceB() const { return this->m_p.sdd[1]; }
+    void setFieldOfViewB(T fov) { this->m_p.fov[1] = std::abs(fov); }
+    T fieldOfViewB() const { return this->m_p.fov[1]; }
+    void setStartAngleB(T angle) { this->m_p.startAngle[1] = angle; }
+    T startAngleB() const { return this->m_p.startAngle[1]; }
+    void setStartAngleDegB(T angle) { this->m_p.startAngle[1] = DEG_TO_RAD<T>() * angle; }
+    T startAngleDegB() const { return RAD_TO_DEG<T>() * this->m_p.startAngle[1]; }
 
     bool validate() override
     {
         updateSpecterDistribution();
         return this->m_specterValid;
     }
-
-protected:
-    struct TubeSetup {
-        T sdd, startAngle, fov, weight;
-        const BeamFilter<T>* bowtie;
-        const SpecterDistribution<T>* specter;
-        const HeelFilter<T>* heel;
-    };
-    TubeSetup tubeSetup(bool tubeA) const
+    typename Source<T>::BeamTables beamTables(std::uint32_t tube) const override
     {
-        if (tubeA)
-            return { this->m_sdd, this->m_startAngle, this->m_fov, m_tubeAweight, this->m_bowTieFilter.get(), this->m_specterDistribution.get(),
-                this->m_heelFilter.get() };
-        return { m_sddB, m_startAngleB, m_fovB, m_tubeBweight, m_bowTieFilterB.get(), m_specterDistributionB.get(), m_heelFilterB.get() };
+        if (tube == 0)
+            return CTSource<T>::beamTables(0);
+        return { m_specterDistributionB.get(), m_heelFilterB.get(), m_bowTieFilterB.get() };
     }
 
-    // both spectra normalised separately; the tubes' relative output (mAs x unnormalised yield) becomes beam weights
+protected:
+    // each spectrum normalised on its own; the tubes' relative output (mAs x unnormalised yield) becomes the two beam weights,
+    // which average one
     void updateSpecterDistribution() override
     {
         if (this->m_specterValid)
             return;
-        const auto energyA = this->m_tube.getEnergy();
-        const auto energyB = m_tubeB.getEnergy();
-        auto specterA = this->m_tube.getSpecter(energyA, false);
-        auto specterB = m_tubeB.getSpecter(energyB, false);
-        const auto sumA = std::accumulate(specterA.cbegin(), specterA.cend(), T { 0.0 });
-        const auto sumB = std::accumulate(specterB.cbegin(), specterB.cend(), T { 0.0 });
-        const auto weightA = m_tubeAmas * sumA;
-        const auto weightB = m_tubeBmas * sumB;
-        for (auto& v : specterA)
-            v = v / sumA;
-        for (auto& v : specterB)
-            v = v / sumB;
-        m_tubeAweight = weightA * T { 2 } / (weightA + weightB);
-        m_tubeBweight = weightB * T { 2 } / (weightA + weightB);
-        this->m_specterDistribution = std::make_shared<SpecterDistribution<T>>(specterA, energyA);
-        m_specterDistributionB = std::make_shared<SpecterDistribution<T>>(specterB, energyB);
-        const auto heelSpan = std::atan(this->m_collimation * T { 0.5 } / this->m_sdd) * T { 2 };
-        this->m_heelFilter = std::make_shared<HeelFilter<T>>(this->m_tube, heelSpan);
-        m_heelFilterB = std::make_shared<HeelFilter<T>>(m_tubeB, heelSpan);
+        T output[2];
+        std::shared_ptr<SpecterDistribution<T>>* spectrum[2] = { &this->m_specterDistribution, &m_specterDistributionB };
+        const Tube<T>* tubes[2] = { &this->m_tube, &m_tubeB };
+        const T mas[2] = { m_tubeAmas, m_tubeBmas };
+        for (int k = 0; k < 2; ++k) {
+            const auto energies = tubes[k]->getEnergy();
+            auto yield = tubes[k]->getSpecter(energies, false);
+            const auto total = std::accumulate(yield.cbegin(), yield.cend(), T { 0.0 });
+            output[k] = mas[k] * total;
+            for (auto& v : yield)
+                v = v / total;
+            *spectrum[k] = std::make_shared<SpecterDistribution<T>>(yield, energies);
+        }
+        this->m_p.tubeWeight[0] = output[0] * T { 2 } / (output[0] + output[1]);
+        this->m_p.tubeWeight[1] = output[1] * T { 2 } / (output[0] + output[1]);
+        this->m_heelFilter = std::make_shared<HeelFilter<T>>(this->m_tube, this->heelSpan());
+        m_heelFilterB = std::make_shared<HeelFilter<T>>(m_tubeB, this->heelSpan());
         this->m_specterValid = true;
     }
 
-    T m_sddB;
-    T m_fovB;
-    T m_startAngleB;
     T m_tubeAmas = 100.0;
     T m_tubeBmas = 100.0;
-    T m_tubeBweight = -1.0;
-    T m_tubeAweight = -1.0;
     std::shared_ptr<BowTieFilter<T>> m_bowTieFilterB;
     Tube<T> m_tubeB;
     std::shared_ptr<SpecterDistribution<T>> m_specterDistributionB;
@@ -362,45 +414,20 @@ public:
     CTAxialSource()
     {
         this->m_type = Source<T>::Type::CTAxial;
-        m_step = this->m_collimation;
-        this->m_scanLenght = m_step;
+        this->m_p.tableStep = this->m_p.beamWidth;
+        this->m_p.scanLength = this->m_p.tableStep;
     }
-    CTAxialSource(const CTSpiralSource<T>& other);
+    CTAxialSource(const CTSpiralSource<T>& spiral);
 
-    Exposure<T> getExposure(std::uint64_t exposureIndex) const override
-    {
-        const std::uint64_t perRotation = this->anglesPerRotation();
-        const std::uint64_t rotation = exposureIndex / perRotation;
-        const auto angle = this->m_startAngle + this->m_exposureAngleStep * (exposureIndex - (rotation * perRotation));
-        const auto frame = this->gantryFrame(this->m_sdd, angle, m_step * rotation);
-        const T weight = this->modulationWeight(T { 1 }, frame.position, angle);
-        return Exposure<T>(frame.position, frame.cosines, this->openingAngles(this->m_fov, this->m_sdd), this->m_historiesPerExposure, weight,
-            this->m_specterDistribution.get(), this->m_heelFilter.get(), this->m_bowTieFilter.get());
-    }
-
-    void setStep(T step)
-    {
-        const auto absStep = std::abs(step);
-        const auto nSteps = this->m_scanLenght / m_step;
-        m_step = absStep > 0.01 ? absStep : 0.01;
-        setScanLenght(m_step * nSteps);
-    }
-    T step() const { return m_step; }
-    void setScanLenght(T scanLenght) override { this->m_scanLenght = std::max(m_step * std::ceil(std::abs(scanLenght) / m_step), m_step); }
-
-    std::uint64_t totalExposures() const override
-    {
-        const std::uint64_t rotations = static_cast<std::uint64_t>(std::round(this->m_scanLenght / m_step));
-        return static_cast<std::uint64_t>(PI_VAL<T>() * T { 2 } / this->m_exposureAngleStep) * rotations;
-    }
+    void setStep(T step) { this->setAxialStep(step); }
+    T step() const { return this->m_p.tableStep; }
+    void setScanLenght(T scanLenght) override { this->setAxialScanLength(scanLenght); }
+    std::uint64_t totalExposures() const override { return this->axialExposures(); }
     T getCalibrationValue(LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr) const override
     {
-        auto copy = *this;
-        return CTSource<T>::ctCalibration(copy, model, progressBar);
+        auto twin = *this;
+        return CTSource<T>::ctCalibration(twin, model, progressBar);
     }
-
-private:
-    T m_step;
 };
 
 template <Floating T = double>
@@ -409,37 +436,20 @@ public:
     CTSpiralSource()
     {
         this->m_type = Source<T>::Type::CTSpiral;
-        m_pitch = 1.0;
+        this->m_p.motion = model::GANTRY_SPIRAL;
+        this->m_p.pitch = 1.0;
     }
 
-    Exposure<T> getExposure(std::uint64_t exposureIndex) const override
-    {
-        constexpr T twoPi = T { 2 } * PI_VAL<T>();
-        const auto angle = this->m_startAngle + this->m_exposureAngleStep * exposureIndex;
-        const T zAdvance = (exposureIndex * this->m_exposureAngleStep) * this->m_collimation * m_pitch / twoPi;
-        const auto frame = this->gantryFrame(this->m_sdd, angle, zAdvance);
-        const T weight = this->modulationWeight(T { 1.0 }, frame.position, angle);
-        return Exposure<T>(frame.position, frame.cosines, this->openingAngles(this->m_fov, this->m_sdd), this->m_historiesPerExposure, weight,
-            this->m_specterDistribution.get(), this->m_heelFilter.get(), this->m_bowTieFilter.get());
-    }
-
-    void setPitch(T pitch) { m_pitch = std::max(T { 0.01 }, pitch); }
-    T pitch() const { return m_pitch; }
-    void setScanLenght(T scanLenght) override { this->m_scanLenght = std::max(std::abs(scanLenght), this->m_collimation * m_pitch * T { 0.5 }); }
-    std::uint64_t totalExposures() const override
-    {
-        constexpr T twoPi = 2 * PI_VAL<T>();
-        return static_cast<std::uint64_t>(this->m_scanLenght * twoPi / (this->m_collimation * m_pitch * this->m_exposureAngleStep));
-    }
-    // CTDIvol of a spiral = CTDIw / pitch: calibrate the equivalent axial scan, then scale
+    void setPitch(T pitch) { this->m_p.pitch = std::max(T { 0.01 }, pitch); }
+    T pitch() const { return this->m_p.pitch; }
+    void setScanLenght(T scanLenght) override { this->m_p.scanLength = std::max(std::abs(scanLenght), this->m_p.beamWidth * this->m_p.pitch * T { 0.5 }); }
+    std::uint64_t totalExposures() const override { return this->spiralExposures(); }
+    // CTDIvol of a spiral = CTDIw / pitch: calibrate the axial twin, then scale
     T getCalibrationValue(LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr) const override
     {
-        CTAxialSource<T> copy = *this;
-        return this->ctCalibration(copy, model, progressBar) * m_pitch;
+        CTAxialSource<T> twin = *this;
+        return this->ctCalibration(twin, model, progressBar) * this->m_p.pitch;
     }
-
-private:
-    T m_pitch;
 };
 
 template <Floating T = double>
@@ -448,47 +458,20 @@ public:
     CTAxialDualSource()
     {
         this->m_type = Source<T>::Type::CTDual;
-        m_step = this->m_collimation;
-        this->m_scanLenght = m_step;
+        this->m_p.tableStep = this->m_p.beamWidth;
+        this->m_p.scanLength = this->m_p.tableStep;
     }
-    CTAxialDualSource(const CTSpiralDualSource<T>& other);
+    CTAxialDualSource(const CTSpiralDualSource<T>& spiral);
 
-    Exposure<T> getExposure(std::uint64_t exposureIndexTotal) const override
-    {
-        const std::uint64_t exposureIndex = exposureIndexTotal / 2;
-        const auto tube = this->tubeSetup(exposureIndexTotal % 2 == 0);
-        const std::uint64_t perRotation = this->anglesPerRotation();
-        const std::uint64_t rotation = exposureIndex / perRotation;
-        const auto angle = tube.startAngle + this->m_exposureAngleStep * (exposureIndex - (rotation * perRotation));
-        // the focal-spot radius is tube A's for both tubes, as in the reference
-        const auto frame = this->gantryFrame(this->m_sdd, angle, m_step * rotation);
-        const T weight = this->modulationWeight(tube.weight, frame.position, angle);
-        return Exposure<T>(frame.position, frame.cosines, this->openingAngles(tube.fov, tube.sdd), this->m_historiesPerExposure, weight, tube.specter,
-            tube.heel, tube.bowtie);
-    }
-
-    void setStep(T step)
-    {
-        const auto absStep = std::abs(step);
-        const auto nSteps = this->m_scanLenght / m_step;
-        m_step = absStep > 0.01 ? absStep : 0.01;
-        setScanLenght(m_step * nSteps);
-    }
-    T step() const { return m_step; }
-    void setScanLenght(T scanLenght) override { this->m_scanLenght = std::max(m_step * std::ceil(std::abs(scanLenght) / m_step), m_step); }
-    std::uint64_t totalExposures() const override
-    {
-        const std::uint64_t rotations = static_cast<std::uint64_t>(std::round(this->m_scanLenght / m_step));
-        return static_cast<std::uint64_t>(PI_VAL<T>() * T { 2 } / this->m_exposureAngleStep) * rotations * 2;
-    }
+    void setStep(T step) { this->setAxialStep(step); }
+    T step() const { return this->m_p.tableStep; }
+    void setScanLenght(T scanLenght) override { this->setAxialScanLength(scanLenght); }
+    std::uint64_t totalExposures() const override { return this->axialExposures(); }
     T getCalibrationValue(LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr) const override
     {
-        auto copy = *this;
-        return this->ctCalibration(copy, model, progressBar);
+        auto twin = *this;
+        return this->ctCalibration(twin, model, progressBar);
     }
-
-private:
-    T m_step;
 };
 
 template <Floating T = double>
@@ -497,86 +480,63 @@ public:
     CTSpiralDualSource()
     {
         this->m_type = Source<T>::Type::CTDual;
-        m_pitch = 1.0;
+        this->m_p.motion = model::GANTRY_SPIRAL;
+        this->m_p.pitch = 1.0;
     }
 
-    Exposure<T> getExposure(std::uint64_t exposureIndexTotal) const override
-    {
-        constexpr T twoPi = T { 2 } * PI_VAL<T>();
-        const std::uint64_t exposureIndex = exposureIndexTotal / 2;
-        const auto tube = this->tubeSetup(exposureIndexTotal % 2 == 0);
-        const auto angle = tube.startAngle + this->m_exposureAngleStep * exposureIndex;
-        const T zAdvance = (exposureIndex * this->m_exposureAngleStep) * this->m_collimation * m_pitch / twoPi;
-        const auto frame = this->gantryFrame(this->m_sdd, angle, zAdvance);
-        const T weight = this->modulationWeight(tube.weight, frame.position, angle);
-        return Exposure<T>(frame.position, frame.cosines, this->openingAngles(tube.fov, tube.sdd), this->m_historiesPerExposure, weight, tube.specter,
-            tube.heel, tube.bowtie);
-    }
-    std::uint64_t totalExposures() const override
-    {
-        const auto single = static_cast<std::uint64_t>(this->scanLenght() * 2 * PI_VAL<T>() / (this->collimation() * pitch() * this->exposureAngleStep()));
-        return single * 2;
-    }
+    std::uint64_t totalExposures() const override { return this->spiralExposures(); }
     T getCalibrationValue(LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr) const override
     {
-        CTAxialDualSource<T> copy = *this;
-        return CTSource<T>::ctCalibration(copy, model, progressBar) * m_pitch;
+        CTAxialDualSource<T> twin = *this;
+        return CTSource<T>::ctCalibration(twin, model, progressBar) * this->m_p.pitch;
     }
-    T pitch() const { return m_pitch; }
-    void setPitch(T pitch) { m_pitch = std::max(T { 0.01 }, pitch); }
+    T pitch() const { return this->m_p.pitch; }
+    void setPitch(T pitch) { this->m_p.pitch = std::max(T { 0.01 }, pitch); }
     void setScanLenght(T scanLenght) override
     {
         CTBaseSource<T>::setScanLenght(std::max(std::abs(scanLenght), this->collimation() * pitch() * T { 0.5 }));
     }
-
-private:
-    T m_pitch = 1.0;
 };
 
 template <Floating T>
-CTAxialSource<T>::CTAxialSource(const CTSpiralSource<T>& other)
-    : CTSource<T>(other)
+CTAxialSource<T>::CTAxialSource(const CTSpiralSource<T>& spiral)
+    : CTSource<T>(spiral)
 {
-    this->m_step = this->m_collimation;
-    setScanLenght(other.scanLenght());
+    this->becomeAxialTwin(spiral.scanLenght());
 }
 
 template <Floating T>
-CTAxialDualSource<T>::CTAxialDualSource(const CTSpiralDualSource<T>& other)
-    : CTDualSource<T>(other)
+CTAxialDualSource<T>::CTAxialDualSource(const CTSpiralDualSource<T>& spiral)
+    : CTDualSource<T>(spiral)
 {
-    m_step = this->m_collimation;
-    setScanLenght(other.scanLenght());
+    this->becomeAxialTwin(spiral.scanLenght());
 }
 
-// scout view: the tube parked at the start angle while the table moves through the scan length
+// scout view: the tube parked at the start angle while the table moves through the scan length, one exposure per millimetre
 template <Floating T>
 class CTTopogramSource : public CTBaseSource<T> {
 public:
-    CTTopogramSource() { this->m_type = Source<T>::Type::CTTopogram; }
-
-    Exposure<T> getExposure(std::uint64_t i) const override
+    CTTopogramSource()
     {
-        const auto step = this->scanLenght() / (totalExposures() - 1);
-        const auto frame = this->gantryFrame(this->m_sdd, this->m_startAngle, step * i);
-        return Exposure<T>(frame.position, frame.cosines, this->openingAngles(this->m_fov, this->m_sdd), this->m_historiesPerExposure, T { 1 },
-            this->m_specterDistribution.get(), this->m_heelFilter.get(), this->m_bowTieFilter.get());
+        this->m_type = Source<T>::Type::CTTopogram;
+        this->m_p.motion = model::GANTRY_TOPOGRAM;
     }
+
     std::uint64_t totalExposures() const override { return std::max(static_cast<std::uint64_t>(std::ceil(this->scanLenght())), std::uint64_t { 1 }); }
 
-    // calibrated through an axial scan of equal collimation whose CTDIvol is scaled by scan length / collimation
+    // calibrated through an axial scan of equal beam width whose CTDIvol is scaled by scan length / beam width
     T getCalibrationValue(LOWENERGYCORRECTION model, ProgressBar<T>* progressBar = nullptr) const override
     {
-        CTAxialSource<T> copy;
-        static_cast<CTBaseSource<T>&>(copy) = *this;
-        copy.setCtdiVol(this->ctdiVol() * this->scanLenght() / this->collimation());
-        copy.setScanLenght(0);
-        copy.setStep(this->m_collimation);
-        constexpr auto maxStep = (2 * PI_VAL<T>()) / 72;
-        copy.setExposureAngleStep(std::min(2 * PI_VAL<T>() / totalExposures(), maxStep));
+        CTAxialSource<T> twin;
+        twin.adoptBaseOf(*this);
+        twin.setCtdiVol(this->ctdiVol() * this->scanLenght() / this->collimation());
+        twin.setScanLenght(0);
+        twin.setStep(this->collimation());
+        constexpr auto coarsest = (2 * PI_VAL<T>()) / 72;
+        twin.setExposureAngleStep(std::min(2 * PI_VAL<T>() / totalExposures(), coarsest));
         const auto exposures = this->totalExposures();
-        const auto factor = CTSource<T>::ctCalibration(copy, model, progressBar);
-        return (factor * exposures) / copy.totalExposures();
+        const auto factor = CTSource<T>::ctCalibration(twin, model, progressBar);
+        return (factor * exposures) / twin.totalExposures();
     }
 };
 }

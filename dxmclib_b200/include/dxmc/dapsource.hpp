@@ -1,6 +1,7 @@
-// dapsource.hpp — tube-based projection sources calibrated by dose-area product: DAPSource and its two concrete
-// forms DXSource (radiography) and CBCTSource (cone-beam rotation); reference include/dxmc/source.hpp:374-787.
-// Included by dxmc/source.hpp.
+// dapsource.hpp — tube-based projection sources calibrated by dose-area product: DAPSource, DXSource (radiography) and
+// CBCTSource (cone-beam rotation). API of reference include/dxmc/source.hpp:374-787; the state is the parameter block of
+// dxmc/sourcemodel.hpp (the focal spot sits `focalOffset` upstream of Source::position along the beam; a cone-beam scan is an
+// ORBIT about the y cosine), the classes are setters over it. Included by dxmc/source.hpp.
 #pragma once
 #include "dxmc/sourcebase.hpp"
 
@@ -11,10 +12,10 @@ class DAPSource : public Source<T> {
 public:
     DAPSource()
     {
-        m_fieldSize = { 100.0, 100.0 };
-        applyFieldSize(m_fieldSize);
         m_tube.setAlFiltration(2.0);
-        this->setDirectionCosines(zeroDirectionCosines());
+        this->m_p.spectrum[0] = 0;
+        this->setDirectionCosines(beamAlongY());
+        setFieldSize({ 100.0, 100.0 });
     }
 
     Tube<T>& tube()
@@ -25,88 +26,83 @@ public:
     const Tube<T>& tube() const { return m_tube; }
     T maxPhotonEnergyProduced() const override { return m_tube.voltage(); }
 
-    void setCollimationAngles(const std::array<T, 2>& angles) { applyCollimation({ std::abs(angles[0]), std::abs(angles[1]) }); }
-    const std::array<T, 2>& collimationAngles() const { return m_collimationAngles; }
-    void setCollimationAnglesDeg(const std::array<T, 2>& angles)
+    // field size at the detector <-> full opening angles; either setter keeps the other quantity consistent
+    void setCollimationAngles(const std::array<T, 2>& angles)
     {
-        applyCollimation({ std::abs(angles[0]) * DEG_TO_RAD<T>(), std::abs(angles[1]) * DEG_TO_RAD<T>() });
+        for (std::size_t k = 0; k < 2; ++k) {
+            m_opening[k] = std::abs(angles[k]);
+            m_fieldSize[k] = std::tan(m_opening[k] / 2) * m_sdd * 2;
+        }
+        openingChanged();
     }
-    const std::array<T, 2> collimationAnglesDeg() const { return { m_collimationAngles[0] * RAD_TO_DEG<T>(), m_collimationAngles[1] * RAD_TO_DEG<T>() }; }
-
-    void setFieldSize(const std::array<T, 2>& mm) { applyFieldSize({ std::abs(mm[0]), std::abs(mm[1]) }); }
+    const std::array<T, 2>& collimationAngles() const { return m_opening; }
+    void setCollimationAnglesDeg(const std::array<T, 2>& angles) { setCollimationAngles({ angles[0] * DEG_TO_RAD<T>(), angles[1] * DEG_TO_RAD<T>() }); }
+    const std::array<T, 2> collimationAnglesDeg() const { return { m_opening[0] * RAD_TO_DEG<T>(), m_opening[1] * RAD_TO_DEG<T>() }; }
+    void setFieldSize(const std::array<T, 2>& mm)
+    {
+        for (std::size_t k = 0; k < 2; ++k) {
+            m_fieldSize[k] = std::abs(mm[k]);
+            m_opening[k] = std::atan(m_fieldSize[k] * T { 0.5 } / m_sdd) * T { 2 };
+        }
+        openingChanged();
+    }
     const std::array<T, 2>& fieldSize() const { return m_fieldSize; }
     void setSourceDetectorDistance(T mm)
     {
         m_sdd = std::abs(mm);
-        applyFieldSize(m_fieldSize);
+        setFieldSize(m_fieldSize);
+        this->m_p.focalOffset = focalDistance();
     }
     T sourceDetectorDistance() const { return m_sdd; }
 
-    // primary: rotation about z; secondary: cranio-caudal tilt; then the tube rotation about the beam
+    // Orientation of the beam frame from two patient angles and the tube's own rotation: start with the beam along +y,
+    // turn about z (primary), tip about x (secondary, kept short of +-90 degrees), then spin about the beam.
     void setSourceAngles(T primaryAngle, T secondaryAngle)
     {
-        constexpr T eps = 1E-6;
-        constexpr T halfPi = PI_VAL<T>() / 2;
-        if (secondaryAngle > halfPi - eps)
-            secondaryAngle = halfPi - eps;
-        if (secondaryAngle < -halfPi + eps)
-            secondaryAngle = -halfPi + eps;
+        constexpr T margin = 1E-6;
+        constexpr T quarterTurn = PI_VAL<T>() / 2;
+        secondaryAngle = std::min(std::max(secondaryAngle, margin - quarterTurn), quarterTurn - margin);
         while (primaryAngle > PI_VAL<T>())
             primaryAngle -= PI_VAL<T>();
         while (primaryAngle < -PI_VAL<T>())
             primaryAngle += PI_VAL<T>();
-
-        auto cos = zeroDirectionCosines();
-        const std::array<T, 3> z = { .0, .0, 1.0 };
-        const std::array<T, 3> x = { 1.0, .0, .0 };
-        vectormath::rotate(cos.data(), z.data(), primaryAngle);
-        vectormath::rotate(&cos[3], z.data(), primaryAngle);
-        vectormath::rotate(cos.data(), x.data(), -secondaryAngle);
-        vectormath::rotate(&cos[3], x.data(), -secondaryAngle);
-        std::array<T, 3> beam;
-        vectormath::cross(cos.data(), beam.data());
-        vectormath::rotate(cos.data(), beam.data(), m_tubeRotationAngle);
-        vectormath::rotate(&cos[3], beam.data(), m_tubeRotationAngle);
-        this->setDirectionCosines(cos);
+        auto frame = beamAlongY();
+        const std::array<T, 3> zAxis = { .0, .0, 1.0 }, xAxis = { 1.0, .0, .0 };
+        turnFrame(frame, zAxis.data(), primaryAngle);
+        turnFrame(frame, xAxis.data(), -secondaryAngle);
+        spinAboutBeam(frame, m_tubeRotationAngle);
+        this->setDirectionCosines(frame);
     }
     void setSourceAngles(const std::array<T, 2>& angles) { setSourceAngles(angles[0], angles[1]); }
+    // the two patient angles back from the frame: undo the tube spin, read them off the beam direction
     std::array<T, 2> sourceAngles() const
     {
-        constexpr T eps = 1E-6;
-        auto cos = this->directionCosines();
+        constexpr T margin = 1E-6;
+        auto frame = this->directionCosines();
+        spinAboutBeam(frame, -m_tubeRotationAngle);
         std::array<T, 3> beam;
-        vectormath::cross(cos.data(), beam.data());
-        vectormath::rotate(cos.data(), beam.data(), -m_tubeRotationAngle);
-        vectormath::rotate(&cos[3], beam.data(), -m_tubeRotationAngle);
-        vectormath::cross(cos.data(), beam.data());
-        const T xy = std::sqrt(beam[0] * beam[0] + beam[1] * beam[1]);
-        if (std::abs(xy) < eps)
+        vectormath::cross(frame.data(), beam.data());
+        if (std::abs(std::sqrt(beam[0] * beam[0] + beam[1] * beam[1])) < margin)
             return { 0, beam[2] > 0 ? -PI_VAL<T>() / 2 : PI_VAL<T>() / 2 };
         const T primary = std::asin(-beam[0]);
-        const T zy = std::sqrt(beam[2] * beam[2] + beam[1] * beam[1]);
-        if (std::abs(zy) < eps)
+        const T inYZ = std::sqrt(beam[2] * beam[2] + beam[1] * beam[1]);
+        if (std::abs(inYZ) < margin)
             return { primary, 0 };
-        return { primary, -std::asin(beam[2] / zy) };
+        return { primary, -std::asin(beam[2] / inYZ) };
     }
     void setSourceAnglesDeg(T primaryAngle, T secondaryAngle) { setSourceAngles(primaryAngle * DEG_TO_RAD<T>(), secondaryAngle * DEG_TO_RAD<T>()); }
     void setSourceAnglesDeg(const std::array<T, 2>& angles) { setSourceAnglesDeg(angles[0], angles[1]); }
     std::array<T, 2> sourceAnglesDeg() const
     {
-        auto a = sourceAngles();
-        a[0] *= RAD_TO_DEG<T>();
-        a[1] *= RAD_TO_DEG<T>();
-        return a;
+        const auto a = sourceAngles();
+        return { a[0] * RAD_TO_DEG<T>(), a[1] * RAD_TO_DEG<T>() };
     }
 
     void setTubeRotation(T angle)
     {
-        const T diff = angle - m_tubeRotationAngle;
-        auto cos = this->directionCosines();
-        std::array<T, 3> beam;
-        vectormath::cross(cos.data(), beam.data());
-        vectormath::rotate(cos.data(), beam.data(), diff);
-        vectormath::rotate(&cos[3], beam.data(), diff);
-        this->setDirectionCosines(cos);
+        auto frame = this->directionCosines();
+        spinAboutBeam(frame, angle - m_tubeRotationAngle);
+        this->setDirectionCosines(frame);
         m_tubeRotationAngle = angle;
     }
     T tubeRotation() const { return m_tubeRotationAngle; }
@@ -120,63 +116,67 @@ public:
     }
     T dap() const { return m_dap; }
 
-    // air kerma per emitted photon from the normalised spectrum against the requested DAP
+    // requested dose-area product over the air kerma the run's photons carry (normalised spectrum x mass energy absorption of air)
     T getCalibrationValue(LOWENERGYCORRECTION, ProgressBar<T>* = nullptr) const override
     {
-        const auto specter = tube().getSpecter(true);
         const Material air("Air, Dry (near sea level)");
-        T calcOutput = 0.0;
-        for (const auto& [keV, weight] : specter) {
-            const T massAbsorb = air.getMassEnergyAbsorbtion(keV);
-            calcOutput += keV * weight * massAbsorb;
+        T kermaPerPhoton = 0.0;
+        for (const auto& [keV, weight] : tube().getSpecter(true)) {
+            const T absorption = air.getMassEnergyAbsorbtion(keV);
+            kermaPerPhoton += keV * weight * absorption;
         }
-        calcOutput *= this->totalExposures() * this->historiesPerExposure();
-        return m_dap / calcOutput;
+        return m_dap / (kermaPerPhoton * (this->totalExposures() * this->historiesPerExposure()));
     }
 
     bool isValid() const override { return m_specterValid; }
     bool validate() override
     {
-        refreshSpectrum();
+        if (!m_specterValid) {
+            const auto energies = m_tube.getEnergy();
+            m_specterDistribution = std::make_shared<SpecterDistribution<T>>(m_tube.getSpecter(energies), energies);
+            m_heelFilter = m_modelHeelEffect ? std::make_shared<HeelFilter<T>>(m_tube, m_opening[1]) : nullptr;
+            this->m_p.heel[0] = m_heelFilter ? 0 : -1;
+            m_specterValid = true;
+        }
         return m_specterValid;
     }
     void setModelHeelEffect(bool on) { m_modelHeelEffect = on; }
     bool modelHeelEffect() const { return m_modelHeelEffect; }
+    typename Source<T>::BeamTables beamTables(std::uint32_t) const override { return { m_specterDistribution.get(), m_heelFilter.get(), nullptr }; }
 
 protected:
-    void applyFieldSize(const std::array<T, 2>& fieldSize)
+    virtual T focalDistance() const { return m_sdd; } // how far upstream of Source::position the focal spot sits
+    const std::array<T, 3> focalSpot() const
     {
-        for (std::size_t i = 0; i < 2; ++i) {
-            m_fieldSize[i] = fieldSize[i];
-            m_collimationAngles[i] = std::atan(m_fieldSize[i] * T { 0.5 } / m_sdd) * T { 2 };
-        }
+        std::array<T, 3> beam, spot;
+        vectormath::cross(this->m_p.cosines, beam.data());
+        for (std::size_t k = 0; k < 3; ++k)
+            spot[k] = this->m_p.position[k] - beam[k] * this->m_p.focalOffset;
+        return spot;
+    }
+    void openingChanged()
+    {
+        this->setOpening(m_opening[0], m_opening[1]);
         m_specterValid = false;
     }
-    void applyCollimation(const std::array<T, 2>& angles)
+    static void turnFrame(std::array<T, 6>& frame, const T* axis, T angle)
     {
-        for (std::size_t i = 0; i < 2; ++i) {
-            m_collimationAngles[i] = angles[i];
-            m_fieldSize[i] = std::tan(m_collimationAngles[i] / 2) * m_sdd * 2;
-        }
-        m_specterValid = false;
+        vectormath::rotate(frame.data(), axis, angle);
+        vectormath::rotate(frame.data() + 3, axis, angle);
     }
-    void refreshSpectrum()
+    static void spinAboutBeam(std::array<T, 6>& frame, T angle)
     {
-        if (m_specterValid)
-            return;
-        const auto energies = m_tube.getEnergy();
-        const auto weights = m_tube.getSpecter(energies);
-        m_specterDistribution = std::make_shared<SpecterDistribution<T>>(weights, energies);
-        m_heelFilter = m_modelHeelEffect ? std::make_shared<HeelFilter<T>>(m_tube, m_collimationAngles[1]) : nullptr;
-        m_specterValid = true;
+        std::array<T, 3> beam;
+        vectormath::cross(frame.data(), beam.data());
+        turnFrame(frame, beam.data(), angle);
     }
-    // beam along +y, anode-cathode along z; setSourceAngles depends on this choice
-    std::array<T, 6> zeroDirectionCosines() const { return { -1.0, .0, .0, .0, .0, 1.0 }; }
+    // anode-cathode axis along z; setSourceAngles is defined relative to this frame
+    static std::array<T, 6> beamAlongY() { return { -1.0, .0, .0, .0, .0, 1.0 }; }
 
     T m_sdd = 1000.0;
     T m_dap = 1.0; // Gy cm2
-    std::array<T, 2> m_fieldSize;
-    std::array<T, 2> m_collimationAngles;
+    std::array<T, 2> m_fieldSize { 100.0, 100.0 };
+    std::array<T, 2> m_opening { 0, 0 };
     Tube<T> m_tube;
     T m_tubeRotationAngle = 0.0;
     std::shared_ptr<SpecterDistribution<T>> m_specterDistribution;
@@ -188,45 +188,34 @@ protected:
 template <Floating T = double>
 class DXSource final : public DAPSource<T> {
 public:
-    DXSource() { this->m_type = Source<T>::Type::DX; }
-
-    Exposure<T> getExposure(std::uint64_t) const override
+    DXSource()
     {
-        return Exposure<T>(tubePosition(), this->m_directionCosines, this->m_collimationAngles, this->m_historiesPerExposure, T { 1 },
-            this->m_specterDistribution.get(), this->m_heelFilter.get());
+        this->m_type = Source<T>::Type::DX;
+        this->m_p.exposures = 1000;
+        this->m_p.focalOffset = this->focalDistance();
     }
-    std::uint64_t totalExposures() const override { return m_totalExposures; }
-    void setTotalExposures(std::uint64_t exposures) { m_totalExposures = std::max(exposures, std::uint64_t { 1 }); }
-
-    // focal spot: source-detector distance upstream of the reference position
-    const std::array<T, 3> tubePosition() const
-    {
-        std::array<T, 3> beam, pos;
-        vectormath::cross(this->m_directionCosines.data(), beam.data());
-        for (std::size_t i = 0; i < 3; ++i)
-            pos[i] = this->m_position[i] - beam[i] * this->m_sdd;
-        return pos;
-    }
-
-private:
-    std::uint64_t m_totalExposures = 1000;
+    std::uint64_t totalExposures() const override { return this->m_p.exposures; }
+    void setTotalExposures(std::uint64_t exposures) { this->m_p.exposures = std::max(exposures, std::uint64_t { 1 }); }
+    const std::array<T, 3> tubePosition() const { return this->focalSpot(); }
 };
 
-// cone-beam CT: the DX geometry stepped about the y direction cosine through the isocentre
+// cone-beam CT: the radiography geometry with the focal spot half a source-detector distance from the isocentre, stepped about
+// the y cosine
 template <Floating T = double>
 class CBCTSource final : public DAPSource<T> {
 public:
     CBCTSource()
     {
         this->m_type = Source<T>::Type::CBCT;
+        this->m_p.motion = model::ORBIT;
         this->setSourceDetectorDistance(500.0);
+        setStepAngle(PI_VAL<T>() / T { 180 });
     }
 
-    const std::array<T, 3> rotationAxis() const { return { this->m_directionCosines[3], this->m_directionCosines[4], this->m_directionCosines[5] }; }
-
+    const std::array<T, 3> rotationAxis() const { return { this->m_p.cosines[3], this->m_p.cosines[4], this->m_p.cosines[5] }; }
     void setSpanAngle(const T spanAngle)
     {
-        m_angleSpan = std::max(spanAngle, m_angleStep);
+        m_angleSpan = std::max(spanAngle, this->m_p.orbitStep);
         recount();
     }
     void setSpanAngleDeg(const T spanAngle) { setSpanAngle(spanAngle * DEG_TO_RAD<T>()); }
@@ -234,48 +223,22 @@ public:
     const T spanAngleDeg() const { return m_angleSpan * RAD_TO_DEG<T>(); }
     void setStepAngle(const T stepAngle)
     {
-        constexpr T minStep = PI_VAL<T>() / T { 360 };
-        m_angleStep = std::max(stepAngle, minStep);
+        constexpr T finest = PI_VAL<T>() / T { 360 };
+        this->m_p.orbitStep = std::max(stepAngle, finest);
         recount();
     }
     void setStepAngleDeg(const T stepAngle) { setStepAngle(stepAngle * DEG_TO_RAD<T>()); }
-    const T stepAngle() const { return m_angleStep; }
-    const T stepAngleDeg() const { return m_angleStep * RAD_TO_DEG<T>(); }
+    const T stepAngle() const { return this->m_p.orbitStep; }
+    const T stepAngleDeg() const { return this->m_p.orbitStep * RAD_TO_DEG<T>(); }
+    std::uint64_t totalExposures() const override { return this->m_p.exposures; }
+    const std::array<T, 3> tubePosition() const { return this->focalSpot(); }
 
-    Exposure<T> getExposure(std::uint64_t i) const override
-    {
-        const auto angle = i * m_angleStep;
-        const auto tube = tubePosition();
-        const auto& iso = this->position();
-        const auto axis = rotationAxis();
-        std::array<T, 3> pos;
-        for (std::size_t k = 0; k < 3; ++k)
-            pos[k] = (tube[k] - iso[k]);
-        vectormath::rotate(pos.data(), axis.data(), angle);
-        for (std::size_t k = 0; k < 3; ++k)
-            pos[k] += iso[k];
-        auto cosines = this->m_directionCosines;
-        vectormath::rotate(cosines.data(), axis.data(), angle);
-        vectormath::rotate(&cosines[3], axis.data(), angle);
-        return Exposure<T>(pos, cosines, this->m_collimationAngles, this->m_historiesPerExposure, T { 1 }, this->m_specterDistribution.get(),
-            this->m_heelFilter.get());
-    }
-    std::uint64_t totalExposures() const override { return m_totalExposures; }
-
-    const std::array<T, 3> tubePosition() const
-    {
-        std::array<T, 3> beam, pos;
-        vectormath::cross(this->m_directionCosines.data(), beam.data());
-        for (std::size_t i = 0; i < 3; ++i)
-            pos[i] = this->m_position[i] - beam[i] * this->m_sdd * T { 0.5 };
-        return pos;
-    }
+protected:
+    T focalDistance() const override { return this->m_sdd * T { 0.5 }; }
 
 private:
-    void recount() { m_totalExposures = std::max(static_cast<std::size_t>(m_angleSpan / m_angleStep), std::size_t { 2 }); }
+    void recount() { this->m_p.exposures = std::max(static_cast<std::size_t>(m_angleSpan / this->m_p.orbitStep), std::size_t { 2 }); }
 
-    std::size_t m_totalExposures = 180;
     T m_angleSpan = PI_VAL<T>();
-    T m_angleStep = PI_VAL<T>() / T { 180 };
 };
 }

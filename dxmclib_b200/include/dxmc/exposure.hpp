@@ -9,6 +9,7 @@
 #pragma once
 #include "dxmc/beamfilters.hpp"
 #include "dxmc/dxmcrandom.hpp"
+#include "dxmc/sourcemodel.hpp"
 #include "dxmc/types.hpp"
 #include "dxmc/vectormath.hpp"
 
@@ -40,6 +41,29 @@ public:
     {
         setCollimationAngles(collimationAngles);
         setDirectionCosines(directionCosines);
+    }
+
+    // An exposure evaluated from a source's parameter block (dxmc/sourcemodel.hpp): the values are final (unit cosines, beam
+    // direction), so nothing is normalised again; the tables are the source's objects the indices stand for.
+    static Exposure fromModel(const model::ExposureValues<T>& v, const SpecterDistribution<T>* specterDistribution, const HeelFilter<T>* heelFilter,
+        const BeamFilter<T>* filter)
+    {
+        Exposure e;
+        e.m_nHistories = v.histories;
+        e.m_weight = v.weight;
+        e.m_monoEnergy = v.monoEnergy;
+        e.m_spectrum = specterDistribution;
+        e.m_heel = heelFilter;
+        e.m_fanFilter = filter;
+        for (std::size_t k = 0; k < 4; ++k)
+            e.m_angles[k] = v.collimation[k];
+        for (std::size_t k = 0; k < 3; ++k) {
+            e.m_origin[k] = v.position[k];
+            e.m_beam[k] = v.beam[k];
+        }
+        for (std::size_t k = 0; k < 6; ++k)
+            e.m_frame[k] = v.cosines[k];
+        return e;
     }
 
     // ---- the draw itself (host equivalent of the device birth stage): fan angle about the y cosine, cone angle
@@ -119,14 +143,16 @@ public:
     void subtractPosition(const Vec3& shift) { std::transform(m_origin.begin(), m_origin.end(), shift.begin(), m_origin.begin(), std::minus<T>()); }
 
 private:
-    std::uint64_t m_nHistories;
-    T m_weight;
+    Exposure() = default;
+
+    std::uint64_t m_nHistories = 0;
+    T m_weight = 1;
     T m_monoEnergy { 0 };
     const SpecterDistribution<T>* m_spectrum = nullptr;
     const HeelFilter<T>* m_heel = nullptr;
     const BeamFilter<T>* m_fanFilter = nullptr;
     std::array<T, 4> m_angles {};
-    Vec3 m_origin;
+    Vec3 m_origin {};
     Cosines m_frame {};
     Vec3 m_beam {};
 };

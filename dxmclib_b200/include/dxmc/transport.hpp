@@ -5,9 +5,12 @@
 // middle: where the reference spawns std::thread workers that pull exposures (parallellRun,
 // :765-778), this class flattens the world, the look-up tables, the beam tables and ALL exposures
 // into the POD structs of include/dxmcb200.h and hands them to the CUDA runtime in
-// libdxmcb200.so. There is no CPU path: without a CUDA device the call throws.
+// libdxmcb200.so. There is no CPU path: without a usable CUDA device the call THROWS std::runtime_error (the reference never
+// throws from operator(); a silent all-zero dose from a machine without a GPU would be worse than an exception).
 //
-// Additions (no existing signature changed): setDevice(), setSeed(), lastStats().
+// Additions (no existing signature changed): setDevice(), setSeed(), setTracking(), lastStats().
+// Precision: the device computes in single precision for every T. Transport<double> converts the world's densities and the
+// look-up tables to float on upload and widens the results on download; sources and table builders run in T on the host.
 #pragma once
 #include "dxmc/attenuationlut.hpp"
 #include "dxmc/exposure.hpp"
@@ -25,8 +28,11 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <map>
 #include <memory>
+#include <optional>
+#include <random>
 #include <stdexcept>
 #include <string>
 #include <string_view>
@@ -71,6 +77,22 @@ namespace detail {
         return device;
     }
 
+    // Seed the calibration run of a CT source derives its own from: a Transport constructed while another one is collecting
+    // (CTBaseSource::ctCalibration) takes a hash of the outer run's seed instead of drawing a fresh one, so that a seeded outer
+    // run is reproducible end to end and the two runs never share per-history streams.
+    inline std::optional<std::uint64_t>& inheritedSeed()
+    {
+        thread_local std::optional<std::uint64_t> seed;
+        return seed;
+    }
+    inline std::uint64_t mixSeed(std::uint64_t z)
+    {
+        z += 0x9E3779B97F4A7C15ULL;
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+        return z ^ (z >> 31);
+    }
+
     struct ContextDeleter {
         void operator()(dxmcb200_ctx* c) const { dxmcb200_destroy(c); }
     };
@@ -101,7 +123,10 @@ namespace detail {
         std::vector<Spectrum> spectra;
         std::vector<Heel> heels;
         std::vector<Bowtie> bowties;
-        std::vector<dxmcb200_exposure> exposures;
+        std::vector<dxmcb200_exposure> exposures; // filled on the host only for sources that cannot describe themselves
+        bool described = false; // the exposure table is generated on the device from `source`
+        dxmcb200_source_params source {};
+        std::vector<float> tubeCurrent; // source.aec_size slice intensities
         double maxWeight = 0; // largest possible photon birth weight
     };
 
@@ -141,6 +166,8 @@ public:
         : m_nThreads(std::max<std::uint64_t>(std::thread::hardware_concurrency(), 1))
         , m_device(detail::currentDevice())
     {
+        if (detail::inheritedSeed())
+            m_seed = detail::mixSeed(*detail::inheritedSeed());
     }
 
     // Copyable like the reference's Transport (validation.cpp passes it by value): a copy takes the settings and the
@@ -152,6 +179,8 @@ public:
         , m_lowenergyCorrection(other.m_lowenergyCorrection)
         , m_device(other.m_device)
         , m_seed(other.m_seed)
+        , m_tracking(other.m_tracking)
+        , m_brickMm(other.m_brickMm)
     {
     }
     Transport& operator=(const Transport& other)
@@ -164,6 +193,8 @@ public:
             m_lowenergyCorrection = other.m_lowenergyCorrection;
             m_device = other.m_device;
             m_seed = other.m_seed;
+            m_tracking = other.m_tracking;
+            m_brickMm = other.m_brickMm;
             m_flat = detail::FlatTables {};
             m_totalExposures = m_histories = 0;
         }
@@ -183,9 +214,20 @@ public:
     // ---- B200 additions
     void setDevice(int device) { m_device = device; }
     int device() const { return m_device; }
-    // master seed of the per-history counter streams (the reference seeds from std::random_device)
+    // Master seed of the per-history counter streams. Unset (the default), every call draws a fresh seed from
+    // std::random_device, like the reference's workers do (transport.hpp:749): repeated calls are independent samples and
+    // can be averaged. setSeed makes the call reproducible bit for bit; seed() is the seed of the last (or next seeded) run.
     void setSeed(std::uint64_t seed) { m_seed = seed; }
-    std::uint64_t seed() const { return m_seed; }
+    void clearSeed() { m_seed.reset(); }
+    std::uint64_t seed() const { return m_seed ? *m_seed : m_runSeed; }
+    // 0: the reference's Woodcock loop everywhere; 1 (default): + empty-space traversal through air bricks of about brickMm
+    // (dxmcb200_set_tracking; -1 / 0 keep the library's defaults and environment overrides)
+    void setTracking(int tracking, float brickMm = 0.0f)
+    {
+        m_tracking = tracking;
+        m_brickMm = brickMm;
+    }
+    int tracking() const { return m_tracking; }
     const dxmcb200_stats& lastStats() const { return m_stats; }
 
     template <typename U>
@@ -253,6 +295,14 @@ public:
             throw std::runtime_error("dxmcb200: no usable CUDA device " + std::to_string(m_device) + " (status " + std::to_string(created)
                 + "); this library has no CPU fallback");
         m_ctx.reset(raw);
+        if (m_tracking >= 0)
+            detail::check(m_ctx.get(), dxmcb200_set_tracking(m_ctx.get(), m_tracking, m_brickMm), "set_tracking");
+        if (m_seed) {
+            m_runSeed = *m_seed;
+        } else {
+            std::random_device entropy;
+            m_runSeed = (static_cast<std::uint64_t>(entropy()) << 32) ^ entropy();
+        }
         trace("  create context");
         // The voxel grid goes to the device first, on a helper thread, while this thread builds the per-material
         // tables (form-factor samplers, scatter functions, shells: independent of the grid). The one thing the
@@ -286,7 +336,8 @@ public:
 
         m_flat = detail::FlatTables {};
         flattenLuts(m_flat);
-        flattenExposures(world, *source, m_totalExposures, m_flat);
+        if (!describeSource(world, *source, m_flat))
+            flattenExposures(world, *source, m_totalExposures, m_flat);
         trace("  flatten tables/exposures");
         detail::check(m_ctx.get(), dxmcb200_set_luts(m_ctx.get(), &m_flat.luts), "set_luts");
         uploadBeamTables(m_ctx.get(), m_flat);
@@ -294,7 +345,9 @@ public:
         dxmcb200_suggest_fixed_point(std::max(historiesAllRanks, m_histories), m_flat.maxWeight * static_cast<double>(source->maxPhotonEnergyProduced()),
             &energyBits, &energySqBits);
         detail::check(m_ctx.get(), dxmcb200_set_fixed_point(m_ctx.get(), energyBits, energySqBits), "set_fixed_point");
-        if (!m_flat.exposures.empty())
+        if (m_flat.described) // all exposures evaluated on the device from the source's parameter block
+            detail::check(m_ctx.get(), dxmcb200_generate_exposures(m_ctx.get(), &m_flat.source, m_flat.tubeCurrent.data(), nullptr), "generate_exposures");
+        else if (!m_flat.exposures.empty())
             detail::check(m_ctx.get(), dxmcb200_upload_exposures(m_ctx.get(), m_flat.exposures.data(), m_flat.exposures.size()), "upload_exposures");
         return true;
     }
@@ -347,8 +400,7 @@ public:
         if (progressbar && progressbar->cancel())
             progress.cancel = 1;
         const auto start = std::chrono::system_clock::now();
-        const int ran = dxmcb200_run(m_ctx.get(), m_flat.exposures.data(), begin, end, static_cast<int>(m_lowenergyCorrection), m_seed, &progress.cancel,
-            callback, &progress);
+        const int ran = dxmcb200_run_range(m_ctx.get(), begin, end, static_cast<int>(m_lowenergyCorrection), m_runSeed, &progress.cancel, callback, &progress);
         m_lastRunTime = std::chrono::system_clock::now() - start;
         if (result)
             result->simulationTime = m_lastRunTime;
@@ -368,7 +420,7 @@ public:
         if (!m_ctx)
             throw std::runtime_error("dxmcb200: Transport::runStrided called before prepare");
         const auto start = std::chrono::system_clock::now();
-        const int ran = dxmcb200_run_strided(m_ctx.get(), first, stride, count, static_cast<int>(m_lowenergyCorrection), m_seed);
+        const int ran = dxmcb200_run_strided(m_ctx.get(), first, stride, count, static_cast<int>(m_lowenergyCorrection), m_runSeed);
         m_lastRunTime = std::chrono::system_clock::now() - start;
         detail::check(m_ctx.get(), ran, "run_strided");
         dxmcb200_get_stats(m_ctx.get(), &m_stats);
@@ -390,10 +442,7 @@ public:
         if (m_outputmode == OUTPUTMODE::DOSE) {
             mode = 1;
             if (useSourceDoseCalibration) {
-                const int outer = detail::currentDevice();
-                detail::currentDevice() = m_device; // a CT calibration run constructs its own Transport
-                calibration = static_cast<float>(source->getCalibrationValue(m_lowenergyCorrection, progressbar));
-                detail::currentDevice() = outer;
+                calibration = static_cast<float>(calibrationValue(source, progressbar));
                 result.dose_units = "mGy";
             } else {
                 result.dose_units = "keV/kg";
@@ -421,10 +470,7 @@ public:
             mode = 1;
             units = "keV/kg";
             if (useSourceDoseCalibration) {
-                const int outer = detail::currentDevice();
-                detail::currentDevice() = m_device;
-                calibration = static_cast<float>(source->getCalibrationValue(m_lowenergyCorrection, nullptr));
-                detail::currentDevice() = outer;
+                calibration = static_cast<float>(calibrationValue(source, nullptr));
                 units = "mGy";
             }
         }
@@ -443,6 +489,147 @@ public:
     AttenuationLut<T>& attenuationLut() { return m_attenuationLut; }
 
 protected:
+    // Source::getCalibrationValue with this run's device and a seed derived from this run's for any Transport it constructs
+    T calibrationValue(Source<T>* source, ProgressBar<T>* progressbar) const
+    {
+        struct Scope {
+            int device = detail::currentDevice();
+            std::optional<std::uint64_t> seed = detail::inheritedSeed();
+            ~Scope()
+            {
+                detail::currentDevice() = device;
+                detail::inheritedSeed() = seed;
+            }
+        } restore;
+        detail::currentDevice() = m_device;
+        detail::inheritedSeed() = m_runSeed;
+        return source->getCalibrationValue(m_lowenergyCorrection, progressbar);
+    }
+
+    // The source as a parameter block for device-side exposure generation, with the beam tables its tubes point to collected
+    // once each. False when the source cannot describe itself (a user-defined Source that overrides getExposure only).
+    template <typename U>
+    bool describeSource(const U& world, const Source<T>& source, detail::FlatTables& f) const
+    {
+        model::SourceParams<T> block;
+        const T* profile = nullptr;
+        if (!source.describe(block, profile))
+            return false;
+        model::SourceParams<float> p;
+        p.motion = block.motion;
+        p.tubes = block.tubes;
+        p.exposures = block.exposures;
+        p.histories = block.histories;
+        const auto narrow = [](const auto& from, auto& to) {
+            for (std::size_t k = 0; k < sizeof(to) / sizeof(to[0]); ++k)
+                to[k] = static_cast<float>(from[k]);
+        };
+        narrow(block.position, p.position);
+        narrow(block.cosines, p.cosines);
+        narrow(block.collimation, p.collimation);
+        narrow(block.sdd, p.sdd);
+        narrow(block.fov, p.fov);
+        narrow(block.startAngle, p.startAngle);
+        narrow(block.tubeWeight, p.tubeWeight);
+        p.monoEnergy = static_cast<float>(block.monoEnergy);
+        p.focalOffset = static_cast<float>(block.focalOffset);
+        p.orbitFullTurn = block.orbitFullTurn;
+        p.orbitStep = static_cast<float>(block.orbitStep);
+        p.beamWidth = static_cast<float>(block.beamWidth);
+        p.angleStep = static_cast<float>(block.angleStep);
+        p.pitch = static_cast<float>(block.pitch);
+        p.tableStep = static_cast<float>(block.tableStep);
+        p.tilt = static_cast<float>(block.tilt);
+        p.scanLength = static_cast<float>(block.scanLength);
+        p.xcare = block.xcare;
+        p.xcareAngle = static_cast<float>(block.xcareAngle);
+        p.xcareSpan = static_cast<float>(block.xcareSpan);
+        p.xcareRamp = static_cast<float>(block.xcareRamp);
+        p.xcareLow = static_cast<float>(block.xcareLow);
+        p.aecSize = block.aecSize;
+        p.aecMin = static_cast<float>(block.aecMin);
+        p.aecMax = static_cast<float>(block.aecMax);
+        p.aecStep = static_cast<float>(block.aecStep);
+        p.align = 1;
+        for (std::size_t k = 0; k < 6; ++k)
+            p.worldCosines[k] = static_cast<float>(world.directionCosines()[k]);
+        double currentMax = 1.0; // largest product of the two tube-current modulations
+        if (block.aecSize) {
+            f.tubeCurrent.assign(profile, profile + block.aecSize);
+            currentMax = std::max(0.0, static_cast<double>(*std::max_element(f.tubeCurrent.begin(), f.tubeCurrent.end())));
+        }
+        if (block.xcare) {
+            constexpr double twoPi = 6.283185307179586;
+            currentMax *= std::max(1.0, (twoPi - block.xcareSpan * block.xcareLow + block.xcareLow * block.xcareRamp) / (twoPi - block.xcareSpan + block.xcareRamp));
+        }
+        for (std::uint32_t t = 0; t < block.tubes; ++t) {
+            const auto tables = source.beamTables(t);
+            double w = block.tubes == 2 ? std::abs(static_cast<double>(block.tubeWeight[t])) : 1.0;
+            p.spectrum[t] = p.heel[t] = p.bowtie[t] = -1;
+            if (tables.specter) {
+                p.spectrum[t] = static_cast<std::int32_t>(f.spectra.size());
+                f.spectra.push_back(flatSpectrum(*tables.specter));
+            }
+            if (tables.heel) {
+                p.heel[t] = static_cast<std::int32_t>(f.heels.size());
+                f.heels.push_back(flatHeel(*tables.heel));
+                w *= std::max(1.0, static_cast<double>(*std::max_element(f.heels.back().weights.begin(), f.heels.back().weights.end())));
+            }
+            if (tables.fan) {
+                p.bowtie[t] = static_cast<std::int32_t>(f.bowties.size());
+                f.bowties.push_back(flatFan(*tables.fan));
+                w *= std::max(1.0, static_cast<double>(*std::max_element(f.bowties.back().weights.begin(), f.bowties.back().weights.end())));
+            }
+            f.maxWeight = std::max(f.maxWeight, w * currentMax);
+        }
+        if (f.maxWeight <= 0)
+            f.maxWeight = 1;
+        static_assert(sizeof(p) == sizeof(f.source));
+        std::memcpy(&f.source, &p, sizeof(p));
+        f.described = true;
+        return true;
+    }
+
+    static detail::FlatTables::Spectrum flatSpectrum(const SpecterDistribution<T>& s)
+    {
+        detail::FlatTables::Spectrum fs;
+        detail::appendFloats(fs.probs, s.probabilityData());
+        detail::appendFloats(fs.energies, s.energies());
+        for (auto a : s.aliasingData())
+            fs.alias.push_back(static_cast<std::uint32_t>(a));
+        return fs;
+    }
+    static detail::FlatTables::Heel flatHeel(const HeelFilter<T>& h)
+    {
+        detail::FlatTables::Heel fh;
+        fh.desc.energy_start = static_cast<float>(h.energyStart());
+        fh.desc.energy_step = static_cast<float>(h.energyStep());
+        fh.desc.energy_size = static_cast<std::uint32_t>(h.energySize());
+        fh.desc.angle_start = static_cast<float>(h.angleStart());
+        fh.desc.angle_step = static_cast<float>(h.angleStep());
+        fh.desc.angle_size = static_cast<std::uint32_t>(h.angleSize());
+        detail::appendFloats(fh.weights, h.weights());
+        return fh;
+    }
+    static detail::FlatTables::Bowtie flatFan(const BeamFilter<T>& b)
+    {
+        detail::FlatTables::Bowtie fb;
+        if (const auto* bt = dynamic_cast<const BowTieFilter<T>*>(&b)) {
+            for (const auto& [angle, weight] : bt->data()) {
+                fb.angles.push_back(static_cast<float>(angle));
+                fb.weights.push_back(static_cast<float>(weight));
+            }
+        } else { // any other BeamFilter is tabulated on |angle| in [0, pi/2] (symmetric filters only)
+            constexpr int n = 2048;
+            for (int k = 0; k < n; ++k) {
+                const T a = (PI_VAL<T>() / 2) * k / (n - 1);
+                fb.angles.push_back(static_cast<float>(a));
+                fb.weights.push_back(static_cast<float>(b.sampleIntensityWeight(a)));
+            }
+        }
+        return fb;
+    }
+
     void flattenLuts(detail::FlatTables& f) const
     {
         const auto& lut = m_attenuationLut;
@@ -488,7 +675,7 @@ protected:
     void flattenExposures(const U& world, const Source<T>& source, std::uint64_t totalExposures, detail::FlatTables& f) const
     {
         std::map<const void*, std::int32_t> spectrumIdx, heelIdx, bowtieIdx;
-        std::vector<double> spectrumMax, heelMax, bowtieMax; // per-table largest weight factor
+        std::vector<double> heelMax, bowtieMax; // per-table largest weight factor
         f.exposures.reserve(totalExposures);
         for (std::uint64_t i = 0; i < totalExposures; ++i) {
             auto e = source.getExposure(i);
@@ -510,29 +697,15 @@ protected:
 
             if (const auto* s = e.specterDistribution()) {
                 auto [it, isNew] = spectrumIdx.try_emplace(s, static_cast<std::int32_t>(f.spectra.size()));
-                if (isNew) {
-                    detail::FlatTables::Spectrum fs;
-                    detail::appendFloats(fs.probs, s->probabilityData());
-                    detail::appendFloats(fs.energies, s->energies());
-                    for (auto a : s->aliasingData())
-                        fs.alias.push_back(static_cast<std::uint32_t>(a));
-                    f.spectra.push_back(std::move(fs));
-                }
+                if (isNew)
+                    f.spectra.push_back(flatSpectrum(*s));
                 pod.spectrum = it->second;
             }
             if (const auto* h = e.heelFilter()) {
                 auto [it, isNew] = heelIdx.try_emplace(h, static_cast<std::int32_t>(f.heels.size()));
                 if (isNew) {
-                    detail::FlatTables::Heel fh;
-                    fh.desc.energy_start = static_cast<float>(h->energyStart());
-                    fh.desc.energy_step = static_cast<float>(h->energyStep());
-                    fh.desc.energy_size = static_cast<std::uint32_t>(h->energySize());
-                    fh.desc.angle_start = static_cast<float>(h->angleStart());
-                    fh.desc.angle_step = static_cast<float>(h->angleStep());
-                    fh.desc.angle_size = static_cast<std::uint32_t>(h->angleSize());
-                    detail::appendFloats(fh.weights, h->weights());
-                    heelMax.push_back(*std::max_element(fh.weights.begin(), fh.weights.end()));
-                    f.heels.push_back(std::move(fh));
+                    f.heels.push_back(flatHeel(*h));
+                    heelMax.push_back(*std::max_element(f.heels.back().weights.begin(), f.heels.back().weights.end()));
                 }
                 pod.heel = it->second;
                 w *= std::max(1.0, heelMax[it->second]);
@@ -540,23 +713,8 @@ protected:
             if (const auto* b = e.beamFilter()) {
                 auto [it, isNew] = bowtieIdx.try_emplace(b, static_cast<std::int32_t>(f.bowties.size()));
                 if (isNew) {
-                    detail::FlatTables::Bowtie fb;
-                    if (const auto* bt = dynamic_cast<const BowTieFilter<T>*>(b)) {
-                        for (const auto& [angle, weight] : bt->data()) {
-                            fb.angles.push_back(static_cast<float>(angle));
-                            fb.weights.push_back(static_cast<float>(weight));
-                        }
-                    } else {
-                        // any other BeamFilter is tabulated on |angle| in [0, pi/2] (symmetric filters only)
-                        constexpr int n = 2048;
-                        for (int k = 0; k < n; ++k) {
-                            const T a = (PI_VAL<T>() / 2) * k / (n - 1);
-                            fb.angles.push_back(static_cast<float>(a));
-                            fb.weights.push_back(static_cast<float>(b->sampleIntensityWeight(a)));
-                        }
-                    }
-                    bowtieMax.push_back(*std::max_element(fb.weights.begin(), fb.weights.end()));
-                    f.bowties.push_back(std::move(fb));
+                    f.bowties.push_back(flatFan(*b));
+                    bowtieMax.push_back(*std::max_element(f.bowties.back().weights.begin(), f.bowties.back().weights.end()));
                 }
                 pod.bowtie = it->second;
                 w *= std::max(1.0, bowtieMax[it->second]);
@@ -631,7 +789,10 @@ private:
     OUTPUTMODE m_outputmode = OUTPUTMODE::DOSE;
     LOWENERGYCORRECTION m_lowenergyCorrection = LOWENERGYCORRECTION::LIVERMORE;
     int m_device = 0;
-    std::uint64_t m_seed = 0xD1C02026ULL;
+    std::optional<std::uint64_t> m_seed; // unset: a fresh seed per call
+    std::uint64_t m_runSeed = 0; // seed of the prepared / last run
+    int m_tracking = -1; // -1: library default
+    float m_brickMm = 0.0f;
     dxmcb200_stats m_stats {};
     std::chrono::duration<float> m_lastRunTime {};
     detail::ContextPtr m_ctx;

@@ -119,6 +119,41 @@ typedef struct dxmcb200_exposure {
  * library also prints this line once to stderr when approximate data is first used (DXMCB200_QUIET=1 silences it). */
 const char* dxmcb200_physics_backend(int* approximate);
 
+/* A whole source as one parameter block: what exposure i looks like is a pure function of (block, i), evaluated for all i
+ * on the device by dxmcb200_generate_exposures (replaces the reference's per-exposure virtual call Source::getExposure(i),
+ * source.hpp:102, for every source type it has; the formulas and their reference lines are in
+ * dxmclib_b200/include/dxmc/sourcemodel.hpp, whose model::SourceParams<float> has exactly this layout). */
+enum dxmcb200_source_motion {
+    DXMCB200_SOURCE_FIXED = 0,           /* every exposure identical: pencil, isotropic, DX */
+    DXMCB200_SOURCE_ORBIT = 1,           /* focal spot and frame turn about an axis: isotropic CT, cone-beam CT */
+    DXMCB200_SOURCE_GANTRY_AXIAL = 2,    /* CT gantry, step-and-shoot */
+    DXMCB200_SOURCE_GANTRY_SPIRAL = 3,   /* CT gantry, continuous table feed */
+    DXMCB200_SOURCE_GANTRY_TOPOGRAM = 4  /* CT gantry parked, table moving */
+};
+typedef struct dxmcb200_source_params {
+    uint32_t motion;
+    uint32_t tubes;            /* gantry: 2 = dual source, even exposure indices tube A, odd tube B */
+    uint64_t exposures;
+    uint64_t histories;        /* per exposure */
+    float position[3];         /* Source::position() */
+    float cosines[6];          /* Source::directionCosines() */
+    float collimation[4];      /* FIXED / ORBIT: x0 x1 y0 y1 */
+    float mono_energy;         /* used when spectrum[0] < 0 */
+    float focal_offset;        /* FIXED / ORBIT: focal spot = position - beam * focal_offset */
+    int32_t spectrum[2], heel[2], bowtie[2]; /* beam-table indices per tube, -1 = none */
+    uint32_t orbit_full_turn;  /* 1: angle_i = 2 pi i / exposures about z through the origin; 0: i * orbit_step about the y cosine through position */
+    float orbit_step;
+    float sdd[2], fov[2], start_angle[2], tube_weight[2]; /* gantry, per tube */
+    float beam_width;          /* collimation along z at the isocentre [mm] */
+    float angle_step, pitch, table_step, tilt, scan_length;
+    uint32_t xcare;            /* organ-based tube current modulation on */
+    float xcare_angle, xcare_span, xcare_ramp, xcare_low;
+    uint32_t aec_size;         /* entries of the tube-current profile along z handed to dxmcb200_generate_exposures (0: none) */
+    float aec_min, aec_max, aec_step;
+    uint32_t align;            /* 1: express the exposures in the basis of world_cosines (Exposure::alignToDirectionCosines) */
+    float world_cosines[6];
+} dxmcb200_source_params;
+
 /* ---- life cycle ------------------------------------------------------------------------- */
 int dxmcb200_device_count(int* count);
 int dxmcb200_create(int device, dxmcb200_ctx** out);
@@ -130,8 +165,12 @@ int dxmcb200_set_world(dxmcb200_ctx*, const dxmcb200_world*);
  * quantity the Woodcock majorant needs (replaces the per-material transform_reduce over all voxels of
  * attenuationinterpolator.hpp:48-59 with one device pass, or a look at the 256-entry table of a palette grid). */
 int dxmcb200_material_max_density(dxmcb200_ctx*, uint32_t n_materials, float* out);
-/* Large device blocks (accumulators, wave buffers, staging arrays) are parked in a per-process pool when a context
- * is destroyed and reused by the next one; this returns the parked blocks of `device` (< 0: all) to the driver. */
+/* Large device blocks (accumulators, wave buffers, staging arrays) can be parked in a per-process pool when a context is
+ * destroyed and reused by the next one (saves the cudaMalloc / cudaFree of tens of GB per Transport call). OFF by default:
+ * nothing stays allocated after a context is destroyed. dxmcb200_set_pool_limit(bytes) (or DXMCB200_POOL_GB=<n> in the
+ * environment) lets up to that many bytes stay parked per process; 0 switches parking off and frees what is parked.
+ * dxmcb200_trim_pool returns the parked blocks of `device` (< 0: all) to the driver. */
+int dxmcb200_set_pool_limit(uint64_t bytes);
 int dxmcb200_trim_pool(int device);
 int dxmcb200_set_luts(dxmcb200_ctx*, const dxmcb200_luts*);
 int dxmcb200_set_beam_tables(dxmcb200_ctx*, uint32_t n_spectra, const dxmcb200_spectrum* spectra, uint32_t n_heel,
@@ -184,9 +223,14 @@ void dxmcb200_history_stream(uint64_t seed, uint64_t exposure, uint64_t history,
 int dxmcb200_run(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t exp_begin, uint64_t exp_end,
     int low_energy_model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user);
 
-/* Same with the exposure table already resident on the device (uploaded once by
- * dxmcb200_upload_exposures); used by bench.py's device-resident timing. */
+/* Same with the exposure table already resident on the device: uploaded once by dxmcb200_upload_exposures, or made on the
+ * device by dxmcb200_generate_exposures — one kernel evaluates all params->exposures exposures of the source from its
+ * parameter block (aec_profile: params->aec_size host floats, may be NULL when aec_size is 0); `out` (may be NULL) receives
+ * a host copy of the table. dxmcb200_run_range is dxmcb200_run on the resident table (cancel flag, progress callback). */
 int dxmcb200_upload_exposures(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t n);
+int dxmcb200_generate_exposures(dxmcb200_ctx*, const dxmcb200_source_params* params, const float* aec_profile, dxmcb200_exposure* out);
+int dxmcb200_run_range(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed,
+    const volatile int* cancel, dxmcb200_progress_cb cb, void* user);
 int dxmcb200_run_resident(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed);
 /* Interleaved partition for multi-GPU runs: transports the resident exposures exp_first + k * exp_stride,
  * k in [0, exp_count). Rank r of N calls (r, N, ceil((n - r) / N)): every GPU then sees the same mix of scan

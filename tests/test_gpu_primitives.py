@@ -207,6 +207,8 @@ def test_device_pool_reuse_and_trim(gpu, product):
     half = [d * 0.5 for d in dim]
     ext = (-half[0], half[0], -half[1], half[1], -half[2], half[2])
     maxima = []
+    free = []
+    assert cabi.lib().dxmcb200_set_pool_limit(C.c_uint64(8 << 30)) == 0  # parking is opt-in (default: nothing stays allocated)
     for trip in range(3):
         ctx = cabi.Context(0)
         ctx.set_world(dim, (1.0, 1.0, 1.0), ext, density, material)
@@ -217,3 +219,14 @@ def test_device_pool_reuse_and_trim(gpu, product):
         if trip == 1:
             assert cabi.lib().dxmcb200_trim_pool(C.c_int(-1)) == 0
     assert all(T.bit_equal(m, maxima[0]) for m in maxima)
+    # with the default limit (0) a destroyed context leaves nothing parked: the device memory in use returns to its starting value
+    import torch
+
+    assert cabi.lib().dxmcb200_set_pool_limit(C.c_uint64(0)) == 0
+    before = torch.cuda.mem_get_info(0)[0]
+    ctx = cabi.Context(0)
+    ctx.set_world(dim, (1.0, 1.0, 1.0), ext, density, material)
+    during = torch.cuda.mem_get_info(0)[0]
+    ctx.close()
+    after = torch.cuda.mem_get_info(0)[0]
+    assert before - during > 100 << 20 and before - after < 32 << 20, (before, during, after)
