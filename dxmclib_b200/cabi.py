@@ -21,8 +21,8 @@ _u64p = C.POINTER(C.c_uint64)
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
     "dxmcb200_physics_backend", "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_set_pool_limit", "dxmcb200_trim_pool",
-    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks",
-    "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_generate_exposures", "dxmcb200_run_range", "dxmcb200_run_resident", "dxmcb200_run_strided",
+    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks", "dxmcb200_get_brick_distance",
+    "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_exposure_table", "dxmcb200_generate_exposures", "dxmcb200_run_range", "dxmcb200_run_resident", "dxmcb200_run_strided",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce",
     "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
     "dxmcb200_sample_interaction",
@@ -223,6 +223,23 @@ class Context:
         self._chk(self.l.dxmcb200_run(self.h, arr, C.c_uint64(begin), C.c_uint64(end), int(model), C.c_uint64(seed), None, None, None),
                   "dxmcb200_run")
 
+    def resident_exposures(self, n: int) -> np.ndarray:
+        """The exposure table resident on the device (uploaded or generated there), as a structured array."""
+        import torch
+
+        dt = np.dtype([("position", "<f4", 3), ("cosines", "<f4", 6), ("beam_direction", "<f4", 3), ("collimation", "<f4", 4), ("weight", "<f4"),
+                       ("mono_energy", "<f4"), ("spectrum", "<i4"), ("heel", "<i4"), ("bowtie", "<i4"), ("reserved", "<u4"), ("histories", "<u8")])
+        assert dt.itemsize == C.sizeof(Exposure)
+        out = np.zeros(int(n), dt)
+        ptr = C.c_void_p()
+        self._chk(self.l.dxmcb200_exposure_table(self.h, C.byref(ptr), None), "dxmcb200_exposure_table")
+
+        class _Block:
+            __cuda_array_interface__ = {"shape": (int(n) * dt.itemsize,), "typestr": "|u1", "data": (ptr.value, True), "version": 2}
+
+        raw = torch.as_tensor(_Block(), device="cuda").cpu().numpy()
+        return raw.view(dt).copy()
+
     def upload_exposures(self, exposures):
         arr = (Exposure * len(exposures))(*exposures)
         self._chk(self.l.dxmcb200_upload_exposures(self.h, arr, C.c_uint64(len(exposures))), "dxmcb200_upload_exposures")
@@ -282,7 +299,9 @@ class Context:
         ratio, bmax, air = np.zeros(n_materials, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
         self._chk(self.l.dxmcb200_get_bricks(self.h, shift, nb, C.byref(f_air), ratio.ctypes.data_as(_f32p), bmax.ctypes.data_as(_f32p),
                                              air.ctypes.data_as(_u8p)), "dxmcb200_get_bricks")
-        return {"shift": list(shift), "nb": list(nb), "f_air": float(f_air.value), "ratio": ratio, "brick_max": bmax, "air": air}
+        dist = np.zeros(n, np.uint8)
+        self._chk(self.l.dxmcb200_get_brick_distance(self.h, dist.ctypes.data_as(_u8p)), "dxmcb200_get_brick_distance")
+        return {"shift": list(shift), "nb": list(nb), "f_air": float(f_air.value), "ratio": ratio, "brick_max": bmax, "air": air, "distance": dist}
 
     def enable_stats(self, on=True):
         self._chk(self.l.dxmcb200_enable_stats(self.h, int(on)), "dxmcb200_enable_stats")

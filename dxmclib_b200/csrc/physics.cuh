@@ -100,9 +100,11 @@ struct BrickView {
     uint32_t shift[3];
     uint32_t nb[3]; // bricks per axis
     float size[3]; // brick edge [mm]
+    float invSize[3];
     float invFAir; // 1 / f_air: free paths in air bricks are the global-majorant ones times this
     uint32_t nWords; // 32-bit words of the bitmap; 0: no air bricks, plain Woodcock tracking everywhere
     const uint32_t* air; // bit b: brick b = (bz * nb[1] + by) * nb[0] + bx is air
+    const uint8_t* distance; // per brick: Chebyshev distance (bricks, <= 255) to the nearest non-air brick, 0 for non-air bricks
 };
 
 struct SpectrumView {
@@ -311,57 +313,67 @@ __device__ __forceinline__ bool inAirBrick(const WorldView& w, const BrickView& 
     return airBit(b.air, brickOfVoxel(b, ix, iy, iz));
 }
 
-// Ray parameter at which the photon's ray leaves the run of air bricks it starts in (parametric ray / grid traversal,
-// Siddon 1985, Amanatides & Woo 1987, over the brick grid); `exits`: the ray leaves the grid there. Round-to-nearest
-// intrinsics throughout: the CPU restatement (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
+// Ray parameter at which the photon's ray leaves the run of air bricks it starts in; `exits`: the ray leaves the grid there.
+// A parametric ray / grid traversal (Siddon 1985, Amanatides & Woo 1987) over the brick grid that does not stop at every
+// brick face: an air brick at Chebyshev distance k from the nearest non-air brick is the centre of a cube of (2k-1)^3 air
+// bricks, which the ray leaves in one step (3-4 steps per walk on the bench phantom instead of 13 face crossings; every
+// step is a dependent table look-up, and that latency is what the walk costs). All face parameters are taken from the
+// starting point, so nothing accumulates. Round-to-nearest intrinsics throughout: the CPU restatement
+// (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
 __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickView& b, const Photon& p, bool& exits, uint32_t& crossed)
 {
     const float pos[3] = { p.px, p.py, p.pz };
     const float dir[3] = { p.dx, p.dy, p.dz };
     int brick[3], step[3];
-    float tMax[3], tDelta[3];
+    float inv[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         brick[i] = static_cast<int>(axisVoxelClamped(w, i, pos[i]) >> b.shift[i]);
         if (fabsf(dir[i]) > kDirEpsilon) {
-            const float inv = __fdiv_rn(1.0f, dir[i]);
+            inv[i] = __fdiv_rn(1.0f, dir[i]);
             step[i] = dir[i] > 0.0f ? 1 : -1;
-            const float face = __fadd_rn(w.ext[2 * i], __fmul_rn(static_cast<float>(brick[i] + (dir[i] > 0.0f ? 1 : 0)), b.size[i]));
-            tMax[i] = fmaxf(__fmul_rn(__fsub_rn(face, pos[i]), inv), 0.0f);
-            tDelta[i] = __fmul_rn(b.size[i], fabsf(inv));
         } else {
+            inv[i] = 0.0f;
             step[i] = 0;
-            tMax[i] = __int_as_float(0x7f800000);
-            tDelta[i] = 0.0f;
         }
     }
     exits = false;
+    float travelled = 0.0f;
     for (;;) {
-        const int a = tMax[0] <= tMax[1] ? (tMax[0] <= tMax[2] ? 0 : 2) : (tMax[1] <= tMax[2] ? 1 : 2);
-        const float t = a == 0 ? tMax[0] : a == 1 ? tMax[1] : tMax[2];
-        const int st = a == 0 ? step[0] : a == 1 ? step[1] : step[2];
-        if (st == 0) { // zero direction: the photon never leaves
-            exits = true;
-            return t;
+        const int k = static_cast<int>(__ldg(b.distance + (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])));
+        float t[3];
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const float face = __fadd_rn(w.ext[2 * i], __fmul_rn(static_cast<float>(brick[i] + (step[i] > 0 ? k : 1 - k)), b.size[i]));
+            t[i] = step[i] != 0 ? __fmul_rn(__fsub_rn(face, pos[i]), inv[i]) : __int_as_float(0x7f800000);
         }
-        const int moved = (a == 0 ? brick[0] : a == 1 ? brick[1] : brick[2]) + st;
+        const int a = t[0] <= t[1] ? (t[0] <= t[2] ? 0 : 2) : (t[1] <= t[2] ? 1 : 2);
+        const float ta = a == 0 ? t[0] : a == 1 ? t[1] : t[2];
+        if ((a == 0 ? step[0] : a == 1 ? step[1] : step[2]) == 0) { // zero direction: the photon never leaves
+            exits = true;
+            return ta;
+        }
+        travelled = fmaxf(ta, travelled);
         ++crossed;
-        if (moved < 0 || moved >= static_cast<int>(a == 0 ? b.nb[0] : a == 1 ? b.nb[1] : b.nb[2])) {
-            exits = true;
-            return t;
+        bool outside = false;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            int c;
+            if (j == a) {
+                c = brick[j] + step[j] * k;
+            } else { // brick of the exit point, inside the cube by construction (the clamp absorbs rounding)
+                const float q = __fmul_rn(__fsub_rn(__fadd_rn(pos[j], __fmul_rn(travelled, dir[j])), w.ext[2 * j]), b.invSize[j]);
+                c = min(max(__float2int_rd(q), brick[j] - (k - 1)), brick[j] + (k - 1));
+            }
+            brick[j] = c;
+            outside = outside || c < 0 || c >= static_cast<int>(b.nb[j]);
         }
-        if (a == 0) {
-            brick[0] = moved;
-            tMax[0] = __fadd_rn(tMax[0], tDelta[0]);
-        } else if (a == 1) {
-            brick[1] = moved;
-            tMax[1] = __fadd_rn(tMax[1], tDelta[1]);
-        } else {
-            brick[2] = moved;
-            tMax[2] = __fadd_rn(tMax[2], tDelta[2]);
+        if (outside) {
+            exits = true;
+            return travelled;
         }
         if (!airBit(b.air, (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])))
-            return t;
+            return travelled;
     }
 }
 

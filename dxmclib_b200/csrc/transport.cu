@@ -1315,8 +1315,9 @@ struct dxmcb200_ctx {
     bool bricksValid = false;
     BrickView bricks {};
     uint32_t* dBrickBits = nullptr;
+    uint8_t* dBrickDistance = nullptr;
     std::vector<float> hRatio, hBrickMax; // what the brick grid was built from, for dxmcb200_get_bricks
-    std::vector<uint8_t> hAir;
+    std::vector<uint8_t> hAir, hDistance;
     float fAir = 0.0f;
     std::vector<float> hKnots, hCoeff, hMaxCoeff; // host copies of the attenuation fits (brick classification)
     int aggregateScores = -1; // warp-aggregated scoring: -1 automatic (narrow beams), 0 never, 1 always (DXMCB200_AGGREGATE)
@@ -1490,6 +1491,7 @@ int ensureBricks(dxmcb200_ctx* c)
     c->hRatio.clear();
     c->hBrickMax.clear();
     c->hAir.clear();
+    c->hDistance.clear();
     if (c->tracking == 0) {
         c->bricksValid = true;
         return DXMCB200_OK;
@@ -1515,8 +1517,10 @@ int ensureBricks(dxmcb200_ctx* c)
     BrickView b {};
     const uint64_t dim[3] = { c->world.dim[0], c->world.dim[1], c->world.dim[2] };
     brickLayout(dim, c->world.spacing, c->brickMm, b.shift, b.nb);
-    for (int i = 0; i < 3; ++i)
+    for (int i = 0; i < 3; ++i) {
         b.size[i] = static_cast<float>(1u << b.shift[i]) * c->world.spacing[i];
+        b.invSize[i] = 1.0f / b.size[i];
+    }
     const size_t nBricks = static_cast<size_t>(b.nb[0]) * b.nb[1] * b.nb[2];
     float* dRatio = nullptr;
     unsigned* dMax = nullptr; // [nBricks] maxima, then [nBricks] measurement flags
@@ -1554,15 +1558,52 @@ int ensureBricks(dxmcb200_ctx* c)
             ++nAir;
         }
     }
+    // Chebyshev distance transform of the air flags (bricks beyond the grid count as air): breadth-first from the non-air bricks
+    // over the 26-neighbourhood; the cube of (2k-1)^3 bricks around an air brick of distance k holds air bricks only
+    c->hDistance.assign(nBricks, 0);
+    {
+        std::vector<size_t> frontier, next;
+        for (size_t k = 0; k < nBricks; ++k) {
+            if (c->hAir[k])
+                c->hDistance[k] = 255;
+            else
+                frontier.push_back(k);
+        }
+        const int64_t n0 = b.nb[0], n1 = b.nb[1], n2 = b.nb[2];
+        for (int d = 1; d < 255 && !frontier.empty(); ++d) {
+            next.clear();
+            for (const size_t k : frontier) {
+                const int64_t x = static_cast<int64_t>(k % b.nb[0]), y = static_cast<int64_t>((k / b.nb[0]) % b.nb[1]), z = static_cast<int64_t>(k / (static_cast<size_t>(b.nb[0]) * b.nb[1]));
+                for (int64_t dz = -1; dz <= 1; ++dz)
+                    for (int64_t dy = -1; dy <= 1; ++dy)
+                        for (int64_t dx = -1; dx <= 1; ++dx) {
+                            const int64_t X = x + dx, Y = y + dy, Z = z + dz;
+                            if (X < 0 || Y < 0 || Z < 0 || X >= n0 || Y >= n1 || Z >= n2)
+                                continue;
+                            const size_t o = static_cast<size_t>((Z * n1 + Y) * n0 + X);
+                            if (c->hDistance[o] == 255 && c->hAir[o]) {
+                                c->hDistance[o] = static_cast<uint8_t>(d);
+                                next.push_back(o);
+                            }
+                        }
+            }
+            frontier.swap(next);
+        }
+    }
     if (nAir > 0) {
         c->fAir = static_cast<float>(std::max(fAir, 1.0e-6));
         b.invFAir = 1.0f / c->fAir;
         b.nWords = static_cast<uint32_t>(bitmap.size());
         cudaFree(c->dBrickBits);
+        cudaFree(c->dBrickDistance);
         c->dBrickBits = nullptr;
+        c->dBrickDistance = nullptr;
         CU_CHECK(c, cudaMalloc(&c->dBrickBits, bitmap.size() * sizeof(uint32_t)));
         CU_CHECK(c, cudaMemcpy(c->dBrickBits, bitmap.data(), bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU_CHECK(c, cudaMalloc(&c->dBrickDistance, nBricks));
+        CU_CHECK(c, cudaMemcpy(c->dBrickDistance, c->hDistance.data(), nBricks, cudaMemcpyHostToDevice));
         b.air = c->dBrickBits;
+        b.distance = c->dBrickDistance;
     }
     c->bricks = b; // nWords == 0: no air bricks, the kernels without the traversal run
     c->bricksValid = true;
@@ -1939,6 +1980,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
     cudaFree(c->dBrickBits);
+    cudaFree(c->dBrickDistance);
     lap("world, tables");
     for (int i = 0; i < kMaxPipes; ++i) {
         auto& pipe = c->pipes[i];
@@ -2389,6 +2431,17 @@ int dxmcb200_generate_exposures(dxmcb200_ctx* c, const dxmcb200_source_params* p
     return DXMCB200_OK;
 }
 
+int dxmcb200_exposure_table(dxmcb200_ctx* c, void** devicePtr, uint64_t* n)
+{
+    if (!c || !c->dExposures)
+        return DXMCB200_ERR_STATE;
+    if (devicePtr)
+        *devicePtr = c->dExposures;
+    if (n)
+        *n = c->nExposuresResident;
+    return DXMCB200_OK;
+}
+
 int dxmcb200_run_range(dxmcb200_ctx* c, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb,
     void* user)
 {
@@ -2592,6 +2645,18 @@ int dxmcb200_set_tracking(dxmcb200_ctx* c, int tracking, float brickMm)
     if (brickMm > 0.0f)
         c->brickMm = brickMm;
     c->bricksValid = false;
+    return DXMCB200_OK;
+}
+
+int dxmcb200_get_brick_distance(dxmcb200_ctx* c, uint8_t* distance)
+{
+    if (!c || !distance || (!c->dVoxels && !c->dPalette) || !c->dLutBlob)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const int st = ensureBricks(c);
+    if (st != DXMCB200_OK)
+        return st;
+    std::copy(c->hDistance.begin(), c->hDistance.end(), distance);
     return DXMCB200_OK;
 }
 

@@ -63,6 +63,36 @@ void applyTube(Tube<float>& t, const dxs_tube& p)
 
 } // namespace
 
+// ---- further source types (same text in dxmclib_b200/host/scene_capi.cpp and oracle/ref_harness.cpp: both class sets have
+// the reference's API) -----------------------------------------------------------------------------------------------------
+namespace {
+template <typename S>
+void applyCtGeometry(S& src, const dxs_ct_params* p)
+{
+    applyTube(src.tube(), p->tube);
+    src.setPosition(p->position[0], p->position[1], p->position[2]);
+    bool anyCos = false;
+    for (int i = 0; i < 6; ++i)
+        anyCos = anyCos || p->cosines[i] != 0;
+    if (anyCos)
+        src.setDirectionCosines({ p->cosines[0], p->cosines[1], p->cosines[2], p->cosines[3], p->cosines[4], p->cosines[5] });
+    if (p->sdd > 0)
+        src.setSourceDetectorDistance(p->sdd);
+    if (p->collimation > 0)
+        src.setCollimation(p->collimation);
+    if (p->fov > 0)
+        src.setFieldOfView(p->fov);
+    src.setStartAngleDeg(p->start_angle_deg);
+    src.setGantryTiltAngleDeg(p->gantry_tilt_deg);
+    if (p->ctdi_vol > 0)
+        src.setCtdiVol(p->ctdi_vol);
+    if (p->ctdi_phantom_diameter > 0)
+        src.setCtdiPhantomDiameter(p->ctdi_phantom_diameter);
+    src.setModelHeelEffect(p->model_heel != 0);
+    src.setHistoriesPerExposure(p->histories);
+}
+} // namespace
+
 extern "C" {
 
 const char* dxs_backend(void) { return "dxmc-b200"; }
@@ -535,6 +565,106 @@ int dxs_source_ct(dxs_scene* s, const dxs_ct_params* p)
         }
         src->setHistoriesPerExposure(p->histories);
         s->ct = src.get();
+        s->source = std::move(src);
+        return DXS_OK;
+    });
+}
+
+int dxs_source_ct_dual(dxs_scene* s, const dxs_ct_dual_params* d)
+{
+    if (!s || !d)
+        return DXS_ERR_ARG;
+    return guarded([&] {
+        const dxs_ct_params* p = &d->a;
+        std::unique_ptr<CTDualSource<float>> src;
+        CTSpiralDualSource<float>* spiral = nullptr;
+        CTAxialDualSource<float>* axial = nullptr;
+        if (p->spiral) {
+            auto sp = std::make_unique<CTSpiralDualSource<float>>();
+            spiral = sp.get();
+            src = std::move(sp);
+        } else {
+            auto ax = std::make_unique<CTAxialDualSource<float>>();
+            axial = ax.get();
+            src = std::move(ax);
+        }
+        applyCtGeometry(*src, p);
+        applyTube(src->tubeB(), d->tube_b);
+        if (d->sdd_b > 0)
+            src->setSourceDetectorDistanceB(d->sdd_b);
+        if (d->fov_b > 0)
+            src->setFieldOfViewB(d->fov_b);
+        src->setStartAngleDegB(d->start_angle_b_deg);
+        if (d->mas_a > 0)
+            src->setTubeAmas(d->mas_a);
+        if (d->mas_b > 0)
+            src->setTubeBmas(d->mas_b);
+        if (p->exposure_step_deg > 0)
+            src->setExposureAngleStepDeg(p->exposure_step_deg);
+        if (spiral) {
+            if (p->pitch > 0)
+                spiral->setPitch(p->pitch);
+        } else {
+            axial->setStep(p->step > 0 ? p->step : src->collimation());
+        }
+        if (p->scan_length > 0)
+            src->setScanLenght(p->scan_length);
+        src->setUseXCareFilter(p->use_xcare != 0);
+        if (p->use_xcare) {
+            auto& x = src->xcareFilter();
+            x.setFilterAngleDeg(p->xcare_filter_angle_deg);
+            if (p->xcare_span_deg > 0)
+                x.setSpanAngleDeg(p->xcare_span_deg);
+            if (p->xcare_ramp_deg > 0)
+                x.setRampAngleDeg(p->xcare_ramp_deg);
+            if (p->xcare_low_weight > 0)
+                x.setLowWeight(p->xcare_low_weight);
+        }
+        s->ct = src.get();
+        s->source = std::move(src);
+        return DXS_OK;
+    });
+}
+
+int dxs_source_topogram(dxs_scene* s, const dxs_ct_params* p)
+{
+    if (!s || !p)
+        return DXS_ERR_ARG;
+    return guarded([&] {
+        auto src = std::make_unique<CTTopogramSource<float>>();
+        applyCtGeometry(*src, p);
+        if (p->scan_length > 0)
+            src->setScanLenght(p->scan_length);
+        s->ct = nullptr;
+        s->source = std::move(src);
+        return DXS_OK;
+    });
+}
+
+int dxs_source_cbct(dxs_scene* s, const dxs_cbct_params* c)
+{
+    if (!s || !c)
+        return DXS_ERR_ARG;
+    return guarded([&] {
+        const dxs_dx_params* p = &c->dx;
+        auto src = std::make_unique<CBCTSource<float>>();
+        applyTube(src->tube(), p->tube);
+        src->setPosition(p->position[0], p->position[1], p->position[2]);
+        if (p->sdd > 0)
+            src->setSourceDetectorDistance(p->sdd);
+        if (p->field_size[0] > 0 && p->field_size[1] > 0)
+            src->setFieldSize({ p->field_size[0], p->field_size[1] });
+        src->setTubeRotationDeg(p->tube_rotation_deg);
+        src->setSourceAnglesDeg(p->source_angles_deg[0], p->source_angles_deg[1]);
+        if (p->dap > 0)
+            src->setDap(p->dap);
+        src->setModelHeelEffect(p->model_heel != 0);
+        src->setHistoriesPerExposure(p->histories);
+        if (c->step_deg > 0)
+            src->setStepAngleDeg(c->step_deg);
+        if (c->span_deg > 0)
+            src->setSpanAngleDeg(c->span_deg);
+        s->ct = nullptr;
         s->source = std::move(src);
         return DXS_OK;
     });

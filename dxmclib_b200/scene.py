@@ -52,6 +52,15 @@ class CTParams(C.Structure):
                 ("histories", C.c_uint64)]
 
 
+class CTDualParams(C.Structure):
+    _fields_ = [("a", CTParams), ("tube_b", Tube), ("sdd_b", C.c_float), ("fov_b", C.c_float), ("start_angle_b_deg", C.c_float),
+                ("mas_a", C.c_float), ("mas_b", C.c_float)]
+
+
+class CBCTParams(C.Structure):
+    _fields_ = [("dx", DXParams), ("span_deg", C.c_float), ("step_deg", C.c_float)]
+
+
 class Exposure(C.Structure):
     _fields_ = [("position", C.c_float * 3), ("cosines", C.c_float * 6), ("beam_direction", C.c_float * 3),
                 ("collimation", C.c_float * 4), ("weight", C.c_float), ("mono_energy", C.c_float), ("has_spectrum", C.c_int32),
@@ -75,7 +84,7 @@ SCENE_SYMBOLS = [
     "dxs_material_form_factor_sq", "dxs_material_scatter_factor", "dxs_material_binding_energies",
     "dxs_material_shells", "dxs_material_density", "dxs_lut_generate", "dxs_lut_attenuation",
     "dxs_lut_max_inverse", "dxs_lut_scatter_factor", "dxs_lut_sample_form_factor", "dxs_lut_table",
-    "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_bowtie",
+    "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_ct_dual", "dxs_source_topogram", "dxs_source_cbct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
     "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport", "dxs_transport_monitored",
     "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_run_strided", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
@@ -375,6 +384,55 @@ class Scene:
         p.use_xcare = int(kw.get("use_xcare", False))
         p.histories = kw.get("histories", 1000000)
         _chk(self.lib.dxs_source_ct(self.h, C.byref(p)), "dxs_source_ct")
+        return self
+
+    def _ct_params(self, spiral, kw):
+        p = CTParams()
+        p.tube = Tube(kw.get("voltage", 0), kw.get("anode_angle_deg", 0), kw.get("al_mm", 0), kw.get("cu_mm", 0),
+                      kw.get("sn_mm", 0), kw.get("energy_resolution", 0))
+        p.spiral = int(spiral)
+        p.position[:] = kw.get("position", (0, 0, 0))
+        p.cosines[:] = kw.get("cosines", (0, 0, 0, 0, 0, 0))
+        for k in ("sdd", "collimation", "fov", "start_angle_deg", "exposure_step_deg", "scan_length", "pitch", "step",
+                  "gantry_tilt_deg", "ctdi_vol", "xcare_filter_angle_deg", "xcare_span_deg", "xcare_ramp_deg",
+                  "xcare_low_weight"):
+            setattr(p, k, kw.get(k, 0))
+        p.ctdi_phantom_diameter = kw.get("ctdi_phantom_diameter", 0)
+        p.model_heel = int(kw.get("model_heel", True))
+        p.use_xcare = int(kw.get("use_xcare", False))
+        p.histories = kw.get("histories", 1000000)
+        return p
+
+    def source_ct_dual(self, spiral=True, **kw):
+        """CTSpiralDualSource / CTAxialDualSource; tube B: voltage_b, al_mm_b, sdd_b, fov_b, start_angle_b_deg, mas_a, mas_b."""
+        d = CTDualParams()
+        d.a = self._ct_params(spiral, kw)
+        d.tube_b = Tube(kw.get("voltage_b", 0), kw.get("anode_angle_deg_b", 0), kw.get("al_mm_b", 0), kw.get("cu_mm_b", 0), kw.get("sn_mm_b", 0), 0)
+        for k in ("sdd_b", "fov_b", "start_angle_b_deg", "mas_a", "mas_b"):
+            setattr(d, k, kw.get(k, 0))
+        _chk(self.lib.dxs_source_ct_dual(self.h, C.byref(d)), "dxs_source_ct_dual")
+        return self
+
+    def source_topogram(self, **kw):
+        p = self._ct_params(False, kw)
+        _chk(self.lib.dxs_source_topogram(self.h, C.byref(p)), "dxs_source_topogram")
+        return self
+
+    def source_cbct(self, **kw):
+        c = CBCTParams()
+        p = c.dx
+        p.tube = Tube(kw.get("voltage", 0), kw.get("anode_angle_deg", 0), kw.get("al_mm", 0), kw.get("cu_mm", 0), kw.get("sn_mm", 0), kw.get("energy_resolution", 0))
+        p.position[:] = kw.get("position", (0, 0, 0))
+        p.sdd = kw.get("sdd", 0)
+        p.field_size[:] = kw.get("field_size", (0, 0))
+        p.source_angles_deg[:] = kw.get("source_angles_deg", (0, 0))
+        p.tube_rotation_deg = kw.get("tube_rotation_deg", 0)
+        p.dap = kw.get("dap", 0)
+        p.model_heel = int(kw.get("model_heel", True))
+        p.histories = kw.get("histories", 1000000)
+        c.span_deg = kw.get("span_deg", 0)
+        c.step_deg = kw.get("step_deg", 0)
+        _chk(self.lib.dxs_source_cbct(self.h, C.byref(c)), "dxs_source_cbct")
         return self
 
     def source_bowtie(self, angles, weights):

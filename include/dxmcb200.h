@@ -201,6 +201,9 @@ int dxmcb200_set_tracking(dxmcb200_ctx*, int tracking, float brick_mm);
  * nb[3] bricks per axis, f_air (0: no air bricks); optional (may be NULL) ratio [n_materials] = max_E mu_total,m(E) /
  * majorant(E), brick_max [nb2*nb1*nb0] = max over the brick's voxels of density * ratio[material], air [nb2*nb1*nb0] flags. */
 int dxmcb200_get_bricks(dxmcb200_ctx*, uint32_t shift[3], uint32_t nb[3], float* f_air, float* ratio, float* brick_max, uint8_t* air);
+/* per brick, the Chebyshev distance (in bricks, at most 255) to the nearest non-air brick, 0 for non-air bricks: the cube of
+ * (2k-1)^3 bricks around an air brick of distance k is all air, which lets the traversal cross it in one step */
+int dxmcb200_get_brick_distance(dxmcb200_ctx*, uint8_t* distance);
 
 /* zero the accumulators and counters */
 int dxmcb200_clear(dxmcb200_ctx*);
@@ -229,6 +232,8 @@ int dxmcb200_run(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t exp
  * a host copy of the table. dxmcb200_run_range is dxmcb200_run on the resident table (cancel flag, progress callback). */
 int dxmcb200_upload_exposures(dxmcb200_ctx*, const dxmcb200_exposure* exposures, uint64_t n);
 int dxmcb200_generate_exposures(dxmcb200_ctx*, const dxmcb200_source_params* params, const float* aec_profile, dxmcb200_exposure* out);
+/* device address and length of the resident exposure table (either pointer may be NULL) */
+int dxmcb200_exposure_table(dxmcb200_ctx*, void** device_ptr, uint64_t* n);
 int dxmcb200_run_range(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed,
     const volatile int* cancel, dxmcb200_progress_cb cb, void* user);
 int dxmcb200_run_resident(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, int low_energy_model, uint64_t seed);

@@ -149,6 +149,23 @@ typedef struct dxs_ct_params {
     uint64_t histories;
 } dxs_ct_params;
 int dxs_source_ct(dxs_scene*, const dxs_ct_params*);
+/* CTAxialDualSource / CTSpiralDualSource: tube A and the scan as in dxs_ct_params, plus tube B (setSourceDetectorDistanceB,
+ * setFieldOfViewB, setStartAngleDegB, tubeB(), setTubeAmas / setTubeBmas); <= 0 keeps the defaults */
+typedef struct dxs_ct_dual_params {
+    dxs_ct_params a;
+    dxs_tube tube_b;
+    float sdd_b, fov_b, start_angle_b_deg, mas_a, mas_b;
+} dxs_ct_dual_params;
+int dxs_source_ct_dual(dxs_scene*, const dxs_ct_dual_params*);
+/* CTTopogramSource from the tube and geometry fields of dxs_ct_params (position, cosines, sdd, collimation, fov, start angle,
+ * gantry tilt, scan_length, histories) */
+int dxs_source_topogram(dxs_scene*, const dxs_ct_params*);
+/* CBCTSource: the DX fields (exposures ignored) plus setSpanAngleDeg / setStepAngleDeg */
+typedef struct dxs_cbct_params {
+    dxs_dx_params dx;
+    float span_deg, step_deg;
+} dxs_cbct_params;
+int dxs_source_cbct(dxs_scene*, const dxs_cbct_params*);
 /* setBowTieFilter(BowTieFilter(angles, weights)) on a CT source */
 int dxs_source_bowtie(dxs_scene*, int n, const float* angles_rad, const float* weights);
 /* setAecFilter(AECFilter(world density, spacing, dims, exposure profile along z[nz])) on a CT source */

@@ -701,7 +701,9 @@ struct Oracle {
         bool enabled = false;
         std::uint32_t shift[3] {}, nb[3] {};
         T size[3] {}; // brick edge [mm]
+        T invSize[3] {}; // 1 / size
         std::vector<std::uint8_t> air; // [nb2][nb1][nb0]
+        std::vector<std::uint8_t> distance; // per brick: Chebyshev distance (in bricks, at most 255) to the nearest non-air brick; 0 for non-air
         std::vector<T> ratio; // per material: max over E of mu_total(E) / majorant(E)
         std::vector<T> brickMax; // per brick: max over voxels of rho * ratio[material]
         T fAir = 0, invFAir = 0;
@@ -734,8 +736,10 @@ struct Oracle {
                     grow = i;
             ++b.shift[grow];
         }
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 3; ++i) {
             b.size[i] = static_cast<T>(1u << b.shift[i]) * spacing[i];
+            b.invSize[i] = T { 1 } / b.size[i];
+        }
         // per material: the largest mu_total(E) * majorantInverse(E) over the table. Inside a segment it is a sum of
         // exponentials in log10 E (convex), so the maximum sits at a segment end; evaluated in double.
         b.ratio.assign(nMat, T { 0 });
@@ -779,6 +783,36 @@ struct Oracle {
         b.fAir = static_cast<T>(std::max(fAir, 1.0e-6));
         b.invFAir = T { 1 } / b.fAir;
         b.enabled = b.nAir > 0;
+        // Chebyshev distance transform of the air flags (bricks beyond the grid count as air): the cube of (2k-1)^3 bricks
+        // around an air brick of distance k holds air bricks only, so a ray can cross it in one step
+        b.distance.assign(nBricks, 0);
+        std::vector<std::size_t> frontier, next;
+        for (std::size_t br = 0; br < nBricks; ++br) {
+            if (b.air[br])
+                b.distance[br] = 255;
+            else
+                frontier.push_back(br);
+        }
+        for (int d = 1; d < 255 && !frontier.empty(); ++d) {
+            next.clear();
+            for (const std::size_t br : frontier) {
+                const std::int64_t x = static_cast<std::int64_t>(br % b.nb[0]), y = static_cast<std::int64_t>((br / b.nb[0]) % b.nb[1]),
+                                   z = static_cast<std::int64_t>(br / (static_cast<std::size_t>(b.nb[0]) * b.nb[1]));
+                for (std::int64_t dz = -1; dz <= 1; ++dz)
+                    for (std::int64_t dy = -1; dy <= 1; ++dy)
+                        for (std::int64_t dx = -1; dx <= 1; ++dx) {
+                            const std::int64_t X = x + dx, Y = y + dy, Z = z + dz;
+                            if (X < 0 || Y < 0 || Z < 0 || X >= b.nb[0] || Y >= b.nb[1] || Z >= b.nb[2])
+                                continue;
+                            const std::size_t o = (static_cast<std::size_t>(Z) * b.nb[1] + static_cast<std::size_t>(Y)) * b.nb[0] + static_cast<std::size_t>(X);
+                            if (b.distance[o] == 255 && b.air[o]) {
+                                b.distance[o] = static_cast<std::uint8_t>(d);
+                                next.push_back(o);
+                            }
+                        }
+            }
+            frontier.swap(next);
+        }
     }
 
     void voxelCoordinates(const T pos[3], std::uint32_t out[3]) const // clamped: also valid on the faces of the world
@@ -798,46 +832,64 @@ struct Oracle {
         return airBrick(b);
     }
 
-    // Ray parameter at which the ray leaves the run of air bricks it starts in; `exits` when it leaves the grid there.
+    // Ray parameter at which the ray leaves the run of air bricks it starts in; `exits` when it leaves the grid there. The
+    // traversal is parametric like Siddon's / Amanatides & Woo's, but it does not stop at every brick face: an air brick at
+    // Chebyshev distance k from the nearest non-air brick is the centre of a cube of (2k-1)^3 air bricks, which the ray leaves in
+    // one step (all face parameters are taken from the starting point, so nothing accumulates).
     T airRunLength(const Particle& p, bool& exits)
     {
         std::uint32_t v[3];
         voxelCoordinates(p.pos, v);
         std::int64_t b[3];
-        T tMax[3], tDelta[3];
+        T inv[3];
         int step[3];
         for (int i = 0; i < 3; ++i) {
             b[i] = v[i] >> bricks.shift[i];
             if (std::abs(p.dir[i]) > N_ERROR) {
-                const T inv = T { 1 } / p.dir[i];
+                inv[i] = T { 1 } / p.dir[i];
                 step[i] = p.dir[i] > 0 ? 1 : -1;
-                const T face = ext[2 * i] + static_cast<T>(b[i] + (p.dir[i] > 0 ? 1 : 0)) * bricks.size[i];
-                tMax[i] = std::max((face - p.pos[i]) * inv, T { 0 });
-                tDelta[i] = bricks.size[i] * std::abs(inv);
             } else {
+                inv[i] = 0;
                 step[i] = 0;
-                tMax[i] = std::numeric_limits<T>::infinity();
-                tDelta[i] = 0;
             }
         }
         exits = false;
+        T travelled = 0;
         for (;;) {
-            const int a = tMax[0] <= tMax[1] ? (tMax[0] <= tMax[2] ? 0 : 2) : (tMax[1] <= tMax[2] ? 1 : 2);
-            const T t = tMax[a];
-            if (step[a] == 0) { // direction is zero along every axis: the photon never leaves
-                exits = true;
-                return t;
+            const std::int64_t k = bricks.distance[(static_cast<std::size_t>(b[2]) * bricks.nb[1] + static_cast<std::size_t>(b[1])) * bricks.nb[0] + static_cast<std::size_t>(b[0])];
+            T t[3];
+            for (int i = 0; i < 3; ++i) {
+                if (step[i] != 0) {
+                    const T face = ext[2 * i] + static_cast<T>(b[i] + (step[i] > 0 ? k : 1 - k)) * bricks.size[i];
+                    t[i] = (face - p.pos[i]) * inv[i];
+                } else {
+                    t[i] = std::numeric_limits<T>::infinity();
+                }
             }
-            b[a] += step[a];
+            const int a = t[0] <= t[1] ? (t[0] <= t[2] ? 0 : 2) : (t[1] <= t[2] ? 1 : 2);
+            if (step[a] == 0) { // zero direction: the photon never leaves
+                exits = true;
+                return t[a];
+            }
+            travelled = std::max(t[a], travelled);
             ++brickSteps;
-            if (b[a] < 0 || b[a] >= static_cast<std::int64_t>(bricks.nb[a])) {
-                exits = true;
-                return t;
+            for (int j = 0; j < 3; ++j) {
+                if (j == a) {
+                    b[j] += step[j] * k;
+                } else { // brick of the exit point, inside the cube by construction (the clamp absorbs rounding)
+                    const T q = ((p.pos[j] + travelled * p.dir[j]) - ext[2 * j]) * bricks.invSize[j];
+                    const std::int64_t c = static_cast<std::int64_t>(std::floor(q));
+                    b[j] = std::min(std::max(c, b[j] - (k - 1)), b[j] + (k - 1));
+                }
             }
-            tMax[a] += tDelta[a];
+            for (int j = 0; j < 3; ++j)
+                if (b[j] < 0 || b[j] >= static_cast<std::int64_t>(bricks.nb[j])) {
+                    exits = true;
+                    return travelled;
+                }
             const std::uint32_t bb[3] = { static_cast<std::uint32_t>(b[0]), static_cast<std::uint32_t>(b[1]), static_cast<std::uint32_t>(b[2]) };
             if (!airBrick(bb))
-                return t;
+                return travelled;
         }
     }
 
@@ -1143,6 +1195,16 @@ int dxmc_oracle_get_bricks(dxmc_oracle* h, uint32_t shift[3], uint32_t nb[3], fl
         std::copy(o->bricks.brickMax.begin(), o->bricks.brickMax.end(), brick_max);
     if (air)
         std::copy(o->bricks.air.begin(), o->bricks.air.end(), air);
+    return DXMCB200_OK;
+}
+
+// per-brick Chebyshev distance to the nearest non-air brick [nb2*nb1*nb0]
+int dxmc_oracle_get_brick_distance(dxmc_oracle* h, uint8_t* distance)
+{
+    auto* o = reinterpret_cast<Oracle*>(h);
+    if (!o || !distance)
+        return DXMCB200_ERR_ARG;
+    std::copy(o->bricks.distance.begin(), o->bricks.distance.end(), distance);
     return DXMCB200_OK;
 }
 

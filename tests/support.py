@@ -167,6 +167,29 @@ def air_gap_scene(lib, histories=20000, exposures=4, forced=False, dim=(40, 36, 
     return sc
 
 
+def ct_dual_scene(lib, spiral=True, histories=100):
+    sc = tissue_block(lib)
+    sc.source_ct_dual(spiral=spiral, voltage=120, al_mm=6, voltage_b=80, al_mm_b=4, sdd=1100, sdd_b=1000, fov=480, fov_b=300, collimation=38.4,
+                      pitch=0.8, step=30.0, scan_length=90, position=(1, 2, 3), exposure_step_deg=10, start_angle_deg=15, start_angle_b_deg=110,
+                      gantry_tilt_deg=7, mas_a=80, mas_b=120, histories=histories, use_xcare=True, xcare_filter_angle_deg=90, xcare_span_deg=100,
+                      xcare_ramp_deg=20, xcare_low_weight=0.6)
+    return sc
+
+
+def topogram_scene(lib, histories=50):
+    sc = tissue_block(lib)
+    sc.source_topogram(voltage=100, al_mm=5, sdd=1000, fov=400, collimation=20, scan_length=57.5, position=(1, -2, 3), start_angle_deg=33,
+                       gantry_tilt_deg=-4, histories=histories)
+    return sc
+
+
+def cbct_scene(lib, histories=70):
+    sc = tissue_block(lib)
+    sc.source_cbct(voltage=90, al_mm=3, sdd=700, field_size=(200, 150), source_angles_deg=(25, -12), tube_rotation_deg=10, dap=1.5,
+                   histories=histories, position=(2, 3, -4), span_deg=200, step_deg=7)
+    return sc
+
+
 def ctdi_scene(lib, histories=4000, diameter=160):
     sc = S.Scene(lib)
     sc.ctdi_phantom(diameter)

@@ -91,6 +91,15 @@ def test_ct_exposures_and_beam_tables_bit_exact(product, reference, spiral):
     assert a.max_energy() == b.max_energy()
 
 
+@pytest.mark.parametrize("build", [lambda lib: T.ct_dual_scene(lib, True), lambda lib: T.ct_dual_scene(lib, False), T.topogram_scene, T.cbct_scene],
+                         ids=["dual_spiral", "dual_axial", "topogram", "cbct"])
+def test_dual_source_topogram_and_cone_beam_exposures_bit_exact(product, reference, build):
+    """Every remaining source type of the reference (source.hpp:679-787 cone beam, :1369-1600 dual source, :1618-1700 topogram):
+    all exposures, evaluated from the product's parameter block on the host, equal the reference's getExposure bit for bit."""
+    a, b = build(product), build(reference)
+    _same_exposures(a, b, range(a.total_exposures()))
+
+
 def test_dx_source(product, reference):
     def build(lib):
         sc = T.tissue_block(lib)
