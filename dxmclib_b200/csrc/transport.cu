@@ -1151,14 +1151,16 @@ __global__ void maxDensityKernel(const uint2* __restrict__ records, uint64_t n, 
 
 // normalizeScoring / energyImpartedToDose (transport.hpp:780-816) fused with the fixed-point decode
 __global__ void resultKernel(const unsigned long long* __restrict__ acc, const uint2* __restrict__ voxels, const uint8_t* __restrict__ palette,
-    const uint2* __restrict__ paletteTable, int paletteNibbles, uint64_t n, int mode,
+    const uint2* __restrict__ paletteTable, int paletteNibbles, uint64_t first, uint64_t n, int mode,
     float energyLsb, float energySqLsb, uint64_t histories, float calibration, float voxelVolume, float* __restrict__ dose,
     uint32_t* __restrict__ nEvents, float* __restrict__ variance)
 {
     const float hInv = 1.0f / static_cast<float>(histories - 1);
     const float hdInv = 1.0e3f / static_cast<float>(histories);
     const float hvInv = 1.0e6f / static_cast<float>(histories);
-    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+    // voxels [first, first + n): the output arrays are indexed from the start of that range
+    for (uint64_t k = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; k < n; k += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t i = first + k;
         const ulonglong4 a = reinterpret_cast<const ulonglong4*>(acc)[i];
         const float e = static_cast<float>(static_cast<double>(static_cast<long long>(a.x)) * static_cast<double>(energyLsb));
         const float e2 = static_cast<float>(static_cast<double>(a.y) * static_cast<double>(energySqLsb));
@@ -1175,11 +1177,11 @@ __global__ void resultKernel(const unsigned long long* __restrict__ acc, const u
             v = de > 0.0f ? e2 * factor * factor : 0.0f;
         }
         if (dose)
-            dose[i] = d;
+            dose[k] = d;
         if (variance)
-            variance[i] = v;
+            variance[k] = v;
         if (nEvents)
-            nEvents[i] = static_cast<uint32_t>(a.z);
+            nEvents[k] = static_cast<uint32_t>(a.z);
     }
 }
 
@@ -1292,6 +1294,8 @@ __global__ void sampleInteractionKernel(LutView lut, int kind, uint8_t material,
 // runtime
 // ================================================================================================
 constexpr int kMaxPipes = 4;
+// accumulator records beyond the grid (always zero): a reduce-scatter over up to 64 GPUs needs equal slices
+constexpr uint64_t kAccPadding = 64;
 
 struct dxmcb200_ctx {
     int device = 0;
@@ -1320,6 +1324,7 @@ struct dxmcb200_ctx {
     std::vector<uint8_t> hAir, hDistance;
     float fAir = 0.0f;
     std::vector<float> hKnots, hCoeff, hMaxCoeff; // host copies of the attenuation fits (brick classification)
+    bool shardedFullOccupancy = false; // experiment (DXMCB200_INTERACT_FULL=1): interaction / air-walk kernels sized for the whole SM
     int aggregateScores = -1; // warp-aggregated scoring: -1 automatic (narrow beams), 0 never, 1 always (DXMCB200_AGGREGATE)
     bool aggregateThisRun = false;
     unsigned long long* dAcc = nullptr;
@@ -1426,7 +1431,7 @@ cudaError_t launchSharded(const dxmcb200_ctx* c, cudaStream_t stream, K kernel, 
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kernel, kThreads, 0);
     if (e != cudaSuccess)
         return e;
-    uint64_t blocks = static_cast<uint64_t>(c->smCount) * blocksPerSmFor(c, blocksPerSm);
+    uint64_t blocks = static_cast<uint64_t>(c->smCount) * (c->shardedFullOccupancy ? blocksPerSm : blocksPerSmFor(c, blocksPerSm));
     blocks = std::min(blocks, (items + kThreads - 1) / kThreads);
     blocks = std::max<uint64_t>(1, blocks / kShards) * kShards;
     kernel<<<static_cast<unsigned>(blocks), kThreads, 0, stream>>>(P);
@@ -1932,6 +1937,8 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     }
     if (const char* env = std::getenv("DXMCB200_AGGREGATE"))
         c->aggregateScores = std::clamp(std::atoi(env), -1, 1);
+    if (const char* env = std::getenv("DXMCB200_INTERACT_FULL"))
+        c->shardedFullOccupancy = env[0] == '1';
     if (const char* env = std::getenv("DXMCB200_TRACKING")) // 0: the reference's Woodcock loop everywhere, 1: + empty-space traversal
         c->tracking = std::clamp(std::atoi(env), 0, 1);
     if (const char* env = std::getenv("DXMCB200_BRICK_MM")) {
@@ -2066,7 +2073,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
         hostio::poolFree(c->dAcc);
         c->dAcc = nullptr;
         c->nVoxels = 0;
-        CU_CHECK(c, hostio::poolAlloc(c->device, &c->dAcc, n * 4 * sizeof(unsigned long long)));
+        CU_CHECK(c, hostio::poolAlloc(c->device, &c->dAcc, (n + kAccPadding) * 4 * sizeof(unsigned long long)));
         c->nVoxels = n;
     }
     hostio::poolFree(c->dVoxels);
@@ -2094,7 +2101,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     float* const dDensity = staged.density;
     uint8_t* const dMat = staged.material;
     uint8_t* const dMeas = staged.measurement;
-    CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, n * 4 * sizeof(unsigned long long), c->stream));
+    CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, (n + kAccPadding) * 4 * sizeof(unsigned long long), c->stream));
     { // caller arrays are pageable: chunked copies through pinned staging on several host threads
         std::vector<hostio::Segment> up;
         up.push_back({ reinterpret_cast<char*>(const_cast<float*>(w->density)), reinterpret_cast<char*>(dDensity), n * sizeof(float) });
@@ -2354,7 +2361,7 @@ int dxmcb200_clear(dxmcb200_ctx* c)
         return DXMCB200_ERR_ARG;
     CU_CHECK(c, cudaSetDevice(c->device));
     if (c->dAcc)
-        CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, c->nVoxels * 4 * sizeof(unsigned long long), c->stream));
+        CU_CHECK(c, cudaMemsetAsync(c->dAcc, 0, (c->nVoxels + kAccPadding) * 4 * sizeof(unsigned long long), c->stream));
     CU_CHECK(c, cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), c->stream));
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     c->totalMs = 0;
@@ -2472,6 +2479,20 @@ int dxmcb200_run_strided(dxmcb200_ctx* c, uint64_t expFirst, uint64_t expStride,
     return runRange(c, c->hExposures.data(), c->dExposures, expFirst, expCount, expStride, model, seed, nullptr, nullptr, nullptr);
 }
 
+int dxmcb200_run_strided_monitored(dxmcb200_ctx* c, uint64_t expFirst, uint64_t expStride, uint64_t expCount, int model, uint64_t seed,
+    const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
+{
+    if (!c || !c->dExposures)
+        return DXMCB200_ERR_STATE;
+    if (expStride == 0)
+        return DXMCB200_ERR_ARG;
+    if (expCount == 0)
+        return DXMCB200_OK;
+    if (expFirst >= c->nExposuresResident || (c->nExposuresResident - 1 - expFirst) / expStride < expCount - 1)
+        return DXMCB200_ERR_STATE;
+    return runRange(c, c->hExposures.data(), c->dExposures, expFirst, expCount, expStride, model, seed, cancel, cb, user);
+}
+
 int dxmcb200_run(dxmcb200_ctx* c, const dxmcb200_exposure* exposures, uint64_t expBegin, uint64_t expEnd, int model, uint64_t seed,
     const volatile int* cancel, dxmcb200_progress_cb cb, void* user)
 {
@@ -2493,12 +2514,12 @@ int dxmcb200_last_run_ms(dxmcb200_ctx* c, double* ms)
     return DXMCB200_OK;
 }
 
-int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, float calibration, float* dose, uint32_t* nEvents, float* variance)
+// decode voxels [first, first + n) of the accumulators into the caller's host arrays (indexed from `first`)
+static int collectRange(dxmcb200_ctx* c, int mode, uint64_t totalHistories, float calibration, uint64_t first, uint64_t n, float* dose, uint32_t* nEvents,
+    float* variance)
 {
-    if (!c || !c->dAcc || mode < 0 || mode > 2)
-        return DXMCB200_ERR_STATE;
-    CU_CHECK(c, cudaSetDevice(c->device));
-    const uint64_t n = c->nVoxels;
+    if (n == 0)
+        return DXMCB200_OK;
     struct Decoded { // device copies of the Result arrays, back to the pool on every exit path
         float* dose = nullptr;
         float* variance = nullptr;
@@ -2517,20 +2538,28 @@ int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, floa
     if (nEvents)
         CU_CHECK(c, hostio::poolAlloc(c->device, &d.events, n * sizeof(uint32_t)));
     const float voxelVolume = c->world.spacing[0] * c->world.spacing[1] * c->world.spacing[2] / 1000.0f;
-    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, static_cast<int>(c->world.paletteNibbles), n, mode,
+    resultKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dAcc, c->dVoxels, c->dPalette, c->dPaletteTable, static_cast<int>(c->world.paletteNibbles), first, n, mode,
         std::ldexp(1.0f, -c->energyBits),
         std::ldexp(1.0f, -c->energySqBits), totalHistories, calibration, voxelVolume, d.dose, d.events, d.variance);
     CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     std::vector<hostio::Segment> down; // caller arrays are pageable: chunked copies through pinned staging
     if (dose)
-        down.push_back({ reinterpret_cast<char*>(dose), reinterpret_cast<char*>(d.dose), n * sizeof(float) });
+        down.push_back({ reinterpret_cast<char*>(dose + first), reinterpret_cast<char*>(d.dose), n * sizeof(float) });
     if (variance)
-        down.push_back({ reinterpret_cast<char*>(variance), reinterpret_cast<char*>(d.variance), n * sizeof(float) });
+        down.push_back({ reinterpret_cast<char*>(variance + first), reinterpret_cast<char*>(d.variance), n * sizeof(float) });
     if (nEvents)
-        down.push_back({ reinterpret_cast<char*>(nEvents), reinterpret_cast<char*>(d.events), n * sizeof(uint32_t) });
+        down.push_back({ reinterpret_cast<char*>(nEvents + first), reinterpret_cast<char*>(d.events), n * sizeof(uint32_t) });
     CU_CHECK(c, hostio::copyChunked(c->device, down, false));
     return DXMCB200_OK;
+}
+
+int dxmcb200_get_result(dxmcb200_ctx* c, int mode, uint64_t totalHistories, float calibration, float* dose, uint32_t* nEvents, float* variance)
+{
+    if (!c || !c->dAcc || mode < 0 || mode > 2)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    return collectRange(c, mode, totalHistories, calibration, 0, c->nVoxels, dose, nEvents, variance);
 }
 
 int dxmcb200_get_raw(dxmcb200_ctx* c, int64_t* energy, uint64_t* energySq, uint64_t* events)
@@ -2579,31 +2608,96 @@ int dxmcb200_accumulators(dxmcb200_ctx* c, void** devicePtr, uint64_t* nU64)
     return DXMCB200_OK;
 }
 
+// ---- NCCL, loaded on first use (a single-GPU user never needs it) -------------------------------------------------------
+namespace {
+struct Nccl {
+    // ncclUint64 = 5, ncclSum = 0
+    int (*allReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*reduceScatter)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+    int (*commInitAll)(void**, int, const int*) = nullptr;
+    int (*commDestroy)(void*) = nullptr;
+    bool ok = false;
+};
+const Nccl& nccl()
+{
+    static const Nccl api = [] {
+        Nccl n;
+        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h)
+            h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            n.allReduce = reinterpret_cast<decltype(n.allReduce)>(dlsym(h, "ncclAllReduce"));
+            n.reduceScatter = reinterpret_cast<decltype(n.reduceScatter)>(dlsym(h, "ncclReduceScatter"));
+            n.commInitAll = reinterpret_cast<decltype(n.commInitAll)>(dlsym(h, "ncclCommInitAll"));
+            n.commDestroy = reinterpret_cast<decltype(n.commDestroy)>(dlsym(h, "ncclCommDestroy"));
+            n.ok = n.allReduce && n.reduceScatter && n.commInitAll && n.commDestroy;
+        }
+        return n;
+    }();
+    return api;
+}
+} // namespace
+
 int dxmcb200_reduce(dxmcb200_ctx* c, void* comm)
 {
     if (!c || !c->dAcc || !comm)
         return DXMCB200_ERR_STATE;
-    // ncclAllReduce(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t); ncclUint64 = 5, ncclSum = 0
-    using AllReduceFn = int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t);
-    static AllReduceFn fn = nullptr;
-    if (!fn) {
-        void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
-        if (!h)
-            h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
-        if (h)
-            fn = reinterpret_cast<AllReduceFn>(dlsym(h, "ncclAllReduce"));
-        if (!fn) {
-            c->error = "libnccl not found";
-            return DXMCB200_ERR_NCCL;
-        }
+    if (!nccl().ok) {
+        c->error = "libnccl not found";
+        return DXMCB200_ERR_NCCL;
     }
     CU_CHECK(c, cudaSetDevice(c->device));
-    if (fn(c->dAcc, c->dAcc, c->nVoxels * 4, 5, 0, comm, c->stream) != 0) {
+    if (nccl().allReduce(c->dAcc, c->dAcc, c->nVoxels * 4, 5, 0, comm, c->stream) != 0) {
         c->error = "ncclAllReduce failed";
         return DXMCB200_ERR_NCCL;
     }
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
     return DXMCB200_OK;
+}
+
+int dxmcb200_comm_create(int n, const int* devices, void** comms)
+{
+    if (n < 1 || !devices || !comms)
+        return DXMCB200_ERR_ARG;
+    if (!nccl().ok)
+        return DXMCB200_ERR_NCCL;
+    return nccl().commInitAll(comms, n, devices) == 0 ? DXMCB200_OK : DXMCB200_ERR_NCCL;
+}
+
+int dxmcb200_comm_destroy(int n, void** comms)
+{
+    if (n < 1 || !comms)
+        return DXMCB200_ERR_ARG;
+    if (!nccl().ok)
+        return DXMCB200_ERR_NCCL;
+    for (int i = 0; i < n; ++i)
+        if (comms[i])
+            nccl().commDestroy(comms[i]);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_reduce_collect(dxmcb200_ctx* c, void* comm, int rank, int nRanks, int mode, uint64_t totalHistories, float calibration, float* dose,
+    uint32_t* nEvents, float* variance)
+{
+    if (!c || !c->dAcc || !comm || nRanks < 1 || nRanks > static_cast<int>(kAccPadding) || rank < 0 || rank >= nRanks || mode < 0 || mode > 2)
+        return DXMCB200_ERR_STATE;
+    if (!nccl().ok) {
+        c->error = "libnccl not found";
+        return DXMCB200_ERR_NCCL;
+    }
+    CU_CHECK(c, cudaSetDevice(c->device));
+    // equal slices of voxels (the last ones reach into the zero padding behind the grid); in place: rank r receives the sums of
+    // its own slice where that slice already lies
+    const uint64_t slice = (c->nVoxels + static_cast<uint64_t>(nRanks) - 1) / static_cast<uint64_t>(nRanks);
+    unsigned long long* mine = c->dAcc + static_cast<uint64_t>(rank) * slice * 4;
+    if (nccl().reduceScatter(c->dAcc, mine, slice * 4, 5, 0, comm, c->stream) != 0) {
+        c->error = "ncclReduceScatter failed";
+        return DXMCB200_ERR_NCCL;
+    }
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    const uint64_t first = std::min(static_cast<uint64_t>(rank) * slice, c->nVoxels);
+    const uint64_t count = std::min(slice, c->nVoxels - first);
+    return collectRange(c, mode, totalHistories, calibration, first, count, dose, nEvents, variance);
 }
 
 int dxmcb200_get_stats(dxmcb200_ctx* c, dxmcb200_stats* s)

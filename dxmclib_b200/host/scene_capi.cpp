@@ -25,6 +25,7 @@ struct dxs_scene {
     AttenuationLut<float> lut;
     bool lutValid = false;
     std::unique_ptr<Transport<float>> prepared; // dxs_b200_prepare .. dxs_b200_release
+    std::vector<int> devices; // dxs_b200_set_devices: more than one entry spreads dxs_transport over several GPUs
 };
 
 namespace {
@@ -828,6 +829,8 @@ int dxs_transport(dxs_scene* s, int model, int outputMode, int useCalibration, u
         trace("World::makeValid");
         if (seed != 0)
             tr.setSeed(seed);
+        if (!s->devices.empty())
+            tr.setDevices(s->devices);
         (void)nWorkers; // n_workers selects host threads / stream mode in the reference harness only
         Result<float> res = tr(*s->world, s->source.get(), nullptr, useCalibration != 0);
         trace("Transport::operator()");
@@ -868,6 +871,8 @@ int dxs_transport_monitored(dxs_scene* s, int model, int outputMode, int useCali
         s->world->makeValid();
         if (seed != 0)
             tr.setSeed(seed);
+        if (!s->devices.empty())
+            tr.setDevices(s->devices);
         Result<float> res = dxs_monitor::run<Result<float>, ProgressBar<float>>(tr, *s->world, s->source.get(), useCalibration != 0, cancelAtPercent, report);
         const auto n = res.dose.size();
         if (dose)
@@ -955,6 +960,14 @@ int dxs_b200_context(dxs_scene* s, void** ctx)
     if (!s || !s->prepared || !ctx)
         return DXS_ERR_STATE;
     *ctx = s->prepared->context();
+    return DXS_OK;
+}
+
+int dxs_b200_set_devices(dxs_scene* s, int n, const int* devices)
+{
+    if (!s || n < 0 || (n > 0 && !devices))
+        return DXS_ERR_ARG;
+    s->devices.assign(devices, devices + n);
     return DXS_OK;
 }
 

@@ -31,6 +31,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <random>
 #include <stdexcept>
@@ -91,6 +92,24 @@ namespace detail {
         z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
         z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
         return z ^ (z >> 31);
+    }
+
+    // NCCL communicators of a set of devices of this process, made once and kept (ncclCommInitAll costs a good fraction of a second)
+    inline std::vector<void*> communicators(const std::vector<int>& devices)
+    {
+        static std::mutex guard;
+        static std::map<std::vector<int>, std::vector<void*>> cache;
+        std::scoped_lock lock(guard);
+        auto it = cache.find(devices);
+        if (it == cache.end()) {
+            std::vector<void*> comms(devices.size(), nullptr);
+            const int made = dxmcb200_comm_create(static_cast<int>(devices.size()), devices.data(), comms.data());
+            if (made != DXMCB200_OK)
+                throw std::runtime_error("dxmcb200: NCCL communicators for " + std::to_string(devices.size()) + " devices could not be made (status "
+                    + std::to_string(made) + ")");
+            it = cache.emplace(devices, std::move(comms)).first;
+        }
+        return it->second;
     }
 
     struct ContextDeleter {
@@ -168,6 +187,25 @@ public:
     {
         if (detail::inheritedSeed())
             m_seed = detail::mixSeed(*detail::inheritedSeed());
+        else if (const char* env = std::getenv("DXMCB200_DEVICES")) { // "0,1,2,3" or "all"; not inherited by calibration runs
+            std::vector<int> devices;
+            if (std::string(env) == "all") {
+                int n = 0;
+                dxmcb200_device_count(&n);
+                for (int k = 0; k < n; ++k)
+                    devices.push_back(k);
+            } else {
+                for (const char* p = env; *p;) {
+                    char* end = nullptr;
+                    const long v = std::strtol(p, &end, 10);
+                    if (end == p)
+                        break;
+                    devices.push_back(static_cast<int>(v));
+                    p = *end ? end + 1 : end;
+                }
+            }
+            setDevices(devices);
+        }
     }
 
     // Copyable like the reference's Transport (validation.cpp passes it by value): a copy takes the settings and the
@@ -181,6 +219,7 @@ public:
         , m_seed(other.m_seed)
         , m_tracking(other.m_tracking)
         , m_brickMm(other.m_brickMm)
+        , m_devices(other.m_devices)
     {
     }
     Transport& operator=(const Transport& other)
@@ -195,6 +234,7 @@ public:
             m_seed = other.m_seed;
             m_tracking = other.m_tracking;
             m_brickMm = other.m_brickMm;
+            m_devices = other.m_devices;
             m_flat = detail::FlatTables {};
             m_totalExposures = m_histories = 0;
         }
@@ -212,8 +252,23 @@ public:
     OUTPUTMODE outputMode() const { return m_outputmode; }
 
     // ---- B200 additions
-    void setDevice(int device) { m_device = device; }
+    void setDevice(int device)
+    {
+        m_device = device;
+        m_devices.clear();
+    }
     int device() const { return m_device; }
+    // Several GPUs of this machine behind the one call (also DXMCB200_DEVICES=0,1,... or "all" in the environment): device k of n
+    // transports exposures k, k + n, ... (world and tables replicated), the fixed-point grids are summed with ONE NCCL
+    // reduce-scatter over voxel slices, and every device decodes and downloads its own slice into the Result. Integer sums:
+    // the Result is bit-identical to the single-GPU one for the same seed.
+    void setDevices(const std::vector<int>& devices)
+    {
+        m_devices = devices;
+        if (!devices.empty())
+            m_device = devices.front();
+    }
+    const std::vector<int>& devices() const { return m_devices; }
     // Master seed of the per-history counter streams. Unset (the default), every call draws a fresh seed from
     // std::random_device, like the reference's workers do (transport.hpp:749): repeated calls are independent samples and
     // can be averaged. setSeed makes the call reproducible bit for bit; seed() is the seed of the last (or next seeded) run.
@@ -235,6 +290,8 @@ public:
     Result<T> operator()(const U& world, Source<T>* source, ProgressBar<T>* progressbar = nullptr, bool useSourceDoseCalibration = true)
     {
         detail::PhaseTrace trace;
+        if (m_devices.size() > 1)
+            return runOnDevices(world, source, progressbar, useSourceDoseCalibration);
         if (!prepare(world, source))
             return Result<T>(world.size());
         trace("prepare (total)");
@@ -339,16 +396,11 @@ public:
         if (!describeSource(world, *source, m_flat))
             flattenExposures(world, *source, m_totalExposures, m_flat);
         trace("  flatten tables/exposures");
-        detail::check(m_ctx.get(), dxmcb200_set_luts(m_ctx.get(), &m_flat.luts), "set_luts");
-        uploadBeamTables(m_ctx.get(), m_flat);
-        int energyBits = 20, energySqBits = 10;
+        m_energyBits = 20;
+        m_energySqBits = 10;
         dxmcb200_suggest_fixed_point(std::max(historiesAllRanks, m_histories), m_flat.maxWeight * static_cast<double>(source->maxPhotonEnergyProduced()),
-            &energyBits, &energySqBits);
-        detail::check(m_ctx.get(), dxmcb200_set_fixed_point(m_ctx.get(), energyBits, energySqBits), "set_fixed_point");
-        if (m_flat.described) // all exposures evaluated on the device from the source's parameter block
-            detail::check(m_ctx.get(), dxmcb200_generate_exposures(m_ctx.get(), &m_flat.source, m_flat.tubeCurrent.data(), nullptr), "generate_exposures");
-        else if (!m_flat.exposures.empty())
-            detail::check(m_ctx.get(), dxmcb200_upload_exposures(m_ctx.get(), m_flat.exposures.data(), m_flat.exposures.size()), "upload_exposures");
+            &m_energyBits, &m_energySqBits);
+        uploadRun(m_ctx.get());
         return true;
     }
 
@@ -489,6 +541,160 @@ public:
     AttenuationLut<T>& attenuationLut() { return m_attenuationLut; }
 
 protected:
+    // everything a device needs besides the voxel grid: look-up tables, beam tables, fixed-point scale, the exposure table
+    void uploadRun(dxmcb200_ctx* ctx) const
+    {
+        detail::check(ctx, dxmcb200_set_luts(ctx, &m_flat.luts), "set_luts");
+        uploadBeamTables(ctx, m_flat);
+        detail::check(ctx, dxmcb200_set_fixed_point(ctx, m_energyBits, m_energySqBits), "set_fixed_point");
+        if (m_flat.described) // all exposures evaluated on the device from the source's parameter block
+            detail::check(ctx, dxmcb200_generate_exposures(ctx, &m_flat.source, m_flat.tubeCurrent.data(), nullptr), "generate_exposures");
+        else if (!m_flat.exposures.empty())
+            detail::check(ctx, dxmcb200_upload_exposures(ctx, m_flat.exposures.data(), m_flat.exposures.size()), "upload_exposures");
+    }
+
+    // operator() over several GPUs of this process, one host thread per device
+    template <typename U>
+    Result<T> runOnDevices(const U& world, Source<T>* source, ProgressBar<T>* progressbar, bool useSourceDoseCalibration)
+    {
+        const int n = static_cast<int>(m_devices.size());
+        m_device = m_devices.front();
+        // the other devices take their copy of the voxel grid while this thread validates, builds the tables and prepares device 0
+        std::vector<detail::ContextPtr> peers(static_cast<std::size_t>(n - 1));
+        std::vector<std::exception_ptr> failure(static_cast<std::size_t>(n));
+        std::vector<std::thread> uploads;
+        const bool worldUsable = world.isValid() && source;
+        for (int k = 1; worldUsable && k < n; ++k)
+            uploads.emplace_back([&, k]() {
+                try {
+                    dxmcb200_ctx* raw = nullptr;
+                    const int created = dxmcb200_create(m_devices[static_cast<std::size_t>(k)], &raw);
+                    if (created != DXMCB200_OK)
+                        throw std::runtime_error("dxmcb200: no usable CUDA device " + std::to_string(m_devices[static_cast<std::size_t>(k)]));
+                    peers[static_cast<std::size_t>(k - 1)].reset(raw);
+                    if (m_tracking >= 0)
+                        detail::check(raw, dxmcb200_set_tracking(raw, m_tracking, m_brickMm), "set_tracking");
+                    uploadWorld(raw, world);
+                } catch (...) {
+                    failure[static_cast<std::size_t>(k)] = std::current_exception();
+                }
+            });
+        bool prepared = false;
+        try {
+            prepared = prepare(world, source);
+        } catch (...) {
+            failure[0] = std::current_exception();
+        }
+        for (auto& t : uploads)
+            t.join();
+        for (const auto& f : failure)
+            if (f)
+                std::rethrow_exception(f);
+        if (!prepared)
+            return Result<T>(world.size());
+        const auto comms = detail::communicators(m_devices);
+        auto contextOf = [&](int k) { return k == 0 ? m_ctx.get() : peers[static_cast<std::size_t>(k - 1)].get(); };
+
+        Result<T> result(world.size());
+        result.numberOfHistories = m_histories;
+        int mode = 0;
+        float calibration = 1.0f;
+        result.dose_units = "eV/history";
+        if (m_outputmode == OUTPUTMODE::DOSE) {
+            mode = 1;
+            result.dose_units = "keV/kg";
+            if (useSourceDoseCalibration) { // before the run: a CT source calibrates with a Transport of its own on device 0
+                calibration = static_cast<float>(calibrationValue(source, progressbar));
+                result.dose_units = "mGy";
+            }
+        }
+        if (progressbar)
+            progressbar->setTotalExposures(m_totalExposures);
+        struct Shared {
+            ProgressBar<T>* bar;
+            volatile int cancel = 0;
+            std::uint64_t reported = 0;
+            int ranks = 1;
+        } shared { progressbar };
+        shared.ranks = n;
+        if (progressbar && progressbar->cancel())
+            shared.cancel = 1;
+        auto callback = [](std::uint64_t done, void* user) { // rank 0 only: its share of the exposures stands for all ranks
+            auto* p = static_cast<Shared*>(user);
+            if (!p->bar)
+                return;
+            p->bar->exposureCompleted((done - p->reported) * static_cast<std::uint64_t>(p->ranks));
+            p->reported = done;
+            if (p->bar->cancel())
+                p->cancel = 1;
+        };
+        std::vector<float> dose32, variance32; // T = double: the devices deliver float
+        float* dose = nullptr;
+        float* variance = nullptr;
+        if constexpr (std::is_same_v<T, float>) {
+            dose = result.dose.data();
+            variance = result.variance.data();
+        } else {
+            dose32.resize(world.size());
+            variance32.resize(world.size());
+            dose = dose32.data();
+            variance = variance32.data();
+        }
+        std::vector<int> status(static_cast<std::size_t>(n), DXMCB200_OK);
+        const auto start = std::chrono::system_clock::now();
+        auto rank = [&](int k) {
+            try {
+                dxmcb200_ctx* ctx = contextOf(k);
+                if (k > 0)
+                    uploadRun(ctx);
+                const std::uint64_t count = static_cast<std::uint64_t>(k) < m_totalExposures ? (m_totalExposures - static_cast<std::uint64_t>(k) + n - 1) / n : 0;
+                int ran = dxmcb200_run_strided_monitored(ctx, static_cast<std::uint64_t>(k), static_cast<std::uint64_t>(n), count,
+                    static_cast<int>(m_lowenergyCorrection), m_runSeed, &shared.cancel, k == 0 ? +callback : nullptr, &shared);
+                status[static_cast<std::size_t>(k)] = ran;
+                detail::check(ctx, ran, "run_strided");
+            } catch (...) {
+                failure[static_cast<std::size_t>(k)] = std::current_exception();
+            }
+        };
+        auto onAllDevices = [&](auto&& work) {
+            std::vector<std::thread> threads;
+            for (int k = 1; k < n; ++k)
+                threads.emplace_back(work, k);
+            work(0);
+            for (auto& t : threads)
+                t.join();
+            for (const auto& f : failure)
+                if (f)
+                    std::rethrow_exception(f);
+        };
+        onAllDevices(rank);
+        m_lastRunTime = std::chrono::system_clock::now() - start;
+        result.simulationTime = m_lastRunTime;
+        dxmcb200_get_stats(m_ctx.get(), &m_stats);
+        const bool cancelled = shared.cancel != 0 || std::any_of(status.begin(), status.end(), [](int s) { return s == DXMCB200_ERR_CANCELLED; });
+        if (cancelled) {
+            result.numberOfHistories = 0;
+        } else {
+            onAllDevices([&](int k) {
+                try {
+                    dxmcb200_ctx* ctx = contextOf(k);
+                    detail::check(ctx,
+                        dxmcb200_reduce_collect(ctx, comms[static_cast<std::size_t>(k)], k, n, mode, m_histories, calibration, dose, result.nEvents.data(), variance),
+                        "reduce_collect");
+                } catch (...) {
+                    failure[static_cast<std::size_t>(k)] = std::current_exception();
+                }
+            });
+            if constexpr (!std::is_same_v<T, float>) {
+                std::copy(dose32.begin(), dose32.end(), result.dose.begin());
+                std::copy(variance32.begin(), variance32.end(), result.variance.begin());
+            }
+        }
+        peers.clear();
+        release();
+        return result;
+    }
+
     // Source::getCalibrationValue with this run's device and a seed derived from this run's for any Transport it constructs
     T calibrationValue(Source<T>* source, ProgressBar<T>* progressbar) const
     {
@@ -793,6 +999,8 @@ private:
     std::uint64_t m_runSeed = 0; // seed of the prepared / last run
     int m_tracking = -1; // -1: library default
     float m_brickMm = 0.0f;
+    std::vector<int> m_devices; // more than one entry: operator() runs on all of them
+    int m_energyBits = 20, m_energySqBits = 10;
     dxmcb200_stats m_stats {};
     std::chrono::duration<float> m_lastRunTime {};
     detail::ContextPtr m_ctx;

@@ -87,7 +87,7 @@ SCENE_SYMBOLS = [
     "dxs_source_pencil", "dxs_source_isotropic", "dxs_source_dx", "dxs_source_ct", "dxs_source_ct_dual", "dxs_source_topogram", "dxs_source_cbct", "dxs_source_bowtie",
     "dxs_source_aec", "dxs_source_total_exposures", "dxs_source_max_energy", "dxs_source_exposure",
     "dxs_source_table", "dxs_source_spectrum", "dxs_source_calibration", "dxs_transport", "dxs_transport_monitored",
-    "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_run_strided", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release",
+    "dxs_b200_prepare", "dxs_b200_run", "dxs_b200_run_strided", "dxs_b200_collect", "dxs_b200_context", "dxs_b200_release", "dxs_b200_set_devices",
 ]
 
 _libs: dict[str, C.CDLL] = {}
@@ -515,6 +515,12 @@ class Scene:
         return Result(dose, ev, var, int(info.histories), float(info.seconds), info.units.decode()), report
 
     # ---- B200 extensions (product library only)
+    def b200_set_devices(self, devices):
+        """Spread subsequent transport() calls over these GPUs of the machine (Transport::setDevices); [] = one GPU."""
+        arr = (C.c_int * max(len(devices), 1))(*devices)
+        _chk(self.lib.dxs_b200_set_devices(self.h, len(devices), arr), "dxs_b200_set_devices")
+        return self
+
     def b200_prepare(self, device=0, model=MODEL_LIVERMORE, seed=0, total_histories_all_ranks=0):
         _chk(self.lib.dxs_b200_prepare(self.h, int(device), int(model), C.c_uint64(seed), C.c_uint64(total_histories_all_ranks)),
              "dxs_b200_prepare")

@@ -244,6 +244,10 @@ int dxmcb200_run_resident(dxmcb200_ctx*, uint64_t exp_begin, uint64_t exp_end, i
 int dxmcb200_run_strided(dxmcb200_ctx*, uint64_t exp_first, uint64_t exp_stride, uint64_t exp_count, int low_energy_model,
     uint64_t seed);
 
+/* dxmcb200_run_strided with the cancel flag and progress callback of dxmcb200_run (the callback counts exposures of this rank) */
+int dxmcb200_run_strided_monitored(dxmcb200_ctx*, uint64_t exp_first, uint64_t exp_stride, uint64_t exp_count, int low_energy_model,
+    uint64_t seed, const volatile int* cancel, dxmcb200_progress_cb cb, void* user);
+
 /* milliseconds the transport kernels of the last run took (CUDA events on the ctx stream) */
 int dxmcb200_last_run_ms(dxmcb200_ctx*, double* kernel_ms);
 
@@ -264,6 +268,17 @@ int dxmcb200_accumulators(dxmcb200_ctx*, void** device_ptr, uint64_t* n_u64);
 /* ncclAllReduce(sum, uint64) of the accumulator block on the ctx stream; comm is an ncclComm_t.
  * libnccl is loaded on first use. */
 int dxmcb200_reduce(dxmcb200_ctx*, void* nccl_comm);
+/* Several GPUs of one process (one ctx and one host thread per device): dxmcb200_comm_create makes the n communicators
+ * (ncclCommInitAll) for `devices`; dxmcb200_reduce_collect is called by every rank with its own ctx and communicator after its
+ * share of the exposures has run. It sums the fixed-point grids with ONE reduce-scatter over voxel slices (rank r ends up with
+ * the total of voxels [r*ceil(V/n), ...)), decodes that slice with the Result post-processing of dxmcb200_get_result and copies
+ * it into the caller's host arrays at the slice's offset: all ranks are handed the SAME array pointers and fill disjoint parts
+ * (replaces all-reduce of the whole grid + decode on one rank: 1/n of the NVLink traffic per GPU, decode and download in
+ * parallel). Integer sums: the result is bit-identical to the single-GPU result. */
+int dxmcb200_comm_create(int n, const int* devices, void** nccl_comms);
+int dxmcb200_comm_destroy(int n, void** nccl_comms);
+int dxmcb200_reduce_collect(dxmcb200_ctx*, void* nccl_comm, int rank, int n_ranks, int output_mode, uint64_t total_histories,
+    float calibration, float* dose, uint32_t* n_events, float* variance);
 
 typedef struct dxmcb200_stats {
     uint64_t histories;        /* photons born */

@@ -252,6 +252,9 @@ int dxs_b200_collect(dxs_scene*, int output_mode, int use_calibration, uint64_t 
 /* the prepared dxmcb200_ctx* (include/dxmcb200.h) for direct C-ABI calls: accumulators, stats, clear */
 int dxs_b200_context(dxs_scene*, void** ctx);
 int dxs_b200_release(dxs_scene*);
+/* Transport::setDevices for subsequent dxs_transport / dxs_transport_monitored calls: with more than one device the one call
+ * spreads the exposures over all of them (one host thread per GPU, NCCL reduce-scatter of the dose grids). n == 0: back to one GPU. */
+int dxs_b200_set_devices(dxs_scene*, int n, const int* devices);
 
 #ifdef __cplusplus
 }

@@ -991,5 +991,6 @@ int dxs_b200_run_strided(dxs_scene*, uint64_t, uint64_t, uint64_t, double*) { re
 int dxs_b200_collect(dxs_scene*, int, int, uint64_t, float*, uint32_t*, float*, dxs_result_info*) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_context(dxs_scene*, void**) { return DXS_ERR_UNSUPPORTED; }
 int dxs_b200_release(dxs_scene*) { return DXS_ERR_UNSUPPORTED; }
+int dxs_b200_set_devices(dxs_scene*, int, const int*) { return DXS_ERR_UNSUPPORTED; }
 
 } // extern "C"
