@@ -104,7 +104,7 @@ struct BrickView {
     float invFAir; // 1 / f_air: free paths in air bricks are the global-majorant ones times this
     uint32_t nWords; // 32-bit words of the bitmap; 0: no air bricks, plain Woodcock tracking everywhere
     const uint32_t* air; // bit b: brick b = (bz * nb[1] + by) * nb[0] + bx is air
-    const uint8_t* distance; // per brick: Chebyshev distance (bricks, <= 255) to the nearest non-air brick, 0 for non-air bricks
+    const uint8_t* distance; // [8][bricks]: per octant of travel directions and brick, the edge (bricks, <= 255) of the largest all-air cube cornered there; 0 for non-air bricks
 };
 
 struct SpectrumView {
@@ -315,17 +315,18 @@ __device__ __forceinline__ bool inAirBrick(const WorldView& w, const BrickView& 
 
 // Ray parameter at which the photon's ray leaves the run of air bricks it starts in; `exits`: the ray leaves the grid there.
 // A parametric ray / grid traversal (Siddon 1985, Amanatides & Woo 1987) over the brick grid that does not stop at every
-// brick face: an air brick at Chebyshev distance k from the nearest non-air brick is the centre of a cube of (2k-1)^3 air
-// bricks, which the ray leaves in one step (3-4 steps per walk on the bench phantom instead of 13 face crossings; every
-// step is a dependent table look-up, and that latency is what the walk costs). All face parameters are taken from the
-// starting point, so nothing accumulates. Round-to-nearest intrinsics throughout: the CPU restatement
-// (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
+// brick face: from an air brick b the ray crosses, in one step, the largest cube of air bricks that has b as its corner and
+// opens in the ray's octant of directions (edge k bricks, tabulated per octant and brick: 2-3 steps per walk on the bench
+// phantom instead of 13 face crossings; every step is a dependent table look-up, and that latency is what the walk costs).
+// All face parameters are taken from the starting point, so nothing accumulates. Round-to-nearest intrinsics throughout: the
+// CPU restatement (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
 __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickView& b, const Photon& p, bool& exits, uint32_t& crossed)
 {
     const float pos[3] = { p.px, p.py, p.pz };
     const float dir[3] = { p.dx, p.dy, p.dz };
     int brick[3], step[3];
     float inv[3];
+    uint32_t octant = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
         brick[i] = static_cast<int>(axisVoxelClamped(w, i, pos[i]) >> b.shift[i]);
@@ -336,11 +337,14 @@ __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickVie
             inv[i] = 0.0f;
             step[i] = 0;
         }
+        if (dir[i] < 0.0f)
+            octant |= 1u << i;
     }
+    const uint8_t* const edge = b.distance + octant * (b.nb[0] * b.nb[1] * b.nb[2]);
     exits = false;
     float travelled = 0.0f;
     for (;;) {
-        const int k = static_cast<int>(__ldg(b.distance + (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])));
+        const int k = static_cast<int>(__ldg(edge + (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])));
         float t[3];
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
@@ -363,7 +367,8 @@ __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickVie
                 c = brick[j] + step[j] * k;
             } else { // brick of the exit point, inside the cube by construction (the clamp absorbs rounding)
                 const float q = __fmul_rn(__fsub_rn(__fadd_rn(pos[j], __fmul_rn(travelled, dir[j])), w.ext[2 * j]), b.invSize[j]);
-                c = min(max(__float2int_rd(q), brick[j] - (k - 1)), brick[j] + (k - 1));
+                const int far = brick[j] + (dir[j] < 0.0f ? -(k - 1) : (k - 1));
+                c = min(max(__float2int_rd(q), min(brick[j], far)), max(brick[j], far));
             }
             brick[j] = c;
             outside = outside || c < 0 || c >= static_cast<int>(b.nb[j]);
@@ -568,9 +573,26 @@ struct ShellView {
     __device__ __forceinline__ float lineEnergy(int i, int k) const { return s[i * DXMCB200_SHELL_FLOATS + 8 + k]; }
 };
 
+// The three interaction samplers come in two forms. The *Deferred form does everything but the change of direction: it
+// reports the polar angle and leaves the azimuth draw and the rotation (peturb) to the caller, so that a kernel whose lanes
+// sit in different channels runs that common tail ONCE for all of them instead of once per channel at a few lanes each
+// (interactKernel: the Rayleigh copy of the tail ran at 2 of 32 lanes and cost 10 % of the kernel's instructions). The draw
+// order is unchanged: the azimuth is the last draw of every channel in the reference too.
+struct Deflection {
+    bool scattered = false;
+    float theta = 0.0f;
+};
+__device__ __forceinline__ void deflect(Photon& p, const Deflection& d, Rng& rng)
+{
+    if (d.scattered) {
+        const float phi = rng.uniform(kTwoPi);
+        peturb(p, d.theta, phi);
+    }
+}
+
 // returns energy imparted locally; p.energy is 0 or the fluorescence line energy afterwards
 template <int L>
-__device__ __forceinline__ float photoAbsorption(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+__device__ __forceinline__ float photoAbsorptionDeferred(const LutView& l, Photon& p, uint32_t material, Rng& rng, Deflection& d)
 {
     const float E = p.energy;
     p.energy = 0.0f;
@@ -600,17 +622,24 @@ __device__ __forceinline__ float photoAbsorption(const LutView& l, Photon& p, ui
                 r3 -= sh.lineProb(idx, line);
             }
             p.energy = sh.lineEnergy(idx, line);
-            const float theta = rng.uniform(kPi);
-            const float phi = rng.uniform(kTwoPi);
-            peturb(p, theta, phi);
+            d.theta = rng.uniform(kPi);
+            d.scattered = true;
             return E - p.energy;
         }
         return E;
     }
 }
+template <int L>
+__device__ __forceinline__ float photoAbsorption(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    Deflection d;
+    const float e = photoAbsorptionDeferred<L>(l, p, material, rng, d);
+    deflect(p, d, rng);
+    return e;
+}
 
 template <int L>
-__device__ __forceinline__ void rayleighScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+__device__ __forceinline__ void rayleighScatterDeferred(const LutView& l, const Photon& p, uint32_t material, Rng& rng, Deflection& d)
 {
     float theta;
     if constexpr (L == 0) {
@@ -634,12 +663,19 @@ __device__ __forceinline__ void rayleighScatter(const LutView& l, Photon& p, uin
         } while ((1.0f + cosAngle * cosAngle) * 0.5f < rng.uniform());
         theta = acosf(cosAngle);
     }
-    const float phi = rng.uniform(kTwoPi);
-    peturb(p, theta, phi);
+    d.theta = theta;
+    d.scattered = true;
+}
+template <int L>
+__device__ __forceinline__ void rayleighScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    Deflection d;
+    rayleighScatterDeferred<L>(l, p, material, rng, d);
+    deflect(p, d, rng);
 }
 
 // EGSnrc-style impulse approximation with Doppler broadening (transport.hpp:342-483)
-__device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+__device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint32_t material, Rng& rng, Deflection& d)
 {
     const ShellView sh { l.shells + material * (DXMCB200_SHELLS * DXMCB200_SHELL_FLOATS) };
     float cum[DXMCB200_SHELLS];
@@ -741,9 +777,8 @@ __device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint
             }
         }
     } while (rejected);
-    const float theta = acosf(cosAngle);
-    const float phi = rng.uniform(kTwoPi);
-    peturb(p, theta, phi);
+    d.theta = acosf(cosAngle);
+    d.scattered = true;
     const float E = p.energy;
     p.energy *= e;
     return E - p.energy;
@@ -751,10 +786,10 @@ __device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint
 
 // Klein-Nishina rejection sampling, optionally weighted by the scatter function (transport.hpp:300-340)
 template <int L>
-__device__ __forceinline__ float comptonScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+__device__ __forceinline__ float comptonScatterDeferred(const LutView& l, Photon& p, uint32_t material, Rng& rng, Deflection& d)
 {
     if constexpr (L == 2) {
-        return comptonScatterIA(l, p, material, rng);
+        return comptonScatterIA(l, p, material, rng, d);
     } else {
         const float E = p.energy;
         const float k = E / kElectronRestMass;
@@ -778,12 +813,19 @@ __device__ __forceinline__ float comptonScatter(const LutView& l, Photon& p, uin
                 rejected = r2 > g;
             }
         } while (rejected);
-        const float theta = acosf(cosAngle);
-        const float phi = rng.uniform(kTwoPi);
-        peturb(p, theta, phi);
+        d.theta = acosf(cosAngle);
+        d.scattered = true;
         p.energy *= e;
         return E - p.energy;
     }
+}
+template <int L>
+__device__ __forceinline__ float comptonScatter(const LutView& l, Photon& p, uint32_t material, Rng& rng)
+{
+    Deflection d;
+    const float e = comptonScatterDeferred<L>(l, p, material, rng, d);
+    deflect(p, d, rng);
+    return e;
 }
 
 } // namespace dxmcb200

@@ -470,54 +470,48 @@ struct Pending { // what an INTERACT lane needs from the step that found the eve
     uint32_t material; // bits 0-7 material, bits 8-15 measurement flag (forced interaction when non-zero)
 };
 
-// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed.
+// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed. The change of direction
+// of whichever channel was sampled is left in `turn` for the caller (see Deflection in physics.cuh).
 template <int L, bool kStats, bool kAggregate>
 __device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores,
-    ScoreSlot& score)
+    ScoreSlot& score, Deflection& turn)
 {
     const uint32_t mat = pe.material & 0xffu;
     const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
     const float r3 = rng.uniform(attTotal);
-    if (r3 < pe.attPhoto) {
-        const float e = photoAbsorption<L>(P.lut, p, mat, rng);
-        if constexpr (kStats)
-            ++nScores;
-        if (p.energy < kEnergyCutoff) {
-            deposit<kAggregate>(P, score, pe.voxel, (e + p.energy) * p.weight);
-            p.energy = 0.0f;
-            return false;
-        }
-        deposit<kAggregate>(P, score, pe.voxel, e * p.weight);
-        energyChanged = true;
-    } else if (r3 < (pe.attPhoto + pe.attCompton)) {
-        const float e = comptonScatter<L>(P.lut, p, mat, rng);
-        if constexpr (kStats)
-            ++nScores;
-        if (p.energy < kEnergyCutoff) {
-            deposit<kAggregate>(P, score, pe.voxel, (e + p.energy) * p.weight);
-            p.energy = 0.0f;
-            return false;
-        }
-        deposit<kAggregate>(P, score, pe.voxel, e * p.weight);
-        energyChanged = true;
-    } else {
-        rayleighScatter<L>(P.lut, p, mat, rng);
+    if (r3 >= (pe.attPhoto + pe.attCompton) && r3 >= pe.attPhoto) {
+        rayleighScatterDeferred<L>(P.lut, p, mat, rng, turn);
+        return true;
     }
+    const float e = r3 < pe.attPhoto ? photoAbsorptionDeferred<L>(P.lut, p, mat, rng, turn) : comptonScatterDeferred<L>(P.lut, p, mat, rng, turn);
+    if constexpr (kStats)
+        ++nScores;
+    if (p.energy < kEnergyCutoff) { // absorbed here: what is left of the energy stays in the voxel, nothing to turn
+        deposit<kAggregate>(P, score, pe.voxel, (e + p.energy) * p.weight);
+        p.energy = 0.0f;
+        turn.scattered = false;
+        return false;
+    }
+    deposit<kAggregate>(P, score, pe.voxel, e * p.weight);
+    energyChanged = true;
     return true;
 }
 
 // computeInteractionsForced (transport.hpp:523-581)
 template <int L, bool kStats, bool kAggregate>
 __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores,
-    ScoreSlot& score, ScoreSlot& forcedScore)
+    ScoreSlot& score, ScoreSlot& forcedScore, Deflection& turn)
 {
     const uint32_t mat = pe.material & 0xffu;
     const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
     const float photoEventProbability = pe.attPhoto / attTotal;
     const float weightCorrection = pe.eventProbability * photoEventProbability;
     {
-        Photon forced = p;
-        const float eForced = photoAbsorption<L>(P.lut, forced, mat, rng);
+        Photon forced = p; // the forced photo-absorption acts on a copy: its fluorescence photon is never followed, only its draws count
+        Deflection unused;
+        const float eForced = photoAbsorptionDeferred<L>(P.lut, forced, mat, rng, unused);
+        if (unused.scattered)
+            (void)rng.uniform(kTwoPi);
         if constexpr (kStats)
             ++nScores;
         if (forced.energy < kEnergyCutoff)
@@ -529,18 +523,19 @@ __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p,
     if (r1 < pe.eventProbability * (1.0f - photoEventProbability)) {
         const float r2 = rng.uniform(pe.attCompton + pe.attRayleigh);
         if (r2 < pe.attCompton) {
-            const float e = comptonScatter<L>(P.lut, p, mat, rng);
+            const float e = comptonScatterDeferred<L>(P.lut, p, mat, rng, turn);
             if constexpr (kStats)
                 ++nScores;
             if (p.energy < kEnergyCutoff) {
                 deposit<kAggregate>(P, score, pe.voxel, (e + p.energy) * p.weight);
                 p.energy = 0.0f;
+                turn.scattered = false;
                 return false;
             }
             deposit<kAggregate>(P, score, pe.voxel, e * p.weight);
             energyChanged = true;
         } else {
-            rayleighScatter<L>(P.lut, p, mat, rng);
+            rayleighScatterDeferred<L>(P.lut, p, mat, rng, turn);
         }
     }
     p.weight *= (1.0f - weightCorrection);
@@ -889,10 +884,12 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
             pe.material = where.y;
             attenuationAt(P.lut, where.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
             bool energyChanged = false;
+            Deflection turn;
             if (where.y & 0xff00u)
-                alive = interactForced<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, forcedScore);
+                alive = interactForced<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, forcedScore, turn);
             else
-                alive = interact<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score);
+                alive = interact<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, turn);
+            deflect(p, turn, rng); // one azimuth draw + rotation for whichever channel scattered
             if constexpr (kStats)
                 ++cInter;
             // Russian roulette (transport.hpp:684-693)
@@ -1563,36 +1560,32 @@ int ensureBricks(dxmcb200_ctx* c)
             ++nAir;
         }
     }
-    // Chebyshev distance transform of the air flags (bricks beyond the grid count as air): breadth-first from the non-air bricks
-    // over the 26-neighbourhood; the cube of (2k-1)^3 bricks around an air brick of distance k holds air bricks only
-    c->hDistance.assign(nBricks, 0);
+    // Per octant of travel directions o = (dx<0) | (dy<0)<<1 | (dz<0)<<2 and per brick b: the edge k (bricks, at most 255) of the
+    // largest cube of air bricks that has b as its corner and opens in that octant's directions (bricks beyond the grid count as
+    // air); 0 for non-air bricks. D(b) = 1 + min over the 7 neighbours one brick further along the octant's directions, swept
+    // from the far corner of the octant backwards (same rule as oracle/dxmc_oracle.cpp buildBricks).
+    c->hDistance.assign(8 * nBricks, 0);
     {
-        std::vector<size_t> frontier, next;
-        for (size_t k = 0; k < nBricks; ++k) {
-            if (c->hAir[k])
-                c->hDistance[k] = 255;
-            else
-                frontier.push_back(k);
-        }
         const int64_t n0 = b.nb[0], n1 = b.nb[1], n2 = b.nb[2];
-        for (int d = 1; d < 255 && !frontier.empty(); ++d) {
-            next.clear();
-            for (const size_t k : frontier) {
-                const int64_t x = static_cast<int64_t>(k % b.nb[0]), y = static_cast<int64_t>((k / b.nb[0]) % b.nb[1]), z = static_cast<int64_t>(k / (static_cast<size_t>(b.nb[0]) * b.nb[1]));
-                for (int64_t dz = -1; dz <= 1; ++dz)
-                    for (int64_t dy = -1; dy <= 1; ++dy)
-                        for (int64_t dx = -1; dx <= 1; ++dx) {
-                            const int64_t X = x + dx, Y = y + dy, Z = z + dz;
+        for (int o = 0; o < 8; ++o) {
+            const int64_t s0 = (o & 1) ? -1 : 1, s1 = (o & 2) ? -1 : 1, s2 = (o & 4) ? -1 : 1;
+            uint8_t* D = c->hDistance.data() + static_cast<size_t>(o) * nBricks;
+            for (int64_t kz = 0; kz < n2; ++kz)
+                for (int64_t ky = 0; ky < n1; ++ky)
+                    for (int64_t kx = 0; kx < n0; ++kx) {
+                        const int64_t x = s0 > 0 ? n0 - 1 - kx : kx, y = s1 > 0 ? n1 - 1 - ky : ky, z = s2 > 0 ? n2 - 1 - kz : kz;
+                        const size_t at = static_cast<size_t>((z * n1 + y) * n0 + x);
+                        if (!c->hAir[at])
+                            continue;
+                        int least = 255;
+                        for (int m = 1; m < 8; ++m) {
+                            const int64_t X = x + ((m & 1) ? s0 : 0), Y = y + ((m & 2) ? s1 : 0), Z = z + ((m & 4) ? s2 : 0);
                             if (X < 0 || Y < 0 || Z < 0 || X >= n0 || Y >= n1 || Z >= n2)
                                 continue;
-                            const size_t o = static_cast<size_t>((Z * n1 + Y) * n0 + X);
-                            if (c->hDistance[o] == 255 && c->hAir[o]) {
-                                c->hDistance[o] = static_cast<uint8_t>(d);
-                                next.push_back(o);
-                            }
+                            least = std::min<int>(least, D[static_cast<size_t>((Z * n1 + Y) * n0 + X)]);
                         }
-            }
-            frontier.swap(next);
+                        D[at] = static_cast<uint8_t>(std::min(least + 1, 255));
+                    }
         }
     }
     if (nAir > 0) {
@@ -1605,8 +1598,8 @@ int ensureBricks(dxmcb200_ctx* c)
         c->dBrickDistance = nullptr;
         CU_CHECK(c, cudaMalloc(&c->dBrickBits, bitmap.size() * sizeof(uint32_t)));
         CU_CHECK(c, cudaMemcpy(c->dBrickBits, bitmap.data(), bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-        CU_CHECK(c, cudaMalloc(&c->dBrickDistance, nBricks));
-        CU_CHECK(c, cudaMemcpy(c->dBrickDistance, c->hDistance.data(), nBricks, cudaMemcpyHostToDevice));
+        CU_CHECK(c, cudaMalloc(&c->dBrickDistance, 8 * nBricks));
+        CU_CHECK(c, cudaMemcpy(c->dBrickDistance, c->hDistance.data(), 8 * nBricks, cudaMemcpyHostToDevice));
         b.air = c->dBrickBits;
         b.distance = c->dBrickDistance;
     }

@@ -201,8 +201,9 @@ int dxmcb200_set_tracking(dxmcb200_ctx*, int tracking, float brick_mm);
  * nb[3] bricks per axis, f_air (0: no air bricks); optional (may be NULL) ratio [n_materials] = max_E mu_total,m(E) /
  * majorant(E), brick_max [nb2*nb1*nb0] = max over the brick's voxels of density * ratio[material], air [nb2*nb1*nb0] flags. */
 int dxmcb200_get_bricks(dxmcb200_ctx*, uint32_t shift[3], uint32_t nb[3], float* f_air, float* ratio, float* brick_max, uint8_t* air);
-/* per brick, the Chebyshev distance (in bricks, at most 255) to the nearest non-air brick, 0 for non-air bricks: the cube of
- * (2k-1)^3 bricks around an air brick of distance k is all air, which lets the traversal cross it in one step */
+/* distance [8][nb2*nb1*nb0]: per octant of travel directions o = (dx<0) | (dy<0)<<1 | (dz<0)<<2 and per brick, the edge k (in
+ * bricks, at most 255) of the largest cube of air bricks that has the brick as its corner and opens in the octant's directions
+ * (bricks beyond the grid count as air), 0 for non-air bricks: the traversal crosses that cube in one step */
 int dxmcb200_get_brick_distance(dxmcb200_ctx*, uint8_t* distance);
 
 /* zero the accumulators and counters */

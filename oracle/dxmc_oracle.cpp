@@ -703,7 +703,10 @@ struct Oracle {
         T size[3] {}; // brick edge [mm]
         T invSize[3] {}; // 1 / size
         std::vector<std::uint8_t> air; // [nb2][nb1][nb0]
-        std::vector<std::uint8_t> distance; // per brick: Chebyshev distance (in bricks, at most 255) to the nearest non-air brick; 0 for non-air
+        // per octant of travel directions o = (dx<0) | (dy<0)<<1 | (dz<0)<<2 and per brick b: the edge k (in bricks, at most 255) of the
+        // largest cube of air bricks that has b as its corner and extends k bricks from it in that octant's directions (bricks
+        // beyond the grid count as air); 0 for non-air bricks. [8][nb2][nb1][nb0]
+        std::vector<std::uint8_t> distance;
         std::vector<T> ratio; // per material: max over E of mu_total(E) / majorant(E)
         std::vector<T> brickMax; // per brick: max over voxels of rho * ratio[material]
         T fAir = 0, invFAir = 0;
@@ -783,35 +786,30 @@ struct Oracle {
         b.fAir = static_cast<T>(std::max(fAir, 1.0e-6));
         b.invFAir = T { 1 } / b.fAir;
         b.enabled = b.nAir > 0;
-        // Chebyshev distance transform of the air flags (bricks beyond the grid count as air): the cube of (2k-1)^3 bricks
-        // around an air brick of distance k holds air bricks only, so a ray can cross it in one step
-        b.distance.assign(nBricks, 0);
-        std::vector<std::size_t> frontier, next;
-        for (std::size_t br = 0; br < nBricks; ++br) {
-            if (b.air[br])
-                b.distance[br] = 255;
-            else
-                frontier.push_back(br);
-        }
-        for (int d = 1; d < 255 && !frontier.empty(); ++d) {
-            next.clear();
-            for (const std::size_t br : frontier) {
-                const std::int64_t x = static_cast<std::int64_t>(br % b.nb[0]), y = static_cast<std::int64_t>((br / b.nb[0]) % b.nb[1]),
-                                   z = static_cast<std::int64_t>(br / (static_cast<std::size_t>(b.nb[0]) * b.nb[1]));
-                for (std::int64_t dz = -1; dz <= 1; ++dz)
-                    for (std::int64_t dy = -1; dy <= 1; ++dy)
-                        for (std::int64_t dx = -1; dx <= 1; ++dx) {
-                            const std::int64_t X = x + dx, Y = y + dy, Z = z + dz;
-                            if (X < 0 || Y < 0 || Z < 0 || X >= b.nb[0] || Y >= b.nb[1] || Z >= b.nb[2])
+        // largest all-air cube with corner b per octant: D(b) = 1 + min over the 7 neighbours one brick further along the
+        // octant's directions (a neighbour beyond the grid counts as 255), swept from the far corner of the octant backwards
+        b.distance.assign(8 * nBricks, 0);
+        const std::int64_t n0 = b.nb[0], n1 = b.nb[1], n2 = b.nb[2];
+        for (int o = 0; o < 8; ++o) {
+            const std::int64_t s0 = (o & 1) ? -1 : 1, s1 = (o & 2) ? -1 : 1, s2 = (o & 4) ? -1 : 1;
+            std::uint8_t* D = b.distance.data() + static_cast<std::size_t>(o) * nBricks;
+            for (std::int64_t kz = 0; kz < n2; ++kz)
+                for (std::int64_t ky = 0; ky < n1; ++ky)
+                    for (std::int64_t kx = 0; kx < n0; ++kx) {
+                        // visit far-to-near along every axis of the octant
+                        const std::int64_t x = s0 > 0 ? n0 - 1 - kx : kx, y = s1 > 0 ? n1 - 1 - ky : ky, z = s2 > 0 ? n2 - 1 - kz : kz;
+                        const std::size_t at = static_cast<std::size_t>((z * n1 + y) * n0 + x);
+                        if (!b.air[at])
+                            continue;
+                        int least = 255;
+                        for (int m = 1; m < 8; ++m) {
+                            const std::int64_t X = x + ((m & 1) ? s0 : 0), Y = y + ((m & 2) ? s1 : 0), Z = z + ((m & 4) ? s2 : 0);
+                            if (X < 0 || Y < 0 || Z < 0 || X >= n0 || Y >= n1 || Z >= n2)
                                 continue;
-                            const std::size_t o = (static_cast<std::size_t>(Z) * b.nb[1] + static_cast<std::size_t>(Y)) * b.nb[0] + static_cast<std::size_t>(X);
-                            if (b.distance[o] == 255 && b.air[o]) {
-                                b.distance[o] = static_cast<std::uint8_t>(d);
-                                next.push_back(o);
-                            }
+                            least = std::min<int>(least, D[static_cast<std::size_t>((Z * n1 + Y) * n0 + X)]);
                         }
-            }
-            frontier.swap(next);
+                        D[at] = static_cast<std::uint8_t>(std::min(least + 1, 255));
+                    }
         }
     }
 
@@ -833,9 +831,10 @@ struct Oracle {
     }
 
     // Ray parameter at which the ray leaves the run of air bricks it starts in; `exits` when it leaves the grid there. The
-    // traversal is parametric like Siddon's / Amanatides & Woo's, but it does not stop at every brick face: an air brick at
-    // Chebyshev distance k from the nearest non-air brick is the centre of a cube of (2k-1)^3 air bricks, which the ray leaves in
-    // one step (all face parameters are taken from the starting point, so nothing accumulates).
+    // traversal is parametric like Siddon's / Amanatides & Woo's, but it does not stop at every brick face: from an air brick b
+    // the ray crosses, in one step, the largest cube of air bricks that has b as its corner and opens in the ray's octant of
+    // directions (edge k bricks, tabulated per octant and brick). All face parameters are taken from the starting point, so
+    // nothing accumulates.
     T airRunLength(const Particle& p, bool& exits)
     {
         std::uint32_t v[3];
@@ -843,6 +842,7 @@ struct Oracle {
         std::int64_t b[3];
         T inv[3];
         int step[3];
+        std::size_t octant = 0;
         for (int i = 0; i < 3; ++i) {
             b[i] = v[i] >> bricks.shift[i];
             if (std::abs(p.dir[i]) > N_ERROR) {
@@ -852,11 +852,15 @@ struct Oracle {
                 inv[i] = 0;
                 step[i] = 0;
             }
+            if (p.dir[i] < 0)
+                octant |= std::size_t { 1 } << i;
         }
+        const std::size_t nBricks = static_cast<std::size_t>(bricks.nb[0]) * bricks.nb[1] * bricks.nb[2];
+        const std::uint8_t* edge = bricks.distance.data() + octant * nBricks;
         exits = false;
         T travelled = 0;
         for (;;) {
-            const std::int64_t k = bricks.distance[(static_cast<std::size_t>(b[2]) * bricks.nb[1] + static_cast<std::size_t>(b[1])) * bricks.nb[0] + static_cast<std::size_t>(b[0])];
+            const std::int64_t k = edge[(static_cast<std::size_t>(b[2]) * bricks.nb[1] + static_cast<std::size_t>(b[1])) * bricks.nb[0] + static_cast<std::size_t>(b[0])];
             T t[3];
             for (int i = 0; i < 3; ++i) {
                 if (step[i] != 0) {
@@ -879,7 +883,8 @@ struct Oracle {
                 } else { // brick of the exit point, inside the cube by construction (the clamp absorbs rounding)
                     const T q = ((p.pos[j] + travelled * p.dir[j]) - ext[2 * j]) * bricks.invSize[j];
                     const std::int64_t c = static_cast<std::int64_t>(std::floor(q));
-                    b[j] = std::min(std::max(c, b[j] - (k - 1)), b[j] + (k - 1));
+                    const std::int64_t far = b[j] + (p.dir[j] < 0 ? -(k - 1) : (k - 1));
+                    b[j] = std::min(std::max(c, std::min(b[j], far)), std::max(b[j], far));
                 }
             }
             for (int j = 0; j < 3; ++j)
@@ -1198,7 +1203,7 @@ int dxmc_oracle_get_bricks(dxmc_oracle* h, uint32_t shift[3], uint32_t nb[3], fl
     return DXMCB200_OK;
 }
 
-// per-brick Chebyshev distance to the nearest non-air brick [nb2*nb1*nb0]
+// per octant and brick, the edge of the largest all-air cube cornered there [8][nb2*nb1*nb0]
 int dxmc_oracle_get_brick_distance(dxmc_oracle* h, uint8_t* distance)
 {
     auto* o = reinterpret_cast<Oracle*>(h);

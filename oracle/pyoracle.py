@@ -140,7 +140,7 @@ class Oracle:
         ratio, bmax, air = np.zeros(n_mat, np.float32), np.zeros(n, np.float32), np.zeros(n, np.uint8)
         self._chk(self.l.dxmc_oracle_get_bricks(self.h, shift, nb, C.byref(f_air), ratio.ctypes.data_as(_f32p), bmax.ctypes.data_as(_f32p),
                                                 air.ctypes.data_as(_u8p)), "dxmc_oracle_get_bricks")
-        dist = np.zeros(n, np.uint8)
+        dist = np.zeros(8 * n, np.uint8)
         self._chk(self.l.dxmc_oracle_get_brick_distance(self.h, dist.ctypes.data_as(_u8p)), "dxmc_oracle_get_brick_distance")
         return {"shift": list(shift), "nb": list(nb), "f_air": float(f_air.value), "ratio": ratio, "brick_max": bmax, "air": air, "distance": dist}
 
