@@ -784,7 +784,39 @@ __device__ __noinline__ float comptonScatterIA(const LutView& l, Photon& p, uint
     return E - p.energy;
 }
 
-// Klein-Nishina rejection sampling, optionally weighted by the scatter function (transport.hpp:300-340)
+// Klein-Nishina rejection sampling, optionally weighted by the scatter function (transport.hpp:300-340): at most maxTrials
+// trials of the reference's loop (maxTrials < 0: until one is accepted). Every trial starts from fresh draws, so a caller may
+// stop after a few rejections and resume later with the same random stream: the draws a history sees do not change. Returns
+// whether a trial was accepted; then `e` is the energy fraction kept by the photon and `cosAngle` the polar cosine.
+template <int L>
+__device__ __forceinline__ bool comptonTrials(const LutView& l, float E, uint32_t material, Rng& rng, int maxTrials, float& e, float& cosAngle)
+{
+    static_assert(L < 2, "the impulse-approximation sampler draws its shell before the loop: comptonScatterIA");
+    const float k = E / kElectronRestMass;
+    const float emin = 1.0f / (1.0f + 2.0f * k);
+    const float gmaxInv = 1.0f / (1.0f / emin + emin);
+    for (int trial = 0; maxTrials < 0 || trial < maxTrials; ++trial) {
+        const float r1 = rng.uniform();
+        e = r1 + (1.0f - r1) * emin;
+        const float t = (1.0f - e) / (k * e);
+        const float sinthetasqr = t * (2.0f - t);
+        cosAngle = 1.0f - t;
+        const float g = (1.0f / e + e - sinthetasqr) * gmaxInv;
+        const float r2 = rng.uniform();
+        bool rejected;
+        if constexpr (L == 1) {
+            constexpr float kInv = 1.0f / kKevToAngstrom;
+            const float q = E * kInv * sqrtf(0.5f - cosAngle * 0.5f);
+            rejected = r2 > g * scatterFactor(l, material, q);
+        } else {
+            rejected = r2 > g;
+        }
+        if (!rejected)
+            return true;
+    }
+    return false;
+}
+
 template <int L>
 __device__ __forceinline__ float comptonScatterDeferred(const LutView& l, Photon& p, uint32_t material, Rng& rng, Deflection& d)
 {
@@ -792,27 +824,8 @@ __device__ __forceinline__ float comptonScatterDeferred(const LutView& l, Photon
         return comptonScatterIA(l, p, material, rng, d);
     } else {
         const float E = p.energy;
-        const float k = E / kElectronRestMass;
-        const float emin = 1.0f / (1.0f + 2.0f * k);
-        const float gmaxInv = 1.0f / (1.0f / emin + emin);
         float e, cosAngle;
-        bool rejected;
-        do {
-            const float r1 = rng.uniform();
-            e = r1 + (1.0f - r1) * emin;
-            const float t = (1.0f - e) / (k * e);
-            const float sinthetasqr = t * (2.0f - t);
-            cosAngle = 1.0f - t;
-            const float g = (1.0f / e + e - sinthetasqr) * gmaxInv;
-            const float r2 = rng.uniform();
-            if constexpr (L == 1) {
-                constexpr float kInv = 1.0f / kKevToAngstrom;
-                const float q = E * kInv * sqrtf(0.5f - cosAngle * 0.5f);
-                rejected = r2 > g * scatterFactor(l, material, q);
-            } else {
-                rejected = r2 > g;
-            }
-        } while (rejected);
+        comptonTrials<L>(l, E, material, rng, -1, e, cosAngle);
         d.theta = acosf(cosAngle);
         d.scattered = true;
         p.energy *= e;

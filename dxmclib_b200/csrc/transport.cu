@@ -163,19 +163,56 @@ __device__ __forceinline__ void energyDependent(const LutView& lut, float energy
 }
 
 // ---- photon records <-> registers ---------------------------------------------------------------------
+// Records are written once and read once, tens of GB per wave pair: they go through L2 with the streaming (evict-first)
+// policy so that they do not push the voxel grid and the accumulator lines out of it.
+#ifndef DXMCB200_STREAM_RECORDS
+#define DXMCB200_STREAM_RECORDS 1
+#endif
+__device__ __forceinline__ void recStore(float4* at, float4 v)
+{
+#if DXMCB200_STREAM_RECORDS
+    __stcs(at, v);
+#else
+    *at = v;
+#endif
+}
+__device__ __forceinline__ void recStore(uint4* at, uint4 v)
+{
+#if DXMCB200_STREAM_RECORDS
+    __stcs(at, v);
+#else
+    *at = v;
+#endif
+}
+__device__ __forceinline__ float4 recLoad(const float4* at)
+{
+#if DXMCB200_STREAM_RECORDS
+    return __ldcs(at);
+#else
+    return *at;
+#endif
+}
+__device__ __forceinline__ uint4 recLoad(const uint4* at)
+{
+#if DXMCB200_STREAM_RECORDS
+    return __ldcs(at);
+#else
+    return *at;
+#endif
+}
 __device__ __forceinline__ void storePhoton(PhotonRecord* r, const Photon& p, const Rng& rng, float logE, float maxAttInv, uint32_t seg, float extra)
 {
-    r->posE = make_float4(p.px, p.py, p.pz, p.energy);
-    r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-    r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
-        static_cast<uint32_t>(rng.inc >> 32));
-    r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), extra);
+    recStore(&r->posE, make_float4(p.px, p.py, p.pz, p.energy));
+    recStore(&r->dirW, make_float4(p.dx, p.dy, p.dz, p.weight));
+    recStore(&r->rng, make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                          static_cast<uint32_t>(rng.inc >> 32)));
+    recStore(&r->lut, make_float4(logE, maxAttInv, __uint_as_float(seg), extra));
 }
 
 __device__ __forceinline__ void loadPhoton(const PhotonRecord* r, Photon& p, Rng& rng, float& logE, float& maxAttInv, uint32_t& seg, float& extra)
 {
-    const float4 a = r->posE, b = r->dirW, d = r->lut;
-    const uint4 c = r->rng;
+    const float4 a = recLoad(&r->posE), b = recLoad(&r->dirW), d = recLoad(&r->lut);
+    const uint4 c = recLoad(&r->rng);
     p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
     p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
     rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
@@ -269,7 +306,7 @@ __device__ __forceinline__ void emitWalked(const KernelParams& P, PhotonRecord* 
         if (slot != kNoSlot) {
             EventRecord* e = P.events + slot;
             storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, ev.eventProbability);
-            e->where = make_uint4(ev.voxel, ev.material, 0u, 0u);
+            recStore(&e->where, make_uint4(ev.voxel, ev.material, 0u, 0u));
         }
     }
 }
@@ -470,33 +507,6 @@ struct Pending { // what an INTERACT lane needs from the step that found the eve
     uint32_t material; // bits 0-7 material, bits 8-15 measurement flag (forced interaction when non-zero)
 };
 
-// ---- (c) computeInteractions (transport.hpp:583-638). Returns false when the photon is absorbed. The change of direction
-// of whichever channel was sampled is left in `turn` for the caller (see Deflection in physics.cuh).
-template <int L, bool kStats, bool kAggregate>
-__device__ __forceinline__ bool interact(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores,
-    ScoreSlot& score, Deflection& turn)
-{
-    const uint32_t mat = pe.material & 0xffu;
-    const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
-    const float r3 = rng.uniform(attTotal);
-    if (r3 >= (pe.attPhoto + pe.attCompton) && r3 >= pe.attPhoto) {
-        rayleighScatterDeferred<L>(P.lut, p, mat, rng, turn);
-        return true;
-    }
-    const float e = r3 < pe.attPhoto ? photoAbsorptionDeferred<L>(P.lut, p, mat, rng, turn) : comptonScatterDeferred<L>(P.lut, p, mat, rng, turn);
-    if constexpr (kStats)
-        ++nScores;
-    if (p.energy < kEnergyCutoff) { // absorbed here: what is left of the energy stays in the voxel, nothing to turn
-        deposit<kAggregate>(P, score, pe.voxel, (e + p.energy) * p.weight);
-        p.energy = 0.0f;
-        turn.scattered = false;
-        return false;
-    }
-    deposit<kAggregate>(P, score, pe.voxel, e * p.weight);
-    energyChanged = true;
-    return true;
-}
-
 // computeInteractionsForced (transport.hpp:523-581)
 template <int L, bool kStats, bool kAggregate>
 __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p, const Pending& pe, Rng& rng, bool& energyChanged, uint32_t& nScores,
@@ -548,10 +558,21 @@ constexpr unsigned kTile = 256; // photon records a warp claims with one atomic
 constexpr unsigned kGroup = 16; // records per cp.async group; the ring holds two groups per warp
 constexpr unsigned kEventTile = 64; // event slots a warp claims with one atomic
 
-__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem)
+__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem, uint64_t policy)
 {
     const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
+#if DXMCB200_STREAM_RECORDS
+    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "l"(policy) : "memory");
+#else
+    (void)policy;
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+#endif
+}
+__device__ __forceinline__ uint64_t evictFirstPolicy()
+{
+    uint64_t policy;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
+    return policy;
 }
 __device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -563,8 +584,11 @@ __device__ __forceinline__ void cpAsyncWait()
 // ---- (b) Woodcock delta tracking (transport.hpp:640-700) -------------------------------------------
 constexpr unsigned kMaxBrickWords = 512; // bitmap of the brick grid in shared memory: at most 16384 bricks
 
+#ifndef DXMCB200_TK_MINBLOCKS
+#define DXMCB200_TK_MINBLOCKS 6
+#endif
 template <bool kStats, bool kAir>
-__global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_constant__ KernelParams P)
+__global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKernel(const __grid_constant__ KernelParams P)
 {
     __shared__ PhotonRecord ring[kThreads / 32][2 * kGroup];
     __shared__ unsigned stage[kThreads / 32][8];
@@ -575,6 +599,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     const unsigned laneLt = (1u << lane) - 1u;
     const unsigned myShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
     PhotonRecord* const myRing = ring[threadIdx.x >> 5];
+    const uint64_t streamPolicy = evictFirstPolicy(); // wave records are read once: they should not displace the voxel grid in L2
     const bool paletteForm = P.world.palette != nullptr;
     if (paletteForm)
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
@@ -655,7 +680,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
         for (unsigned t = 0; t < (kGroup * sizeof(PhotonRecord) / 16) / 32; ++t) {
             const unsigned piece = lane + 32 * t;
             if (piece < cnt * (sizeof(PhotonRecord) / 16))
-                cpAsync16(dst + piece * 16, src + piece * 16);
+                cpAsync16(dst + piece * 16, src + piece * 16, streamPolicy);
         }
         cpAsyncCommit();
         __syncwarp(); // all lanes have read the words lane 0 is about to write
@@ -772,12 +797,8 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
                 EventRecord* e = P.events + (rank < room ? first + rank : fresh + (rank - room));
                 if (full && rank >= room)
                     e = P.events; // region overflow: the run is flagged invalid, keep the store in bounds
-                e->photon.posE = make_float4(p.px, p.py, p.pz, p.energy);
-                e->photon.dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-                e->photon.rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32),
-                    static_cast<uint32_t>(rng.inc), static_cast<uint32_t>(rng.inc >> 32));
-                e->photon.lut = make_float4(logE, maxAttInv, __uint_as_float(seg), eventProbability);
-                e->where = make_uint4(voxel, material, 0u, 0u);
+                storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, eventProbability);
+                recStore(&e->where, make_uint4(voxel, material, 0u, 0u));
                 state = DEAD;
             }
             deadMask |= eventMask;
@@ -835,7 +856,7 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
     cpAsyncWait<0>();
     // mark the unused slots of the warp's last event tile
     for (unsigned slot = outPos + lane; slot < outEnd; slot += 32)
-        P.events[slot].where = make_uint4(0u, kNoEvent, 0u, 0u);
+        recStore(&P.events[slot].where, make_uint4(0u, kNoEvent, 0u, 0u));
 
     if constexpr (kStats) {
         const unsigned long long s = warpSum(cSteps), l = warpSum(cLookups);
@@ -847,6 +868,12 @@ __global__ void __launch_bounds__(kThreads, 6) transportKernel(const __grid_cons
 }
 
 // ---- (c) interactions + (d) scoring: one event per thread ------------------------------------------
+// computeInteractions (transport.hpp:583-638). The channels cost very different amounts of work per event (ncu: the RITA search of
+// the Rayleigh sampler runs at 2.3 of 32 lanes, the Klein-Nishina loop at 9), but regrouping events by channel has not paid in any
+// form tried: a block-level sort and a per-warp Rayleigh queue in shared memory (round 1), and handing Rayleigh events and
+// Compton events with two rejected trials on to channel-pure follow-up passes through lists in HBM (round 2: 2.77e9 -> 2.64e9
+// histories/s; Rayleigh alone: 2.66e9). The kernel is bound by the latency of its loads and atomics, not by issue slots, and
+// every extra pass adds a load-compute-atomic-store chain per event it touches (profiles/README.md).
 template <int L, bool kStats, bool kAggregate>
 __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_constant__ KernelParams P)
 {
@@ -863,32 +890,57 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
         const unsigned i = base + threadIdx.x;
         const EventRecord* e = region + min(i, nSlots - 1u);
-        const uint4 where = i < nSlots ? e->where : make_uint4(0u, kNoEvent, 0u, 0u);
-        bool alive = false;
+        const uint4 where = i < nSlots ? recLoad(&e->where) : make_uint4(0u, kNoEvent, 0u, 0u);
+        bool alive = false; // the photon goes on to the next wave
+        bool done = false; // the interaction has been sampled (false: no event in this slot)
+        bool energyChanged = false;
         Photon p {};
         Rng rng { 0, 1 };
         float logE = 0.0f, maxAttInv = 0.0f;
         uint32_t seg = 0;
+        Deflection turn;
         ScoreSlot score, forcedScore; // deposits of this event, scored once the warp has reconverged
+        const uint32_t mat = where.y & 0xffu;
+        // energy `imparted` was given up by the photon in a photoelectric or Compton event (transport.hpp:598-625)
+        auto afterEnergyLoss = [&](float imparted) {
+            if constexpr (kStats)
+                ++cScores;
+            if (p.energy < kEnergyCutoff) { // absorbed here: what is left of the energy stays in the voxel, nothing to turn
+                deposit<kAggregate>(P, score, where.x, (imparted + p.energy) * p.weight);
+                p.energy = 0.0f;
+                turn.scattered = false;
+                alive = false;
+            } else {
+                deposit<kAggregate>(P, score, where.x, imparted * p.weight);
+                energyChanged = true;
+                alive = true;
+            }
+            done = true;
+        };
         if (where.y != kNoEvent) {
-            const float4 a = e->photon.posE, b = e->photon.dirW, d = e->photon.lut;
-            const uint4 c = e->photon.rng;
-            p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
-            p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
-            rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
-            rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
-            logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
             Pending pe;
-            pe.eventProbability = d.w;
+            loadPhoton(&e->photon, p, rng, logE, maxAttInv, seg, pe.eventProbability);
             pe.voxel = where.x;
             pe.material = where.y;
-            attenuationAt(P.lut, where.y & 0xffu, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
-            bool energyChanged = false;
-            Deflection turn;
-            if (where.y & 0xff00u)
+            attenuationAt(P.lut, mat, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
+            if (where.y & 0xff00u) {
                 alive = interactForced<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, forcedScore, turn);
-            else
-                alive = interact<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, turn);
+                done = true;
+            } else { // the channel draw of computeInteractions (transport.hpp:590-596)
+                const float attTotal = ((0.0f + pe.attPhoto) + pe.attCompton) + pe.attRayleigh;
+                const float r3 = rng.uniform(attTotal);
+                if (r3 < pe.attPhoto) {
+                    afterEnergyLoss(photoAbsorptionDeferred<L>(P.lut, p, mat, rng, turn));
+                } else if (r3 < (pe.attPhoto + pe.attCompton)) {
+                    afterEnergyLoss(comptonScatterDeferred<L>(P.lut, p, mat, rng, turn));
+                } else {
+                    rayleighScatterDeferred<L>(P.lut, p, mat, rng, turn);
+                    alive = true;
+                    done = true;
+                }
+            }
+        }
+        if (done) {
             deflect(p, turn, rng); // one azimuth draw + rotation for whichever channel scattered
             if constexpr (kStats)
                 ++cInter;
@@ -914,13 +966,8 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
         if (aliveMask == 0)
             continue;
         PhotonRecord* r = appendPhotons(P, aliveMask, lane);
-        if (r) {
-            r->posE = make_float4(p.px, p.py, p.pz, p.energy);
-            r->dirW = make_float4(p.dx, p.dy, p.dz, p.weight);
-            r->rng = make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
-                static_cast<uint32_t>(rng.inc >> 32));
-            r->lut = make_float4(logE, maxAttInv, __uint_as_float(seg), 0.0f);
-        }
+        if (r)
+            storePhoton(r, p, rng, logE, maxAttInv, seg, 0.0f);
     }
     if constexpr (kStats) {
         const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
@@ -967,7 +1014,7 @@ __global__ void exposureKernel(const __grid_constant__ dxmc::model::SourceParams
 // reset the cursors of one buffer between waves
 __global__ void resetCursorsKernel(ShardCursor* cursors, int storedToo)
 {
-    if (threadIdx.x < kShards) {
+    {
         cursors[threadIdx.x].taken = 0;
         if (storedToo)
             cursors[threadIdx.x].stored = 0;
@@ -1321,7 +1368,10 @@ struct dxmcb200_ctx {
     std::vector<uint8_t> hAir, hDistance;
     float fAir = 0.0f;
     std::vector<float> hKnots, hCoeff, hMaxCoeff; // host copies of the attenuation fits (brick classification)
-    bool shardedFullOccupancy = false; // experiment (DXMCB200_INTERACT_FULL=1): interaction / air-walk kernels sized for the whole SM
+    // interaction / air-walk kernels are sized for all block slots of an SM rather than their pipeline's share: they are not persistent,
+    // surplus blocks just queue, and the other pipeline's persistent kernels leave slots free at their tails (measured +3.6 %;
+    // DXMCB200_INTERACT_FULL=0 for the former sizing)
+    bool shardedFullOccupancy = true;
     int aggregateScores = -1; // warp-aggregated scoring: -1 automatic (narrow beams), 0 never, 1 always (DXMCB200_AGGREGATE)
     bool aggregateThisRun = false;
     unsigned long long* dAcc = nullptr;
@@ -1369,7 +1419,10 @@ struct dxmcb200_ctx {
     bool collectStats = false;
     uint32_t waveRecords = 1u << 26; // photons per wave: 6.4 GB per photon buffer, 8.1 GB of event records, x2 pipelines (measured at 1e10
                                      // histories: 2^25: 2.38e9, 2^26: 2.44e9, 2^27: 2.45e9 histories/s; a third pipeline adds < 0.5 %)
-    uint32_t refillBatch = 8; // empty lanes that make a warp stop stepping and re-fill (measured: 4: 2.17e9, 8: 2.20e9, 12: 2.18e9 histories/s)
+    // empty lanes that make a warp stop stepping and re-fill. With the reference's tracking (32 steps per history) 4: 2.17e9, 8: 2.20e9,
+    // 12: 2.18e9 histories/s; with the empty-space traversal a photon segment is 3 steps long and the service code weighs more:
+    // 8: 2.59e9, 16: 2.66e9
+    uint32_t refillBatch = 0; // 0: 16 with the empty-space traversal, 8 without
 
     double lastRunMs = 0, totalMs = 0;
     uint64_t launches = 0;
@@ -1702,7 +1755,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     base.expStride = stride;
     base.nExp = static_cast<uint32_t>(nExp);
     base.uniformHistories = uniform ? static_cast<uint32_t>(hostExposures[expBegin].histories) : 0u;
-    base.refillBatch = c->refillBatch;
+    base.refillBatch = c->refillBatch ? c->refillBatch : (air ? 16u : 8u);
     base.seed = seed;
     base.photonRegion = static_cast<uint32_t>(c->photonRegion);
     base.eventRegion = static_cast<uint32_t>(c->eventRegion);
@@ -2160,27 +2213,31 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     c->world.paletteTable = c->dPaletteTable;
     c->bricksValid = false;
 
-    // Optional (DXMCB200_L2PERSIST=1): pin the voxel grid in L2 with a persisting carve-out + access-policy window.
-    // Measured on B200 with the 105 MB palette grid it LOWERS throughput (1.64e9 vs 2.00e9 histories/s): the carve-out
-    // takes L2 away from the accumulator and record traffic. Off by default, kept for smaller grids.
+    // Optional (DXMCB200_L2PERSIST=<MB>, 1 = as much as the device allows): keep the voxel grid in L2 with a persisting carve-out
+    // of that size + an access-policy window on every pipeline's stream. Measured on B200 it LOWERS throughput at every size
+    // tried (profiles/README.md): the carve-out takes L2 away from the accumulator and record traffic. Off by default.
     {
         const char* env = std::getenv("DXMCB200_L2PERSIST");
         int maxPersist = 0, maxWindow = 0;
         cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, c->device);
         cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, c->device);
         cudaStreamAttrValue attr {};
-        if (env && env[0] == '1' && maxPersist > 0 && maxWindow > 0) {
+        const long mb = env ? std::atol(env) : 0;
+        if (mb > 0 && maxPersist > 0 && maxWindow > 0) {
             const size_t gridBytes = palette ? (c->world.paletteNibbles ? (n + 1) / 2 : n) : n * sizeof(uint2);
-            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, static_cast<size_t>(maxPersist));
+            const size_t persist = mb == 1 ? static_cast<size_t>(maxPersist) : std::min<size_t>(static_cast<size_t>(mb) << 20, static_cast<size_t>(maxPersist));
+            cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persist);
             attr.accessPolicyWindow.base_ptr = palette ? static_cast<void*>(c->dPalette) : static_cast<void*>(c->dVoxels);
             attr.accessPolicyWindow.num_bytes = std::min<size_t>(gridBytes, static_cast<size_t>(maxWindow));
-            attr.accessPolicyWindow.hitRatio = std::min(1.0f, static_cast<float>(maxPersist) / static_cast<float>(attr.accessPolicyWindow.num_bytes));
+            attr.accessPolicyWindow.hitRatio = std::min(1.0f, static_cast<float>(persist) / static_cast<float>(attr.accessPolicyWindow.num_bytes));
             attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
             attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
         } else {
             attr.accessPolicyWindow.num_bytes = 0;
         }
-        cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &attr);
+        for (int i = 0; i < c->nPipes; ++i)
+            if (c->pipes[i].stream)
+                cudaStreamSetAttribute(c->pipes[i].stream, cudaStreamAttributeAccessPolicyWindow, &attr);
         cudaGetLastError(); // a refused hint is not an error
     }
     return DXMCB200_OK;
