@@ -74,8 +74,9 @@ constexpr uint32_t kNoEvent = 0xffffffffu;
 constexpr unsigned kShards = 64;
 struct alignas(128) ShardCursor {
     unsigned int stored; // slots appended to the region
+    unsigned int live; // photons among them (interactKernel claims slots in tiles; what a tile does not use is marked dead)
     unsigned int taken; // slots of the region claimed by the consumer
-    unsigned int pad[30];
+    unsigned int pad[29];
 };
 struct WaveCursors {
     ShardCursor photons[2][kShards];
@@ -133,8 +134,8 @@ __device__ __forceinline__ size_t appendSlots(ShardCursor* cursors, uint32_t reg
     unsigned base = 0;
     const int leader = __ffs(mask) - 1;
     const unsigned n = __popc(mask);
-    if (static_cast<int>(lane) == leader)
-        base = atomicAdd(&cursors[shard].stored, n);
+    if (static_cast<int>(lane) == leader) // stored += n and live += n with one 64-bit atomic
+        base = static_cast<unsigned>(atomicAdd(reinterpret_cast<unsigned long long*>(&cursors[shard].stored), (static_cast<unsigned long long>(n) << 32) | n));
     base = __shfl_sync(kFull, base, leader);
     if (base + n > region) {
         if (static_cast<int>(lane) == leader)
@@ -405,15 +406,18 @@ __global__ void __launch_bounds__(kThreads) airWalkKernel(const __grid_constant_
     const PhotonRecord* const region = P.airborne + static_cast<size_t>(shard) * P.photonRegion;
     for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
         const unsigned i = base + threadIdx.x;
-        const bool valid = i < nSlots;
         Photon p {};
         Rng rng { 0, 1 };
         float logE = 0.0f, maxAttInv = 0.0f, extra = 0.0f;
         uint32_t seg = 0;
         uint32_t outcome = WALK_GONE;
         WalkEvent ev;
+        bool valid = i < nSlots;
         if (valid) {
             loadPhoton(region + i, p, rng, logE, maxAttInv, seg, extra);
+            valid = p.energy > 0.0f; // energy 0: an unused slot of a transportKernel tile
+        }
+        if (valid) {
             outcome = airWalk<kStats>(P, p, rng, logE, seg, maxAttInv, ev, cSteps, cLookups, cBricks);
             if constexpr (kStats)
                 ++cWalks;
@@ -552,34 +556,67 @@ __device__ __forceinline__ bool interactForced(const KernelParams& P, Photon& p,
     return true;
 }
 
-// ---- (b) Woodcock delta tracking + (c) interactions + (d) scoring ---------------------------------
-// ---- record staging: global -> shared with cp.async (LDGSTS), so a re-fill never waits on HBM ------
-constexpr unsigned kTile = 256; // photon records a warp claims with one atomic
-constexpr unsigned kGroup = 16; // records per cp.async group; the ring holds two groups per warp
+// ---- record hand-over between the kernels ------------------------------------------------------------
+constexpr unsigned kTile = 256; // photon records a warp of transportKernel claims with one atomic
 constexpr unsigned kEventTile = 64; // event slots a warp claims with one atomic
-
-__device__ __forceinline__ void cpAsync16(void* smem, const void* gmem, uint64_t policy)
-{
-    const unsigned s = static_cast<unsigned>(__cvta_generic_to_shared(smem));
-#if DXMCB200_STREAM_RECORDS
-    asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "l"(policy) : "memory");
-#else
-    (void)policy;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem) : "memory");
+constexpr unsigned kSurvivorTile = 64; // next-wave photon slots a warp of interactKernel claims with one atomic
+constexpr unsigned kAirTile = 64; // air-walk slots a warp of transportKernel claims with one atomic
+#ifndef DXMCB200_INTERACT_PREFETCH
+#define DXMCB200_INTERACT_PREFETCH 0
 #endif
-}
-__device__ __forceinline__ uint64_t evictFirstPolicy()
-{
-    uint64_t policy;
-    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-    return policy;
-}
-__device__ __forceinline__ void cpAsyncCommit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cpAsyncWait()
-{
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
+
+// A warp's private window into its shard region of an output buffer. Slots are claimed a tile at a time, and AHEAD of need:
+// `prepare` issues the atomic as soon as the current tile might not take one more slot per lane, `take` first looks at its
+// result when the slots are actually needed, typically a trip of the caller's loop later, so the atomic's round trip through
+// L2 never stalls the warp (ncu: 14 % of interactKernel's stall samples sat on it when every trip claimed its exact count).
+// What a warp has claimed but not used by the end of the kernel is marked dead (`finish`), and the consumer skips it.
+// All members are warp-uniform except `claimed`, which only lane 0 holds.
+struct TileWriter {
+    unsigned pos = 0, end = 0; // unused slots of the current tile, as indices inside the shard region
+    unsigned claimed = 0; // base of the tile claimed ahead
+    bool ahead = false;
+
+    __device__ __forceinline__ void prepare(ShardCursor* cursor, unsigned tile, unsigned lane)
+    {
+        if (!ahead && end - pos < 32u) {
+            if (lane == 0)
+                claimed = atomicAdd(&cursor->stored, tile);
+            ahead = true;
+        }
+    }
+    // one slot for every lane in `mask` (at most 32 - a prepare() came first); returns this lane's slot inside the region
+    __device__ __forceinline__ unsigned take(unsigned mask, unsigned lane, unsigned tile, unsigned region, unsigned int* overflow)
+    {
+        const unsigned n = __popc(mask), room = end - pos, first = pos;
+        unsigned fresh = 0;
+        if (n > room) { // move on to the tile claimed ahead
+            fresh = __shfl_sync(kFull, claimed, 0);
+            ahead = false;
+            if (fresh + tile > region) { // region full: the run is flagged invalid, stores stay in bounds
+                if (lane == 0)
+                    atomicExch(overflow, 1u);
+                fresh = 0;
+            }
+            pos = fresh + (n - room);
+            end = fresh + tile;
+        } else {
+            pos += n;
+        }
+        const unsigned rank = __popc(mask & ((1u << lane) - 1u));
+        return rank < room ? first + rank : fresh + (rank - room);
+    }
+    // calls mark(slot) for every slot the warp claimed and did not use
+    template <typename Mark>
+    __device__ __forceinline__ void finish(unsigned lane, unsigned tile, unsigned region, Mark mark)
+    {
+        for (unsigned slot = pos + lane; slot < end; slot += 32)
+            mark(slot);
+        const unsigned spare = __shfl_sync(kFull, claimed, 0);
+        if (ahead && spare + tile <= region)
+            for (unsigned slot = spare + lane; slot < spare + tile; slot += 32)
+                mark(slot);
+    }
+};
 
 // ---- (b) Woodcock delta tracking (transport.hpp:640-700) -------------------------------------------
 constexpr unsigned kMaxBrickWords = 512; // bitmap of the brick grid in shared memory: at most 16384 bricks
@@ -587,19 +624,24 @@ constexpr unsigned kMaxBrickWords = 512; // bitmap of the brick grid in shared m
 #ifndef DXMCB200_TK_MINBLOCKS
 #define DXMCB200_TK_MINBLOCKS 6
 #endif
+// Persistent grid; a lane steps one photon until it leaves the world, loses Russian roulette, or a real / forced interaction
+// (or, with the empty-space traversal, an air walk) is due. When `refillBatch` lanes are empty the warp services them together:
+// lanes with an interaction due write an event record, lanes bound for the air walk a photon record (both through TileWriters),
+// and all empty lanes take the next records of the wave, straight from global memory: the warp claims tiles of kTile
+// consecutive records with one atomic, asks for the whole tile in L2 at once (prefetch), and the lanes' 64-byte loads of
+// consecutive records coalesce. With the empty-space traversal a photon stays for 3 steps on average, so the service code
+// weighs as much as the step itself, and this form of it takes a third of the instructions of the staged one it replaced (a
+// per-warp cp.async ring in shared memory, which hid the load latency but cost 190 warp instructions per warp-step in
+// bookkeeping); the latency is left to the other warps, and the shared memory it frees goes back to L1.
 template <bool kStats, bool kAir>
 __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKernel(const __grid_constant__ KernelParams P)
 {
-    __shared__ PhotonRecord ring[kThreads / 32][2 * kGroup];
-    __shared__ unsigned stage[kThreads / 32][8];
     __shared__ uint2 sPalette[256];
     __shared__ unsigned sAir[kAir ? kMaxBrickWords : 1];
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
     const unsigned myShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
-    PhotonRecord* const myRing = ring[threadIdx.x >> 5];
-    const uint64_t streamPolicy = evictFirstPolicy(); // wave records are read once: they should not displace the voxel grid in L2
     const bool paletteForm = P.world.palette != nullptr;
     if (paletteForm)
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
@@ -620,95 +662,35 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
     uint32_t state = DEAD;
     uint32_t cSteps = 0, cLookups = 0;
 
-    // ---- staging, all warp-uniform. Input: the warp claims tiles of kTile records from the shards of the wave and
-    // streams them through its ring in groups of kGroup records (group k lives in ring half k & 1); empty lanes take
-    // records from the current group. Output: event slots are claimed in tiles of kEventTile. The four values every
-    // service needs live in registers, the rest of the bookkeeping (touched once per group / tile) in shared memory.
-    unsigned ringPos = 0, ringEnd = 0; // ring slots of the current group not yet handed out: [ringPos, ringEnd)
-    unsigned outPos = 0, outEnd = 0; // event slots of the current tile not yet written
+    // input (warp-uniform): records [inPos, inEnd) of the tile in hand; tiles come from the warp's own shard first, then round the others
+    unsigned inPos = 0, inEnd = 0;
+    unsigned inShard = myShard, shardsTried = 0;
+    TileWriter events, airborne;
     unsigned exhaustedMask = 0;
     unsigned refillAt = P.refillBatch; // empty lanes that trigger a service: refillBatch + the exhausted ones
-    enum { TILE_NEXT, TILE_END, SHARDS_TRIED, ISSUED, CONSUMED, COUNT0, COUNT1, IN_SHARD };
-    volatile unsigned* const st = stage[threadIdx.x >> 5];
-    if (lane < 8)
-        st[lane] = lane == IN_SHARD ? myShard : 0u;
-    __syncwarp();
 
-    // The bookkeeping words in `st` are warp-uniform: every lane reads them, lane 0 alone writes them, with a __syncwarp
-    // between a write and the next read (compute-sanitizer racecheck runs clean on this kernel).
-    // request the next group of records into the free half of the ring (no-op when both halves are in flight)
-    auto issueGroup = [&]() {
-        const unsigned issued = st[ISSUED];
-        if (issued - st[CONSUMED] >= 2)
-            return;
-        unsigned tileNext = st[TILE_NEXT], tileEnd = st[TILE_END];
-        if (tileNext >= tileEnd) { // claim the next tile: from the warp's own shard first, then round the others
-            unsigned tried = st[SHARDS_TRIED], shard = st[IN_SHARD];
-            for (;;) {
-                if (tried >= kShards) { // every shard is drained: remember it, so that the next call returns at once
-                    __syncwarp(); // all lanes have read the words lane 0 is about to write
-                    if (lane == 0)
-                        st[SHARDS_TRIED] = tried;
-                    __syncwarp();
-                    return;
-                }
-                const unsigned n = min(P.inCursors[shard].stored, P.photonRegion); // filled by completed kernels
-                unsigned t = n;
-                if (lane == 0 && n)
-                    t = atomicAdd(&P.inCursors[shard].taken, kTile);
-                t = __shfl_sync(kFull, t, 0);
-                if (t < n) {
-                    tileNext = shard * P.photonRegion + t;
-                    tileEnd = shard * P.photonRegion + min(t + kTile, n);
-                    break;
-                }
-                shard = (shard + 1) % kShards;
-                ++tried;
+    // claim the next tile of the wave; false when every shard is drained
+    auto claimTile = [&]() {
+        while (shardsTried < kShards) {
+            const unsigned n = min(P.inCursors[inShard].stored, P.photonRegion); // filled by completed kernels
+            unsigned t = n;
+            if (lane == 0 && n)
+                t = atomicAdd(&P.inCursors[inShard].taken, kTile);
+            t = __shfl_sync(kFull, t, 0);
+            if (t < n) {
+                inPos = inShard * P.photonRegion + t;
+                inEnd = inShard * P.photonRegion + min(t + kTile, n);
+                // the whole tile on its way into L2: one 128-byte line per two records
+                const char* lines = reinterpret_cast<const char*>(P.photonsIn + inPos);
+                for (unsigned k = lane; 2 * k < inEnd - inPos; k += 32)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(lines + 128u * k));
+                return true;
             }
-            __syncwarp(); // all lanes have read the words lane 0 is about to write
-            if (lane == 0) {
-                st[IN_SHARD] = shard;
-                st[SHARDS_TRIED] = tried;
-                st[TILE_END] = tileEnd;
-            }
+            inShard = (inShard + 1) % kShards;
+            ++shardsTried;
         }
-        const unsigned half = issued & 1u;
-        const unsigned cnt = min(kGroup, tileEnd - tileNext);
-        const char* src = reinterpret_cast<const char*>(P.photonsIn + tileNext);
-        char* dst = reinterpret_cast<char*>(myRing + half * kGroup);
-#pragma unroll
-        for (unsigned t = 0; t < (kGroup * sizeof(PhotonRecord) / 16) / 32; ++t) {
-            const unsigned piece = lane + 32 * t;
-            if (piece < cnt * (sizeof(PhotonRecord) / 16))
-                cpAsync16(dst + piece * 16, src + piece * 16, streamPolicy);
-        }
-        cpAsyncCommit();
-        __syncwarp(); // all lanes have read the words lane 0 is about to write
-        if (lane == 0) {
-            st[COUNT0 + half] = cnt;
-            st[TILE_NEXT] = tileNext + kGroup;
-            st[ISSUED] = issued + 1;
-        }
-        __syncwarp();
+        return false;
     };
-    // make the oldest requested group the current one; false when the wave is drained
-    auto openGroup = [&]() {
-        const unsigned issued = st[ISSUED], consumed = st[CONSUMED];
-        if (issued == consumed)
-            return false;
-        if (issued - consumed == 2)
-            cpAsyncWait<1>(); // the older of the two groups in flight has landed
-        else
-            cpAsyncWait<0>();
-        __syncwarp();
-        const unsigned half = consumed & 1u;
-        ringPos = half * kGroup;
-        ringEnd = ringPos + st[COUNT0 + half];
-        return true;
-    };
-    issueGroup();
-    issueGroup();
-    openGroup();
 
     for (;;) {
         // ---- one Woodcock step (transport.hpp:655-682)
@@ -767,58 +749,36 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
         const unsigned notStepping = __ballot_sync(kFull, state != STEP); // lanes with an event due, dead or exhausted
         if (static_cast<unsigned>(__popc(notStepping)) < refillAt && notStepping != kFull)
             continue; // keep stepping until enough lanes are empty
-        const unsigned eventMask = __ballot_sync(kFull, state == EVENT);
-        unsigned deadMask = __ballot_sync(kFull, state == DEAD);
 
-        // ---- lanes with an interaction due append their photon to the event buffer and become empty
+        // ---- service. Tiles for this round's (or the next one's) records are claimed first, nothing waits for them yet
+        events.prepare(P.eventCursors + myShard, kEventTile, lane);
+        if constexpr (kAir)
+            airborne.prepare(P.airCursors + myShard, kAirTile, lane);
+        // lanes with an interaction due write an event record and become empty
+        const unsigned eventMask = __ballot_sync(kFull, state == EVENT);
         if (eventMask) {
-            const unsigned n = __popc(eventMask);
-            const unsigned room = outEnd - outPos;
-            const unsigned first = outPos;
-            unsigned fresh = 0; // first slot of a newly claimed tile, when the current one cannot take all n
-            bool full = false;
-            if (n > room) {
-                if (lane == 0)
-                    fresh = atomicAdd(&P.eventCursors[myShard].stored, kEventTile);
-                fresh = __shfl_sync(kFull, fresh, 0);
-                full = fresh + kEventTile > P.eventRegion;
-                if (full && lane == 0)
-                    atomicExch(P.overflow, 1u);
-                fresh += myShard * P.eventRegion;
-                if (!full) {
-                    outPos = fresh + (n - room);
-                    outEnd = fresh + kEventTile;
-                }
-            } else {
-                outPos += n;
-            }
+            const unsigned slot = events.take(eventMask, lane, kEventTile, P.eventRegion, P.overflow);
             if (state == EVENT) {
-                const unsigned rank = __popc(eventMask & laneLt);
-                EventRecord* e = P.events + (rank < room ? first + rank : fresh + (rank - room));
-                if (full && rank >= room)
-                    e = P.events; // region overflow: the run is flagged invalid, keep the store in bounds
+                EventRecord* e = P.events + static_cast<size_t>(myShard) * P.eventRegion + slot;
                 storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, eventProbability);
                 recStore(&e->where, make_uint4(voxel, material, 0u, 0u));
                 state = DEAD;
             }
-            deadMask |= eventMask;
         }
-        if constexpr (kAir) { // ---- lanes whose photon stands in an air brick hand it to the air walk
+        if constexpr (kAir) { // lanes whose photon stands in an air brick hand it to the air walk
             const unsigned airMask = __ballot_sync(kFull, state == AIRBORNE);
             if (airMask) {
-                const size_t slot = appendSlots(P.airCursors, P.photonRegion, P.overflow, airMask, lane);
-                if (slot != kNoSlot)
-                    storePhoton(P.airborne + slot, p, rng, logE, maxAttInv, seg, 0.0f);
-                if (state == AIRBORNE)
+                const unsigned slot = airborne.take(airMask, lane, kAirTile, P.photonRegion, P.overflow);
+                if (state == AIRBORNE) {
+                    storePhoton(P.airborne + static_cast<size_t>(myShard) * P.photonRegion + slot, p, rng, logE, maxAttInv, seg, 0.0f);
                     state = DEAD;
-                deadMask |= airMask;
+                }
             }
         }
-
-        // ---- re-fill empty lanes from the ring (a second pass when the current group runs out half-way)
-#pragma unroll 1
-        for (int pass = 0; pass < 3 && deadMask; ++pass) {
-            if (ringPos == ringEnd) { // drained: nothing left to hand out in this wave
+        // empty lanes take the next records of the wave (again when a tile ends half-way, or a record is a dead marker)
+        unsigned deadMask = __ballot_sync(kFull, state == DEAD);
+        while (deadMask) {
+            if (inPos == inEnd && !claimTile()) { // drained: nothing left to hand out in this wave
                 if (state == DEAD)
                     state = EXHAUSTED;
                 exhaustedMask |= deadMask;
@@ -826,37 +786,26 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
                 break;
             }
             const unsigned rank = __popc(deadMask & laneLt);
-            if (state == DEAD && rank < ringEnd - ringPos) {
-                const PhotonRecord* r = myRing + ringPos + rank;
-                const float4 a = r->posE, b = r->dirW, d = r->lut;
-                const uint4 c = r->rng;
-                p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
-                p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
-                rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
-                rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
-                logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z);
+            if (state == DEAD && rank < inEnd - inPos) {
+                float unused;
+                loadPhoton(P.photonsIn + inPos + rank, p, rng, logE, maxAttInv, seg, unused);
                 lowWeight = p.energy * p.weight < kRouletteThreshold;
-                state = STEP;
+                state = p.energy > 0.0f ? STEP : DEAD; // energy 0: an unused slot of an interactKernel tile
             }
-            ringPos = min(ringEnd, ringPos + static_cast<unsigned>(__popc(deadMask)));
+            inPos = min(inEnd, inPos + static_cast<unsigned>(__popc(deadMask)));
             deadMask = __ballot_sync(kFull, state == DEAD);
-            if (ringPos == ringEnd) { // group handed out completely: recycle its half, move on to the next group
-                const unsigned consumed = st[CONSUMED];
-                __syncwarp(); // every lane has read its record (and the counter) before the half is requested again
-                if (lane == 0)
-                    st[CONSUMED] = consumed + 1;
-                __syncwarp();
-                issueGroup();
-                openGroup(); // leaves ringPos == ringEnd when the wave is drained
-            }
         }
         if (exhaustedMask == kFull)
             break;
     }
-    cpAsyncWait<0>();
-    // mark the unused slots of the warp's last event tile
-    for (unsigned slot = outPos + lane; slot < outEnd; slot += 32)
-        recStore(&P.events[slot].where, make_uint4(0u, kNoEvent, 0u, 0u));
+    // dead markers in what is left of the warp's tiles
+    events.finish(lane, kEventTile, P.eventRegion, [&](unsigned slot) {
+        recStore(&P.events[static_cast<size_t>(myShard) * P.eventRegion + slot].where, make_uint4(0u, kNoEvent, 0u, 0u));
+    });
+    if constexpr (kAir)
+        airborne.finish(lane, kAirTile, P.photonRegion, [&](unsigned slot) {
+            recStore(&P.airborne[static_cast<size_t>(myShard) * P.photonRegion + slot].posE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        });
 
     if constexpr (kStats) {
         const unsigned long long s = warpSum(cSteps), l = warpSum(cLookups);
@@ -887,10 +836,29 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     // as unused.
     const unsigned nSlots = min(P.eventCursors[shard].stored, P.eventRegion);
     const EventRecord* const region = P.events + static_cast<size_t>(shard) * P.eventRegion;
+    // survivors go to the next wave through a TileWriter: its atomic is issued at the start of a trip and hides behind the sampling
+    const unsigned outShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
+    TileWriter out;
+    unsigned survivors = 0; // photons this warp has stored
     for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
         const unsigned i = base + threadIdx.x;
+#if DXMCB200_INTERACT_PREFETCH
+        { // the events of the warp's next trip: 32 x 80 bytes = 20 lines
+            const unsigned next = base + blocksPerShard * kThreads + (threadIdx.x & ~31u);
+            if (next < nSlots && lane < 20u) {
+                const char* line = reinterpret_cast<const char*>(region + next) + 128u * lane;
+#if DXMCB200_INTERACT_PREFETCH == 1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
+#else
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
+#endif
+            }
+        }
+#endif
         const EventRecord* e = region + min(i, nSlots - 1u);
         const uint4 where = i < nSlots ? recLoad(&e->where) : make_uint4(0u, kNoEvent, 0u, 0u);
+        if (__any_sync(kFull, where.y != kNoEvent))
+            out.prepare(P.outCursors + outShard, kSurvivorTile, lane);
         bool alive = false; // the photon goes on to the next wave
         bool done = false; // the interaction has been sampled (false: no event in this slot)
         bool energyChanged = false;
@@ -965,10 +933,16 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
         const unsigned aliveMask = __ballot_sync(kFull, alive);
         if (aliveMask == 0)
             continue;
-        PhotonRecord* r = appendPhotons(P, aliveMask, lane);
-        if (r)
-            storePhoton(r, p, rng, logE, maxAttInv, seg, 0.0f);
+        survivors += __popc(aliveMask);
+        const unsigned slot = out.take(aliveMask, lane, kSurvivorTile, P.photonRegion, P.overflow);
+        if (alive)
+            storePhoton(P.photonsOut + static_cast<size_t>(outShard) * P.photonRegion + slot, p, rng, logE, maxAttInv, seg, 0.0f);
     }
+    if (lane == 0 && survivors)
+        atomicAdd(&P.outCursors[outShard].live, survivors);
+    out.finish(lane, kSurvivorTile, P.photonRegion, [&](unsigned slot) { // dead markers (energy 0): transportKernel drops them at the re-fill
+        recStore(&P.photonsOut[static_cast<size_t>(outShard) * P.photonRegion + slot].posE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    });
     if constexpr (kStats) {
         const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
         if (lane == 0) {
@@ -1016,8 +990,10 @@ __global__ void resetCursorsKernel(ShardCursor* cursors, int storedToo)
 {
     {
         cursors[threadIdx.x].taken = 0;
-        if (storedToo)
+        if (storedToo) {
             cursors[threadIdx.x].stored = 0;
+            cursors[threadIdx.x].live = 0;
+        }
     }
 }
 
@@ -1406,7 +1382,8 @@ struct dxmcb200_ctx {
         WaveCursors* dCursors = nullptr;
         WaveCursors* hCursors = nullptr; // pinned host copy for the per-wave read-back
         int cur = 0;
-        unsigned survivors = 0;
+        unsigned survivors = 0; // slots of the next wave's buffer that hold records (a few of them dead markers)
+        unsigned alive = 0; // photons among them
         bool pending = false;
     } pipes[kMaxPipes];
     int nPipes = 2;
@@ -1719,8 +1696,10 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     const int nPipes = total >= 4 * static_cast<uint64_t>(c->waveRecords) ? c->nPipes : 1; // small runs: one pipeline
     const uint64_t wave = std::max<uint64_t>(std::min<uint64_t>(c->waveRecords, total), 1024);
     const uint64_t warpsPerShard = (static_cast<uint64_t>(maxTransportBlocks(c)) * (kThreads / 32) + kShards - 1) / kShards;
-    const uint64_t photonRegion = ((wave + wave / 2) / kShards + 1024 + 15) & ~15ULL;
-    const uint64_t eventRegion = (photonRegion + warpsPerShard * kEventTile + kEventTile - 1) / kEventTile * kEventTile;
+    // + the tiles interactKernel's warps hold open (two per warp, at most 8 blocks of 8 warps per SM)
+    const uint64_t tileSlack = (static_cast<uint64_t>(c->smCount) * 64 / kShards + 1) * 2 * kSurvivorTile;
+    const uint64_t photonRegion = ((wave + wave / 2) / kShards + 1024 + tileSlack + 15) & ~15ULL;
+    const uint64_t eventRegion = (photonRegion + 2 * warpsPerShard * kEventTile + kEventTile - 1) / kEventTile * kEventTile; // a warp holds up to two tiles
     if (photonRegion > c->photonRegion || eventRegion > c->eventRegion) {
         for (auto& pipe : c->pipes) {
             hostio::poolFree(pipe.dPhotons[0]);
@@ -1788,7 +1767,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         if (air)
             resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->air, 1);
         // (a) births
-        const uint64_t births = std::min<uint64_t>(wave - pipe.survivors, total - issuedHistories);
+        const uint64_t births = std::min<uint64_t>(wave - std::min<uint64_t>(pipe.alive, wave), total - issuedHistories);
         P.photonsOut = pipe.dPhotons[cur];
         P.outCursors = pipe.dCursors->photons[cur];
         CU_CHECK(c, cudaEventRecord(pipe.mark[0], pipe.stream));
@@ -1859,14 +1838,17 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             c->error = "wave buffer region overflow";
             return DXMCB200_ERR_STATE;
         }
-        uint64_t alive = 0;
-        for (unsigned k = 0; k < kShards; ++k)
-            alive += pipe.hCursors->photons[nxt][k].stored;
+        uint64_t slots = 0, alive = 0;
+        for (unsigned k = 0; k < kShards; ++k) {
+            slots += pipe.hCursors->photons[nxt][k].stored;
+            alive += pipe.hCursors->photons[nxt][k].live;
+        }
         if (alive > wave) {
             c->error = "wave buffer overflow";
             return DXMCB200_ERR_STATE;
         }
-        pipe.survivors = static_cast<unsigned>(alive);
+        pipe.survivors = static_cast<unsigned>(slots);
+        pipe.alive = static_cast<unsigned>(alive);
         pipe.cur = nxt;
         return DXMCB200_OK;
     };
@@ -1876,6 +1858,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         auto& pipe = c->pipes[i];
         pipe.cur = 0;
         pipe.survivors = 0;
+        pipe.alive = 0;
         pipe.pending = false;
         CU_CHECK(c, cudaMemsetAsync(pipe.dCursors, 0, sizeof(WaveCursors), pipe.stream));
     }
@@ -1898,7 +1881,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
             status = DXMCB200_ERR_CANCELLED;
             break;
         }
-        if (issuedHistories < total || pipe.survivors > 0) {
+        if (issuedHistories < total || pipe.alive > 0) { // dead markers alone (survivors > 0, alive == 0) are not worth a wave
             status = enqueueWave(pipe);
             if (status != DXMCB200_OK)
                 break;
