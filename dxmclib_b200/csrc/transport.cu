@@ -67,6 +67,7 @@ struct alignas(16) EventRecord {
     uint4 where; // voxel index, material | measurement << 8 (kNoEvent marks an unused slot), 0, 0
 };
 constexpr uint32_t kNoEvent = 0xffffffffu;
+constexpr uint32_t kInAirBrick = 0x10000u; // bit 16 of a voxel record's second word: the voxel lies in an air brick (flagRecordsKernel)
 
 // Every buffer is split into kShards regions with their own append / claim cursors on separate 128-byte lines:
 // tens of thousands of warps appending through ONE counter serialise in a single L2 atomic unit (measured: the
@@ -619,7 +620,7 @@ struct TileWriter {
 };
 
 // ---- (b) Woodcock delta tracking (transport.hpp:640-700) -------------------------------------------
-constexpr unsigned kMaxBrickWords = 512; // bitmap of the brick grid in shared memory: at most 16384 bricks
+constexpr unsigned kMaxBrickWords = 512; // the brick grid holds at most 16384 bricks (rule shared with the CPU restatement)
 
 #ifndef DXMCB200_TK_MINBLOCKS
 #define DXMCB200_TK_MINBLOCKS 6
@@ -637,7 +638,6 @@ template <bool kStats, bool kAir>
 __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKernel(const __grid_constant__ KernelParams P)
 {
     __shared__ uint2 sPalette[256];
-    __shared__ unsigned sAir[kAir ? kMaxBrickWords : 1];
 
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
@@ -645,14 +645,9 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
     const bool paletteForm = P.world.palette != nullptr;
     if (paletteForm)
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
-    if constexpr (kAir) {
-        for (unsigned k = threadIdx.x; k < P.bricks.nWords; k += kThreads)
-            sAir[k] = P.bricks.air[k];
-    }
     __syncthreads();
     // shared-state-space address of the table: the look-up below is one LEA + LDS instead of a generic-window address
     const unsigned paletteBase = static_cast<unsigned>(__cvta_generic_to_shared(sPalette));
-    const unsigned airBase = static_cast<unsigned>(__cvta_generic_to_shared(sAir));
 
     Rng rng { 0, 1 };
     Photon p {};
@@ -702,9 +697,7 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
             if (!insideWorld(P.world, p.px, p.py, p.pz)) {
                 state = DEAD;
             } else {
-                uint32_t ix, iy, iz;
-                voxelCoords(P.world, p.px, p.py, p.pz, ix, iy, iz);
-                voxel = (iz * P.world.dim[1] + iy) * P.world.dim[0] + ix;
+                voxel = voxelIndex(P.world, p.px, p.py, p.pz);
                 uint2 rec;
                 // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
                 if (paletteForm) {
@@ -736,11 +729,8 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
                             lowWeight = p.energy * p.weight < kRouletteThreshold;
                         }
                     }
-                    if constexpr (kAir) { // a virtual collision in an air brick: the photon leaves for the air walk
-                        const unsigned brick = brickOfVoxel(P.bricks, ix, iy, iz);
-                        unsigned word;
-                        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(word) : "r"(airBase + 4u * (brick >> 5)));
-                        if (state == STEP && ((word >> (brick & 31u)) & 1u))
+                    if constexpr (kAir) { // a virtual collision in an air brick (bit 16 of the voxel record): the photon leaves for the air walk
+                        if (state == STEP && (material & kInAirBrick))
                             state = AIRBORNE;
                     }
                 }
@@ -1136,6 +1126,75 @@ __global__ void brickMaxKernel(WorldView w, BrickView b, const float* __restrict
     }
 }
 
+// ---- "this voxel lies in an air brick" as bit 16 of the voxel record --------------------------------------
+// transportKernel hands a photon to the air walk after a virtual collision in an air brick. Testing the brick bitmap for that
+// cost a brick index and a shared-memory look-up on 80 % of all steps (7 % of the kernel's instructions); with the answer in
+// the record the look-up brings it along. Record grids get the bit per voxel. Palette grids get, for every entry that can
+// occur in an air brick, a second entry with the bit set, and the voxels inside air bricks are re-indexed to it (the tables
+// `baseOf` / `flaggedOf` map an index to its plain and its flagged entry, so the pass can be repeated for another brick grid).
+
+__device__ __forceinline__ bool voxelInAirBrick(const WorldView& w, const BrickView& b, const uint32_t* __restrict__ bitmap, uint32_t voxel)
+{
+    const uint32_t plane = w.dim[0] * w.dim[1];
+    const uint32_t iz = voxel / plane, rem = voxel - iz * plane;
+    const uint32_t iy = rem / w.dim[0], ix = rem - iy * w.dim[0];
+    const uint32_t brick = brickOfVoxel(b, ix, iy, iz);
+    return (bitmap[brick >> 5] >> (brick & 31u)) & 1u;
+}
+
+// bitmap == nullptr clears the flags
+__global__ void flagRecordsKernel(WorldView w, BrickView b, const uint32_t* __restrict__ bitmap, uint64_t n, uint2* __restrict__ voxels)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        uint2 r = voxels[i];
+        const uint32_t y = (r.y & ~kInAirBrick) | (bitmap && voxelInAirBrick(w, b, bitmap, static_cast<uint32_t>(i)) ? kInAirBrick : 0u);
+        if (y != r.y) {
+            r.y = y;
+            voxels[i] = r;
+        }
+    }
+}
+
+// remap = baseOf[256] followed by flaggedOf[256]
+__global__ void flagPaletteKernel(WorldView w, BrickView b, const uint32_t* __restrict__ bitmap, uint64_t n, const uint8_t* __restrict__ remap,
+    uint8_t* __restrict__ palette, int nibbles)
+{
+    __shared__ uint8_t sRemap[512];
+    for (unsigned k = threadIdx.x; k < 512; k += blockDim.x)
+        sRemap[k] = remap[k];
+    __syncthreads();
+    auto mapped = [&](uint64_t voxel, unsigned index) -> unsigned {
+        const unsigned plain = sRemap[index];
+        return bitmap && voxelInAirBrick(w, b, bitmap, static_cast<uint32_t>(voxel)) ? sRemap[256 + plain] : plain;
+    };
+    const uint64_t items = nibbles ? (n + 1) / 2 : n; // bytes
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < items; i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const unsigned old = palette[i];
+        unsigned now;
+        if (nibbles) {
+            const unsigned lo = mapped(2 * i, old & 15u);
+            const unsigned hi = 2 * i + 1 < n ? mapped(2 * i + 1, old >> 4) : 0u;
+            now = lo | (hi << 4);
+        } else {
+            now = mapped(i, old);
+        }
+        if (now != old)
+            palette[i] = static_cast<uint8_t>(now);
+    }
+}
+
+// a palette grid that has outgrown its form: 4-bit indices to bytes, bytes to 8-byte records
+__global__ void expandNibblesKernel(const uint8_t* __restrict__ nibbles, uint64_t n, uint8_t* __restrict__ bytes)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        bytes[i] = (nibbles[i >> 1] >> ((i & 1u) * 4u)) & 15u;
+}
+__global__ void expandPaletteKernel(const uint8_t* __restrict__ palette, const uint2* __restrict__ table, uint64_t n, uint2* __restrict__ voxels)
+{
+    for (uint64_t i = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<uint64_t>(gridDim.x) * blockDim.x)
+        voxels[i] = table[palette[i]];
+}
+
 // Per-material maximum density of the grid: the input of the Woodcock majorant (attenuationinterpolator.hpp:48-59,
 // where it is one transform_reduce(init 0, max) over all voxels per material). Positive floats order like their bit
 // patterns; a negative, -0.0f or NaN density (nothing upstream rejects them) counts as 0, exactly like std::max(0, x)
@@ -1332,6 +1391,10 @@ struct dxmcb200_ctx {
     uint2* dPaletteTable = nullptr; // ... into this 256-entry record table
     bool allowPalette = true;
     bool allowNibbles = true;
+    unsigned paletteCount = 0; // distinct records of the grid = plain entries of the palette table
+    std::vector<uint2> hPaletteBase; // host copy of the plain entries
+    bool voxelsFlagged = false; // the grid carries air-brick flags (bit 16 of the records) of some brick grid
+    uint8_t* dPaletteRemap = nullptr; // baseOf[256], flaggedOf[256] of the flagged palette
     // tracking: 1 = Woodcock + empty-space traversal through air bricks (default), 0 = the reference's Woodcock loop with the
     // global majorant everywhere (DXMCB200_TRACKING, dxmcb200_set_tracking)
     int tracking = 1;
@@ -1490,6 +1553,12 @@ unsigned maxTransportBlocks(const dxmcb200_ctx* c)
 // shortest brick edge in mm is doubled (ties: z before y before x).
 constexpr uint64_t kMaxBricks = static_cast<uint64_t>(kMaxBrickWords) * 32;
 constexpr double kAirThreshold = 0.02;
+inline float __uint_as_float_host(uint32_t bits)
+{
+    float f;
+    std::memcpy(&f, &bits, sizeof f);
+    return f;
+}
 
 void brickLayout(const uint64_t dim[3], const float spacing[3], float brickMm, uint32_t shift[3], uint32_t nb[3])
 {
@@ -1513,6 +1582,94 @@ void brickLayout(const uint64_t dim[3], const float spacing[3], float brickMm, u
     }
 }
 
+// Write the air-brick flags of brick grid `b` into the voxel records (b == nullptr: clear them); see flagRecordsKernel.
+// `ratio` as in ensureBricks. A palette grid whose flagged entries no longer fit its form is widened: 4-bit indices to bytes,
+// bytes to 8-byte records.
+int applyAirFlags(dxmcb200_ctx* c, const BrickView* b, const std::vector<float>& ratio)
+{
+    const uint64_t n = c->nVoxels;
+    const BrickView none {};
+    if (c->voxelsFlagged) { // flags of a former brick grid: every voxel back to its plain record
+        if (c->dPalette)
+            flagPaletteKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->world, none, nullptr, n, c->dPaletteRemap, c->dPalette, static_cast<int>(c->world.paletteNibbles));
+        else
+            flagRecordsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->world, none, nullptr, n, c->dVoxels);
+        CU_CHECK(c, cudaGetLastError());
+        CU_CHECK(c, cudaStreamSynchronize(c->stream));
+        c->voxelsFlagged = false;
+    }
+    if (!b)
+        return DXMCB200_OK;
+    if (c->dPalette) {
+        // plain entries that can occur in an air brick get a flagged twin behind the plain ones
+        std::vector<uint8_t> remap(512, 0);
+        std::vector<uint2> table(c->hPaletteBase);
+        unsigned total = c->paletteCount;
+        for (unsigned i = 0; i < c->paletteCount; ++i) {
+            remap[i] = static_cast<uint8_t>(i);
+            remap[256 + i] = static_cast<uint8_t>(i);
+            const uint2 r = table[i];
+            const float f = __uint_as_float_host(r.x) * ratio[r.y & 0xffu];
+            const bool airLike = !(r.y & 0xff00u) && !(1.001 * static_cast<double>(f > 0.0f ? f : 0.0f) > kAirThreshold);
+            if (!airLike)
+                continue;
+            if (total < 256) {
+                table[total] = make_uint2(r.x, r.y | kInAirBrick);
+                remap[total] = static_cast<uint8_t>(i);
+                remap[256 + i] = static_cast<uint8_t>(total);
+            }
+            ++total;
+        }
+        if (total > 256) { // no room for the twins: 8-byte records from here on
+            CU_CHECK(c, hostio::poolAlloc(c->device, &c->dVoxels, n * sizeof(uint2)));
+            if (c->world.paletteNibbles) {
+                uint8_t* bytes = nullptr;
+                CU_CHECK(c, hostio::poolAlloc(c->device, &bytes, n));
+                expandNibblesKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dPalette, n, bytes);
+                expandPaletteKernel<<<gridFor(c, n), 256, 0, c->stream>>>(bytes, c->dPaletteTable, n, c->dVoxels);
+                CU_CHECK(c, cudaStreamSynchronize(c->stream));
+                hostio::poolFree(bytes);
+            } else {
+                expandPaletteKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dPalette, c->dPaletteTable, n, c->dVoxels);
+                CU_CHECK(c, cudaStreamSynchronize(c->stream));
+            }
+            hostio::poolFree(c->dPalette);
+            cudaFree(c->dPaletteTable);
+            c->dPalette = nullptr;
+            c->dPaletteTable = nullptr;
+            c->world.palette = nullptr;
+            c->world.paletteTable = nullptr;
+            c->world.paletteNibbles = 0;
+            c->world.voxels = c->dVoxels;
+        } else {
+            if (c->world.paletteNibbles && total > 16) { // 4-bit indices no longer do
+                uint8_t* bytes = nullptr;
+                CU_CHECK(c, hostio::poolAlloc(c->device, &bytes, n));
+                expandNibblesKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->dPalette, n, bytes);
+                CU_CHECK(c, cudaStreamSynchronize(c->stream));
+                hostio::poolFree(c->dPalette);
+                c->dPalette = bytes;
+                c->world.palette = bytes;
+                c->world.paletteNibbles = 0;
+            }
+            if (!c->dPaletteRemap)
+                CU_CHECK(c, cudaMalloc(&c->dPaletteRemap, 512));
+            CU_CHECK(c, cudaMemcpyAsync(c->dPaletteRemap, remap.data(), 512, cudaMemcpyHostToDevice, c->stream));
+            CU_CHECK(c, cudaMemcpyAsync(c->dPaletteTable, table.data(), 256 * sizeof(uint2), cudaMemcpyHostToDevice, c->stream));
+            flagPaletteKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->world, *b, b->air, n, c->dPaletteRemap, c->dPalette, static_cast<int>(c->world.paletteNibbles));
+            CU_CHECK(c, cudaGetLastError());
+            CU_CHECK(c, cudaStreamSynchronize(c->stream)); // `remap` and `table` live on this stack frame
+            c->voxelsFlagged = true;
+            return DXMCB200_OK;
+        }
+    }
+    flagRecordsKernel<<<gridFor(c, n), 256, 0, c->stream>>>(c->world, *b, b->air, n, c->dVoxels);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    c->voxelsFlagged = true;
+    return DXMCB200_OK;
+}
+
 // Classify the bricks of the uploaded grid against the uploaded attenuation fits (once per world / table pair).
 int ensureBricks(dxmcb200_ctx* c)
 {
@@ -1525,6 +1682,9 @@ int ensureBricks(dxmcb200_ctx* c)
     c->hAir.clear();
     c->hDistance.clear();
     if (c->tracking == 0) {
+        const int st = applyAirFlags(c, nullptr, {});
+        if (st != DXMCB200_OK)
+            return st;
         c->bricksValid = true;
         return DXMCB200_OK;
     }
@@ -1622,7 +1782,7 @@ int ensureBricks(dxmcb200_ctx* c)
         c->fAir = static_cast<float>(std::max(fAir, 1.0e-6));
         b.invFAir = 1.0f / c->fAir;
         b.nWords = static_cast<uint32_t>(bitmap.size());
-        cudaFree(c->dBrickBits);
+    cudaFree(c->dBrickBits);
         cudaFree(c->dBrickDistance);
         c->dBrickBits = nullptr;
         c->dBrickDistance = nullptr;
@@ -1634,6 +1794,11 @@ int ensureBricks(dxmcb200_ctx* c)
         b.distance = c->dBrickDistance;
     }
     c->bricks = b; // nWords == 0: no air bricks, the kernels without the traversal run
+    {
+        const int st = applyAirFlags(c, nAir > 0 ? &b : nullptr, ratio);
+        if (st != DXMCB200_OK)
+            return st;
+    }
     c->bricksValid = true;
     return DXMCB200_OK;
 }
@@ -2015,6 +2180,7 @@ void dxmcb200_destroy(dxmcb200_ctx* c)
     cudaFree(c->dBeamBlob);
     cudaFree(c->dExposures);
     cudaFree(c->dPrefix);
+    cudaFree(c->dPaletteRemap);
     cudaFree(c->dBrickBits);
     cudaFree(c->dBrickDistance);
     lap("world, tables");
@@ -2168,6 +2334,9 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
             CU_CHECK(c, cudaStreamSynchronize(c->stream));
             palette = true;
             c->world.paletteNibbles = static_cast<uint32_t>(nibbles);
+            c->paletteCount = distinct;
+            c->hPaletteBase.assign(256, make_uint2(0u, 0u));
+            CU_CHECK(c, cudaMemcpy(c->hPaletteBase.data(), c->dPaletteTable, 256 * sizeof(uint2), cudaMemcpyDeviceToHost));
         }
         cudaFree(dTable);
         cudaFree(dSlotIndex);
@@ -2195,6 +2364,7 @@ int dxmcb200_set_world(dxmcb200_ctx* c, const dxmcb200_world* w)
     c->world.palette = c->dPalette;
     c->world.paletteTable = c->dPaletteTable;
     c->bricksValid = false;
+    c->voxelsFlagged = false;
 
     // Optional (DXMCB200_L2PERSIST=<MB>, 1 = as much as the device allows): keep the voxel grid in L2 with a persisting carve-out
     // of that size + an access-policy window on every pipeline's stream. Measured on B200 it LOWERS throughput at every size
