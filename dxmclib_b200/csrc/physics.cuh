@@ -313,7 +313,8 @@ __device__ __forceinline__ bool inAirBrick(const WorldView& w, const BrickView& 
     return airBit(b.air, brickOfVoxel(b, ix, iy, iz));
 }
 
-// Ray parameter at which the photon's ray leaves the run of air bricks it starts in; `exits`: the ray leaves the grid there.
+// Ray parameter at which the photon's ray leaves the run of air bricks it starts in (or has crossed DXMCB200_WALK_MAX_CUBES all-air
+// cubes of it); `exits`: the ray leaves the grid there.
 // A parametric ray / grid traversal (Siddon 1985, Amanatides & Woo 1987) over the brick grid that does not stop at every
 // brick face: from an air brick b the ray crosses, in one step, the largest cube of air bricks that has b as its corner and
 // opens in the ray's octant of directions (edge k bricks, tabulated per octant and brick: 2-3 steps per walk on the bench
@@ -322,6 +323,7 @@ __device__ __forceinline__ bool inAirBrick(const WorldView& w, const BrickView& 
 // CPU restatement (oracle/dxmc_oracle.cpp, airRunLength) computes the same bits.
 __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickView& b, const Photon& p, bool& exits, uint32_t& crossed)
 {
+    crossed = 0;
     const float pos[3] = { p.px, p.py, p.pz };
     const float dir[3] = { p.dx, p.dy, p.dz };
     int brick[3], step[3];
@@ -378,6 +380,8 @@ __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickVie
             return travelled;
         }
         if (!airBit(b.air, (static_cast<uint32_t>(brick[2]) * b.nb[1] + static_cast<uint32_t>(brick[1])) * b.nb[0] + static_cast<uint32_t>(brick[0])))
+            return travelled;
+        if (crossed >= DXMCB200_WALK_MAX_CUBES) // the run goes on, this walk does not: the photon rejoins the Woodcock steps on this face
             return travelled;
     }
 }

@@ -54,6 +54,13 @@ typedef struct dxmcb200_world {
 
 enum { DXMCB200_RITA_N = 56, DXMCB200_SPLINE_N = 16, DXMCB200_SHELLS = 12, DXMCB200_SHELL_FLOATS = 11,
     DXMCB200_SPLINE_FLOATS = 63 };
+/* tracking mode 1: an air walk crosses at most this many all-air cubes; a photon that is still in air then rejoins the Woodcock
+ * steps where it stands (and is picked up by the next walk). Bounds the trip count of the walk loop, whose slowest lane sets a
+ * warp's pace; shared with the CPU restatement so that both walk draw for draw alike. */
+#ifndef DXMCB200_WALK_MAX_CUBES_VALUE
+#define DXMCB200_WALK_MAX_CUBES_VALUE 3
+#endif
+enum { DXMCB200_WALK_MAX_CUBES = DXMCB200_WALK_MAX_CUBES_VALUE };
 
 /* AttenuationLut<T> flattened (reference attenuationlut.hpp:267-274, attenuationinterpolator.hpp:37-45).
  * All arrays are HOST pointers, copied. */

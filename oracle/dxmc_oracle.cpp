@@ -859,6 +859,7 @@ struct Oracle {
         const std::uint8_t* edge = bricks.distance.data() + octant * nBricks;
         exits = false;
         T travelled = 0;
+        int cubes = 0;
         for (;;) {
             const std::int64_t k = edge[(static_cast<std::size_t>(b[2]) * bricks.nb[1] + static_cast<std::size_t>(b[1])) * bricks.nb[0] + static_cast<std::size_t>(b[0])];
             T t[3];
@@ -894,6 +895,8 @@ struct Oracle {
                 }
             const std::uint32_t bb[3] = { static_cast<std::uint32_t>(b[0]), static_cast<std::uint32_t>(b[1]), static_cast<std::uint32_t>(b[2]) };
             if (!airBrick(bb))
+                return travelled;
+            if (++cubes >= DXMCB200_WALK_MAX_CUBES) // the run goes on, this walk does not: the photon rejoins the Woodcock steps on this face
                 return travelled;
         }
     }

@@ -300,3 +300,10 @@ def compare_dose(a_sum, a_sum2, b_sum, b_sum2, rel_err_limit=0.02, n_sigma=3.0):
         return 0.0, 0, 0.0
     z = np.abs(a_sum[sel] - b_sum[sel]) / np.sqrt(sa[sel] ** 2 + sb[sel] ** 2)
     return float((z > n_sigma).mean()), int(sel.sum()), float(z.max())
+
+
+def allowed_outliers(tested, n_sigma_tail=0.0027):
+    """Voxels allowed beyond 3 sigma when two correct, statistically independent runs are compared over `tested` voxels: the
+    Gaussian tail puts 0.27 % of them there, the count is binomial, the bound is its mean plus three standard deviations (+1)."""
+    expected = n_sigma_tail * tested
+    return expected + 3.0 * np.sqrt(expected) + 1.0

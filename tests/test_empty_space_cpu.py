@@ -46,7 +46,7 @@ def test_mode1_statistically_equivalent_to_reference_tracking(product, name, bui
 
     outside, tested, worst = T.compare_dose(blocks(a), blocks(a2), blocks(b), blocks(b2), rel_err_limit=0.05)
     assert tested >= 50
-    assert outside <= 0.01 and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
+    assert outside * tested <= T.allowed_outliers(tested) and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
 
 
 def test_mode1_without_air_bricks_is_mode0(product):

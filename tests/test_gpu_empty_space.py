@@ -143,7 +143,7 @@ def test_statistically_equivalent_to_plain_woodcock(gpu, product, name, historie
     assert abs(int(aev.sum()) - int(bev.sum())) < 2e-3 * int(aev.sum())
     outside, tested, worst = T.compare_dose(a, a2, b, b2)
     assert tested >= 100, "scene too sparse for the per-voxel criterion"
-    assert outside <= 0.004 and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
+    assert outside * tested <= T.allowed_outliers(tested) and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f})"
 
 
 def test_schedule_invariance_with_air_walks(gpu, product, monkeypatch):

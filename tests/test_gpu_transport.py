@@ -76,8 +76,7 @@ def test_live_reference_three_sigma(gpu, product, reference, name, builder, mode
     # Two correct, statistically INDEPENDENT runs put 0.27 % of the voxels beyond 3 sigma (Gaussian tails); the count over `tested`
     # voxels is binomial, so the bound is its mean plus three standard deviations (tracking 1). With identical streams on both
     # sides (tracking 0) the differences are far smaller than the combined sigma and the plain 0.3 % bound holds with room.
-    expected = 0.0027 * tested
-    allowed = 0.003 * tested if tracking == "0" else expected + 3.0 * np.sqrt(expected) + 1.0
+    allowed = 0.003 * tested if tracking == "0" else T.allowed_outliers(tested)
     assert outside * tested <= allowed and worst < 5.0, f"{outside:.4%} of {tested} voxels beyond 3 sigma (worst {worst:.2f}, allowed {allowed:.1f} voxels)"
 
 
