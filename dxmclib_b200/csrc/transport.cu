@@ -2979,6 +2979,22 @@ int dxmcb200_get_bricks(dxmcb200_ctx* c, uint32_t shift[3], uint32_t nb[3], floa
     return DXMCB200_OK;
 }
 
+int dxmcb200_get_grid_form(dxmcb200_ctx* c, int* bitsPerVoxel, uint32_t* distinctRecords)
+{
+    if (!c || !bitsPerVoxel || (!c->dVoxels && !c->dPalette))
+        return DXMCB200_ERR_STATE;
+    if (c->dLutBlob) { // the air-brick flags of tracking mode 1 may widen a palette grid
+        CU_CHECK(c, cudaSetDevice(c->device));
+        const int st = ensureBricks(c);
+        if (st != DXMCB200_OK)
+            return st;
+    }
+    *bitsPerVoxel = c->dPalette ? (c->world.paletteNibbles ? 4 : 8) : 64;
+    if (distinctRecords)
+        *distinctRecords = c->dPalette ? c->paletteCount : 0u;
+    return DXMCB200_OK;
+}
+
 int dxmcb200_enable_stats(dxmcb200_ctx* c, int on)
 {
     if (!c)

@@ -213,6 +213,12 @@ int dxmcb200_get_bricks(dxmcb200_ctx*, uint32_t shift[3], uint32_t nb[3], float*
  * (bricks beyond the grid count as air), 0 for non-air bricks: the traversal crosses that cube in one step */
 int dxmcb200_get_brick_distance(dxmcb200_ctx*, uint8_t* distance);
 
+/* How the voxel grid is held on the device: 64 = one 8-byte record per voxel, 8 / 4 = palette indices of that many bits per voxel
+ * (grids with at most 256 / 16 distinct {density, material, measurement} records; distinct_records, optional, reports how many).
+ * With tracking mode 1 the records also say whether the voxel lies in an air brick, which can take a palette grid to the next
+ * wider form; the answer is the form the kernels will read. */
+int dxmcb200_get_grid_form(dxmcb200_ctx*, int* bits_per_voxel, uint32_t* distinct_records);
+
 /* zero the accumulators and counters */
 int dxmcb200_clear(dxmcb200_ctx*);
 

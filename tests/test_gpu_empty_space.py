@@ -115,6 +115,42 @@ def test_record_grid_follows_oracle(gpu, product):
     ctx.close()
 
 
+# the scene has air + three denser materials: 3 * tissue_records + air_records plain records, air_records flagged twins
+@pytest.mark.parametrize("tissue_records,air_records,bits", [(4, 1, 4), (4, 3, 8), (83, 7, 64)])
+def test_air_brick_flags_widen_the_palette_and_change_nothing(gpu, product, tissue_records, air_records, bits, monkeypatch):
+    """Tracking mode 1 writes "this voxel lies in an air brick" into the voxel records; a palette grid gets flagged twins of the
+    entries that occur in air bricks and is widened (4-bit -> byte -> 8-byte records) when they do not fit. Whatever form results,
+    the accumulators are the bits of the plain 8-byte record grid."""
+    sc = T.air_gap_scene(product, histories=20000, exposures=4)
+    flat = dict(T.flatten_scene(sc))
+    d, m = flat["density"].copy(), flat["material"]
+    air = d < 0.01
+    assert air.any() and (~air).any()
+    idx = np.arange(d.size)
+    dense = np.flatnonzero(~air)
+    d[dense] = (d[dense] * (1.0 - 1e-3 * (idx[dense] % tissue_records))).astype(np.float32)
+    thin = np.flatnonzero(air)
+    d[thin] = (d[thin] * (1.0 - 1e-2 * (idx[thin] % air_records))).astype(np.float32)
+    flat["density"] = d
+    exps = T.exposures_of(sc)
+    grids = {}
+    for palette in ("1", "0"):
+        monkeypatch.setenv("DXMCB200_PALETTE", palette)
+        ctx = cabi.Context(0)
+        T.load_context(ctx, flat)
+        ctx.set_tracking(1, 8.0)
+        ctx.set_fixed_point(22, 12)
+        ctx.run(exps, 0, len(exps), model=1, seed=31)
+        grids[palette] = (ctx.get_raw(), ctx.grid_form())
+        ctx.close()
+    (a, form_a), (b, form_b) = grids["1"], grids["0"]
+    assert form_b[0] == 64
+    assert form_a[0] == bits, f"{form_a[1]} distinct records ended up as {form_a[0]} bits per voxel"
+    for x, y in zip(a, b):
+        assert T.bit_equal(x, y)
+    assert a[2].sum() > 5000
+
+
 @pytest.mark.parametrize("name,histories", [("air_gap", 60_000_000), ("ct_spiral", 2_000_000)])
 def test_statistically_equivalent_to_plain_woodcock(gpu, product, name, histories):
     """Mode 1 against mode 0 (the reference's algorithm) with independent seeds: total deposited energy within 0.1 % (north_star:
