@@ -215,7 +215,8 @@ __device__ __forceinline__ void peturb(Photon& p, float theta, float phi)
 // ---- geometry (transport.hpp:485-521, 702-728) ----------------------------------------------
 __device__ __forceinline__ bool insideWorld(const WorldView& w, float x, float y, float z)
 {
-    return (x > w.ext[0] && x < w.ext[1]) && (y > w.ext[2] && y < w.ext[3]) && (z > w.ext[4] && z < w.ext[5]);
+    // six compares and-ed as predicates (no short-circuit branches: the kernels call this on every step)
+    return (x > w.ext[0]) & (x < w.ext[1]) & (y > w.ext[2]) & (y < w.ext[3]) & (z > w.ext[4]) & (z < w.ext[5]);
 }
 
 __device__ __forceinline__ void voxelCoords(const WorldView& w, float x, float y, float z, uint32_t& ix, uint32_t& iy, uint32_t& iz)

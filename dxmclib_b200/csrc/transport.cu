@@ -314,8 +314,11 @@ __device__ __forceinline__ void emitWalked(const KernelParams& P, PhotonRecord* 
 }
 
 // ---- (a) exposure-to-photon generation -------------------------------------------------------------
+#ifndef DXMCB200_WALK_MINBLOCKS
+#define DXMCB200_WALK_MINBLOCKS 6
+#endif
 template <bool kStats, bool kAir>
-__global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant__ KernelParams P)
+__global__ void __launch_bounds__(kThreads, DXMCB200_WALK_MINBLOCKS) generateKernel(const __grid_constant__ KernelParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t cHist = 0, cWorld = 0, cSteps = 0, cLookups = 0, cBricks = 0, cWalks = 0;
@@ -397,7 +400,7 @@ __global__ void __launch_bounds__(kThreads) generateKernel(const __grid_constant
 
 // photons the transport kernel left in air bricks: walk them, survivors join the NEXT wave
 template <bool kStats>
-__global__ void __launch_bounds__(kThreads) airWalkKernel(const __grid_constant__ KernelParams P)
+__global__ void __launch_bounds__(kThreads, DXMCB200_WALK_MINBLOCKS) airWalkKernel(const __grid_constant__ KernelParams P)
 {
     const unsigned lane = threadIdx.x & 31u;
     uint32_t cSteps = 0, cLookups = 0, cBricks = 0, cWalks = 0;
