@@ -302,7 +302,11 @@ __device__ __forceinline__ uint32_t axisVoxelClamped(const WorldView& w, int axi
     const float rel = __fsub_rn(x, w.ext[2 * axis]);
     if (!(rel > 0.0f))
         return 0u;
-    const uint32_t v = w.exactInverse ? __float2uint_rz(__fmul_rn(rel, w.invSpacing[axis])) : truncDiv(rel, w.spacing[axis], w.invSpacing[axis]);
+    uint32_t v;
+    if (w.exactInverse) // a uniform branch, not a select: the other side is the costlier one
+        v = __float2uint_rz(__fmul_rn(rel, w.invSpacing[axis]));
+    else
+        v = truncDiv(rel, w.spacing[axis], w.invSpacing[axis]);
     return min(v, w.dim[axis] - 1u);
 }
 
@@ -334,7 +338,7 @@ __device__ __forceinline__ float airRunLength(const WorldView& w, const BrickVie
     for (int i = 0; i < 3; ++i) {
         brick[i] = static_cast<int>(axisVoxelClamped(w, i, pos[i]) >> b.shift[i]);
         if (fabsf(dir[i]) > kDirEpsilon) {
-            inv[i] = __fdiv_rn(1.0f, dir[i]);
+            inv[i] = __frcp_rn(dir[i]); // the correctly rounded reciprocal = 1.0f / dir[i]
             step[i] = dir[i] > 0.0f ? 1 : -1;
         } else {
             inv[i] = 0.0f;
