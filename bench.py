@@ -47,8 +47,10 @@ from dxmclib_b200 import scene as S  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch of the dominant kernel, from the committed
 # `ncu --set full` capture under profiles/ (bytes); None until a capture of the current kernels is committed
-TRAFFIC_PER_LAUNCH = {"transportKernel": None, "interactKernel": None}
-TRAFFIC_SOURCE = "profiles/ (no capture of the current kernels yet)"
+TRAFFIC_PER_LAUNCH = {"transportKernel": 10_662_282_000, "interactKernel": 10_082_640_000}
+TRAFFIC_SOURCE = ("profiles/r2_v10_{transport,interact}Kernel_ncu_summary.csv: one steady-state launch (a wave of 2^26 photon segments). The captured "
+                  "transportKernel launch made 2.5e8 look-ups = 1.5 GB of algorithmic bytes; the rest of its traffic is the record hand-over "
+                  "(64 B read per segment, 80 B written per event, 64 B per air-walk photon) and the sectors of missed palette look-ups")
 
 SEED = 0xD1C02026
 MODEL = S.MODEL_LIVERMORE
@@ -417,7 +419,10 @@ def main():
                 "launches": lines[dominant]["launches"], "kernels": lines,
                 "kernel_share_of_step": {k: v[0] / max(sum(x[0] for x in per_kernel.values()), 1e-9) for k, v in per_kernel.items()},
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in per_kernel.items()},
-                "pipelines": 2, "note": "two wave pipelines overlap on the GPU, so per-kernel device times add up to more than the step",
+                "pipelines": 2, "note": "two wave pipelines overlap on the GPU, so per-kernel device times add up to more than the step. The algorithmic "
+                                        "bytes are 6 B x look-ups: the empty-space traversal removes two thirds of the reference algorithm's look-ups "
+                                        "(32 -> 11.5 per history), so `achieved`/`frac` fall while histories/s rise; the kernels are bound by instruction "
+                                        "issue and latency, not by HBM (profiles/README.md)",
                 "whole_pipeline": {"bytes_per_history": b_alg, "achieved": hist_rank * b_alg / pipeline_s / 1e9,
                                    "frac": hist_rank * b_alg / pipeline_s / 1e9 / peak},
                 "lookups_per_history": L, "score_events_per_history": Sev, "steps_per_history": st["steps"] / sample_hist,

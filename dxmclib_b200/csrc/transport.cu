@@ -637,7 +637,10 @@ constexpr unsigned kMaxBrickWords = 512; // the brick grid holds at most 16384 b
 // weighs as much as the step itself, and this form of it takes a third of the instructions of the staged one it replaced (a
 // per-warp cp.async ring in shared memory, which hid the load latency but cost 190 warp instructions per warp-step in
 // bookkeeping); the latency is left to the other warps, and the shared memory it frees goes back to L1.
-template <bool kStats, bool kAir>
+// kNibbleGrid: the voxel grid is a 4-bit palette and the spacings are powers of two (segmentation phantoms at 1 mm, the bench
+// workload): the three warp-uniform tests "palette form? 4-bit? exact inverse spacing?" leave the step loop (10 of 224 warp
+// instructions per step). false: any grid, tested at run time.
+template <bool kStats, bool kAir, bool kNibbleGrid>
 __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKernel(const __grid_constant__ KernelParams P)
 {
     __shared__ uint2 sPalette[256];
@@ -645,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
     const unsigned lane = threadIdx.x & 31u;
     const unsigned laneLt = (1u << lane) - 1u;
     const unsigned myShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
-    const bool paletteForm = P.world.palette != nullptr;
+    const bool paletteForm = kNibbleGrid || P.world.palette != nullptr;
     if (paletteForm)
         sPalette[threadIdx.x] = P.world.paletteTable[threadIdx.x];
     __syncthreads();
@@ -700,14 +703,23 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
             if (!insideWorld(P.world, p.px, p.py, p.pz)) {
                 state = DEAD;
             } else {
-                voxel = voxelIndex(P.world, p.px, p.py, p.pz);
                 uint2 rec;
                 // random look-ups have no reuse in L1: cache them in L2 only and leave L1 to the LUT coefficients
-                if (paletteForm) {
-                    const unsigned slot = paletteBase + 8u * paletteIndex(P.world, voxel);
-                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rec.x), "=r"(rec.y) : "r"(slot));
-                } else
-                    rec = __ldcg(P.world.voxels + voxel);
+                if constexpr (kNibbleGrid) {
+                    const uint32_t ix = __float2uint_rz(__fmul_rn(__fsub_rn(p.px, P.world.ext[0]), P.world.invSpacing[0]));
+                    const uint32_t iy = __float2uint_rz(__fmul_rn(__fsub_rn(p.py, P.world.ext[2]), P.world.invSpacing[1]));
+                    const uint32_t iz = __float2uint_rz(__fmul_rn(__fsub_rn(p.pz, P.world.ext[4]), P.world.invSpacing[2]));
+                    voxel = (iz * P.world.dim[1] + iy) * P.world.dim[0] + ix;
+                    const unsigned index = (static_cast<uint32_t>(__ldcg(P.world.palette + (voxel >> 1))) >> ((voxel & 1u) * 4u)) & 15u;
+                    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rec.x), "=r"(rec.y) : "r"(paletteBase + 8u * index));
+                } else {
+                    voxel = voxelIndex(P.world, p.px, p.py, p.pz);
+                    if (paletteForm) {
+                        const unsigned slot = paletteBase + 8u * paletteIndex(P.world, voxel);
+                        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(rec.x), "=r"(rec.y) : "r"(slot));
+                    } else
+                        rec = __ldcg(P.world.voxels + voxel);
+                }
                 const float density = __uint_as_float(rec.x);
                 material = rec.y;
                 if constexpr (kStats)
@@ -1541,13 +1553,27 @@ cudaError_t launchInteract(const dxmcb200_ctx* c, cudaStream_t stream, const Ker
                            : launchSharded(c, stream, interactKernel<L, false, false>, P, items);
 }
 
+template <bool kAir, bool kNibbleGrid>
+cudaError_t launchTransportForm(const dxmcb200_ctx* c, cudaStream_t stream, const KernelParams& P, uint64_t items)
+{
+    return c->collectStats ? launchPersistent(c, stream, transportKernel<true, kAir, kNibbleGrid>, P, items)
+                           : launchPersistent(c, stream, transportKernel<false, kAir, kNibbleGrid>, P, items);
+}
+cudaError_t launchTransport(const dxmcb200_ctx* c, cudaStream_t stream, const KernelParams& P, uint64_t items, bool air)
+{
+    const bool nibbleGrid = P.world.palette && P.world.paletteNibbles && P.world.exactInverse;
+    if (air)
+        return nibbleGrid ? launchTransportForm<true, true>(c, stream, P, items) : launchTransportForm<true, false>(c, stream, P, items);
+    return nibbleGrid ? launchTransportForm<false, true>(c, stream, P, items) : launchTransportForm<false, false>(c, stream, P, items);
+}
+
 unsigned maxTransportBlocks(const dxmcb200_ctx* c)
 {
     int occ[4] = { 0, 0, 0, 0 };
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], transportKernel<false, false>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], transportKernel<true, false>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], transportKernel<false, true>, kThreads, 0);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], transportKernel<true, true>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], transportKernel<false, false, false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], transportKernel<true, false, false>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], transportKernel<false, true, true>, kThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[3], transportKernel<true, true, true>, kThreads, 0);
     return static_cast<unsigned>(c->smCount) * static_cast<unsigned>(std::max({ occ[0], occ[1], occ[2], occ[3], 1 }));
 }
 
@@ -1962,12 +1988,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
         P.inCursors = pipe.dCursors->photons[cur];
         resetCursorsKernel<<<1, kShards, 0, pipe.stream>>>(pipe.dCursors->photons[cur], 0);
         CU_CHECK(c, cudaEventRecord(pipe.mark[1], pipe.stream));
-        if (air)
-            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true, true>, P, records)
-                                        : launchPersistent(c, pipe.stream, transportKernel<false, true>, P, records));
-        else
-            CU_CHECK(c, c->collectStats ? launchPersistent(c, pipe.stream, transportKernel<true, false>, P, records)
-                                        : launchPersistent(c, pipe.stream, transportKernel<false, false>, P, records));
+        CU_CHECK(c, launchTransport(c, pipe.stream, P, records, air));
         CU_CHECK(c, cudaEventRecord(pipe.mark[2], pipe.stream));
         // (b') photons left in air bricks take the air walk; (c)+(d) interactions and scoring; the survivors of both open the next wave
         P.photonsOut = pipe.dPhotons[nxt];
