@@ -61,11 +61,16 @@ struct alignas(16) PhotonRecord {
     float4 lut; // log10(E), 1/majorant, LUT segment (bits), event probability (event records only)
 };
 
-// a photon with an interaction due: 5 x 16 bytes
+// a photon with an interaction due: 4 x 16 bytes. The photon record's majorant is left out (interactKernel recomputes it in the
+// few cases the energy does not change) and the LUT segment shares a word with the voxel's material word, which has 17 bits.
 struct alignas(16) EventRecord {
-    PhotonRecord photon;
-    uint4 where; // voxel index, material | measurement << 8 (kNoEvent marks an unused slot), 0, 0
+    float4 posE; // px py pz energy
+    float4 dirW; // dx dy dz weight
+    uint4 rng; // state lo/hi, increment lo/hi
+    uint4 where; // voxel index, material | measurement << 8 | in-air-brick << 16 | LUT segment << 17 (kNoEvent marks an unused slot),
+                 // log10(E) bits, event probability bits
 };
+constexpr unsigned kSegmentShift = 17;
 constexpr uint32_t kNoEvent = 0xffffffffu;
 constexpr uint32_t kInAirBrick = 0x10000u; // bit 16 of a voxel record's second word: the voxel lies in an air brick (flagRecordsKernel)
 
@@ -164,7 +169,7 @@ __device__ __forceinline__ void energyDependent(const LutView& lut, float energy
     maxAttInv = maxAttenuationInverse(lut, logE);
 }
 
-// ---- photon records <-> registers ---------------------------------------------------------------------
+// ---- photon and event records <-> registers -----------------------------------------------------------
 // Records are written once and read once, tens of GB per wave pair: they go through L2 with the streaming (evict-first)
 // policy so that they do not push the voxel grid and the accumulator lines out of it.
 #ifndef DXMCB200_STREAM_RECORDS
@@ -220,6 +225,16 @@ __device__ __forceinline__ void loadPhoton(const PhotonRecord* r, Photon& p, Rng
     rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
     rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
     logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z), extra = d.w;
+}
+
+__device__ __forceinline__ void storeEvent(EventRecord* e, const Photon& p, const Rng& rng, float logE, uint32_t seg, uint32_t voxel, uint32_t material,
+    float eventProbability)
+{
+    recStore(&e->posE, make_float4(p.px, p.py, p.pz, p.energy));
+    recStore(&e->dirW, make_float4(p.dx, p.dy, p.dz, p.weight));
+    recStore(&e->rng, make_uint4(static_cast<uint32_t>(rng.state), static_cast<uint32_t>(rng.state >> 32), static_cast<uint32_t>(rng.inc),
+                          static_cast<uint32_t>(rng.inc >> 32)));
+    recStore(&e->where, make_uint4(voxel, material | (seg << kSegmentShift), __float_as_uint(logE), __float_as_uint(eventProbability)));
 }
 
 // -ln(r) * maxAttInv * 10 (transport.hpp:655-657) is evaluated as lg2(r) * kStepScale * maxAttInv; cm -> mm is the factor 10
@@ -306,9 +321,7 @@ __device__ __forceinline__ void emitWalked(const KernelParams& P, PhotonRecord* 
     if (eventMask) {
         const size_t slot = appendSlots(P.eventCursors, P.eventRegion, P.overflow, eventMask, lane);
         if (slot != kNoSlot) {
-            EventRecord* e = P.events + slot;
-            storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, ev.eventProbability);
-            recStore(&e->where, make_uint4(ev.voxel, ev.material, 0u, 0u));
+            storeEvent(P.events + slot, p, rng, logE, seg, ev.voxel, ev.material, ev.eventProbability);
         }
     }
 }
@@ -764,9 +777,7 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
         if (eventMask) {
             const unsigned slot = events.take(eventMask, lane, kEventTile, P.eventRegion, P.overflow);
             if (state == EVENT) {
-                EventRecord* e = P.events + static_cast<size_t>(myShard) * P.eventRegion + slot;
-                storePhoton(&e->photon, p, rng, logE, maxAttInv, seg, eventProbability);
-                recStore(&e->where, make_uint4(voxel, material, 0u, 0u));
+                storeEvent(P.events + static_cast<size_t>(myShard) * P.eventRegion + slot, p, rng, logE, seg, voxel, material, eventProbability);
                 state = DEAD;
             }
         }
@@ -874,6 +885,7 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
         Deflection turn;
         ScoreSlot score, forcedScore; // deposits of this event, scored once the warp has reconverged
         const uint32_t mat = where.y & 0xffu;
+        const uint32_t flags = where.y & ((1u << kSegmentShift) - 1u); // material | measurement << 8 | in-air-brick << 16
         // energy `imparted` was given up by the photon in a photoelectric or Compton event (transport.hpp:598-625)
         auto afterEnergyLoss = [&](float imparted) {
             if constexpr (kStats)
@@ -892,11 +904,21 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
         };
         if (where.y != kNoEvent) {
             Pending pe;
-            loadPhoton(&e->photon, p, rng, logE, maxAttInv, seg, pe.eventProbability);
+            {
+                const float4 a = recLoad(&e->posE), b = recLoad(&e->dirW);
+                const uint4 c = recLoad(&e->rng);
+                p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
+                p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
+                rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
+                rng.inc = (static_cast<uint64_t>(c.w) << 32) | c.z;
+            }
+            logE = __uint_as_float(where.z);
+            seg = where.y >> kSegmentShift;
+            pe.eventProbability = __uint_as_float(where.w);
             pe.voxel = where.x;
-            pe.material = where.y;
+            pe.material = flags;
             attenuationAt(P.lut, mat, seg, logE, pe.attPhoto, pe.attCompton, pe.attRayleigh);
-            if (where.y & 0xff00u) {
+            if (flags & 0xff00u) {
                 alive = interactForced<L, kStats, kAggregate>(P, p, pe, rng, energyChanged, cScores, score, forcedScore, turn);
                 done = true;
             } else { // the channel draw of computeInteractions (transport.hpp:590-596)
@@ -927,8 +949,12 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
                     p.weight *= factor;
                 }
             }
-            if (alive && energyChanged)
-                energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+            if (alive) { // the next wave's record carries the majorant of the photon's energy
+                if (energyChanged)
+                    energyDependent(P.lut, p.energy, logE, seg, maxAttInv);
+                else
+                    maxAttInv = maxAttenuationInverse(P.lut, logE);
+            }
         }
         if constexpr (kAggregate) {
             scoreWarp(P, score, lane);
@@ -1844,11 +1870,22 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     c->lastRunMs = 0;
     if (nExp == 0)
         return DXMCB200_OK;
+    const char* traceEnv = std::getenv("DXMCB200_TRACE");
+    const bool trace = traceEnv && traceEnv[0] == '1';
+    auto t0 = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!trace)
+            return;
+        const auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[dxmcb200]     run: %-24s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t0).count());
+        t0 = now;
+    };
     {
         const int st = ensureBricks(c);
         if (st != DXMCB200_OK)
             return st;
     }
+    lap("brick grid + air flags");
     const bool air = c->bricks.nWords > 0; // empty-space traversal on and the grid has air bricks
     if (nExp >= (1ULL << 32)) {
         c->error = "more than 2^32 exposures in one run";
@@ -2043,6 +2080,7 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     };
 
     CU_CHECK(c, cudaStreamSynchronize(c->stream)); // uploads issued on the ctx stream are visible to both pipelines
+    lap("wave buffers, prefix");
     for (int i = 0; i < nPipes; ++i) {
         auto& pipe = c->pipes[i];
         pipe.cur = 0;
@@ -2090,6 +2128,9 @@ int runRange(dxmcb200_ctx* c, const dxmcb200_exposure* hostExposures, const dxmc
     CU_CHECK(c, cudaStreamSynchronize(c->pipes[0].stream));
     float ms = 0;
     CU_CHECK(c, cudaEventElapsedTime(&ms, c->evStart, c->evStop));
+    lap("waves (host wall)");
+    if (trace)
+        std::fprintf(stderr, "[dxmcb200]     run: %-24s %8.1f ms\n", "waves (device events)", static_cast<double>(ms));
     c->lastRunMs = ms;
     c->totalMs += ms;
     if (cb)
@@ -2425,6 +2466,10 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
     if (!c || !l || !l->knots || !l->coefficients || !l->max_coefficients || !l->rita || !l->spline || !l->shells || l->n_materials == 0
         || l->n_segments == 0)
         return DXMCB200_ERR_ARG;
+    if (l->n_segments >= (1u << (32 - kSegmentShift))) { // event records keep the segment in 15 bits
+        c->error = "more than 32767 LUT segments";
+        return DXMCB200_ERR_ARG;
+    }
     CU_CHECK(c, cudaSetDevice(c->device));
     const size_t nKnots = l->n_segments;
     const size_t nCoeffIn = static_cast<size_t>(l->n_materials) * l->n_segments * 6;
