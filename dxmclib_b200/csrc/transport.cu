@@ -482,9 +482,14 @@ __device__ __forceinline__ void scoreNow(const KernelParams& P, uint32_t voxel, 
 }
 
 // kAggregate: park the deposit for scoreWarp; otherwise score at once
+// A deposit that is not a finite number is dropped: the impulse-approximation sampler inherits from the reference a 2^-32-per-draw
+// path to NaN (transport.hpp:441-455: a uniform draw of exactly 0 makes log(0) = -inf, then sqrt(-inf)), which in the reference
+// poisons the voxel's float sum and in a fixed-point sum would read as -2^63.
 template <bool kAggregate>
 __device__ __forceinline__ void deposit(const KernelParams& P, ScoreSlot& slot, uint32_t voxel, float energyImparted)
 {
+    if (!(fabsf(energyImparted) <= 3.0e38f))
+        return;
     if constexpr (kAggregate)
         slot.set(voxel, energyImparted);
     else
@@ -936,6 +941,8 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
             }
         }
         if (done) {
+            if (!(p.energy <= 3.0e38f)) // NaN or inf from the sampler (see deposit): the history ends here
+                alive = false;
             deflect(p, turn, rng); // one azimuth draw + rotation for whichever channel scattered
             if constexpr (kStats)
                 ++cInter;
@@ -1491,6 +1498,7 @@ struct dxmcb200_ctx {
         bool pending = false;
     } pipes[kMaxPipes];
     int nPipes = 2;
+    int persistentBlocks = 0; // blocks per SM of a persistent kernel; 0: occupancy / pipelines
     double kernelMs[4] = { 0, 0, 0, 0 }; // summed device time of generate / transport / air walk / interact launches since clear
     uint64_t kernelLaunches[4] = { 0, 0, 0, 0 };
     uint64_t photonRegion = 0, eventRegion = 0; // slots per shard region of the photon / event buffers
@@ -1539,7 +1547,12 @@ T* advancePtr(char*& cursor, size_t count)
 
 // persistent grid: a whole number of resident CTAs per SM, never more lanes than work items
 // with n pipelines every kernel takes 1/n of an SM's block slots so that kernels of all pipelines are co-resident
-int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy) { return std::max(1, occupancy / std::max(1, c->nPipes)); }
+int blocksPerSmFor(const dxmcb200_ctx* c, int occupancy)
+{
+    if (c->persistentBlocks > 0) // experiment (DXMCB200_PERSIST_BLOCKS): a fixed share, whatever the number of pipelines
+        return std::min(occupancy, c->persistentBlocks);
+    return std::max(1, occupancy / std::max(1, c->nPipes));
+}
 
 template <typename K>
 cudaError_t launchPersistent(const dxmcb200_ctx* c, cudaStream_t stream, K kernel, const KernelParams& P, uint64_t items)
@@ -2196,6 +2209,8 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     }
     if (const char* env = std::getenv("DXMCB200_AGGREGATE"))
         c->aggregateScores = std::clamp(std::atoi(env), -1, 1);
+    if (const char* env = std::getenv("DXMCB200_PERSIST_BLOCKS"))
+        c->persistentBlocks = std::clamp(std::atoi(env), 0, 8);
     if (const char* env = std::getenv("DXMCB200_INTERACT_FULL"))
         c->shardedFullOccupancy = env[0] == '1';
     if (const char* env = std::getenv("DXMCB200_TRACKING")) // 0: the reference's Woodcock loop everywhere, 1: + empty-space traversal
