@@ -47,10 +47,10 @@ from dxmclib_b200 import scene as S  # noqa: E402
 
 # dram__bytes_read.sum + dram__bytes_write.sum of one full-size launch of the dominant kernel, from the committed
 # `ncu --set full` capture under profiles/ (bytes); None until a capture of the current kernels is committed
-TRAFFIC_PER_LAUNCH = {"transportKernel": 10_662_282_000, "interactKernel": 10_082_640_000}
-TRAFFIC_SOURCE = ("profiles/r2_v10_{transport,interact}Kernel_ncu_summary.csv: one steady-state launch (a wave of 2^26 photon segments). The captured "
-                  "transportKernel launch made 2.5e8 look-ups = 1.5 GB of algorithmic bytes; the rest of its traffic is the record hand-over "
-                  "(64 B read per segment, 80 B written per event, 64 B per air-walk photon) and the sectors of missed palette look-ups")
+TRAFFIC_PER_LAUNCH = {"transportKernel": 9_741_176_000, "interactKernel": 8_909_366_000}
+TRAFFIC_SOURCE = ("profiles/r2_v11_{transport,interact}Kernel_ncu_summary.csv: one steady-state launch (a wave of 2^26 photon segments). The captured "
+                  "transportKernel launch made 2.3e8 look-ups = 1.4 GB of algorithmic bytes; the rest of its traffic is the record hand-over "
+                  "(64 B read per segment, 64 B written per event, 64 B per air-walk photon) and the sectors of missed palette look-ups")
 
 SEED = 0xD1C02026
 MODEL = S.MODEL_LIVERMORE
