@@ -586,9 +586,6 @@ constexpr unsigned kAirTile = 64; // air-walk slots a warp of transportKernel cl
 #ifndef DXMCB200_INTERACT_PREFETCH
 #define DXMCB200_INTERACT_PREFETCH 0
 #endif
-#ifndef DXMCB200_INTERACT_STAGE
-#define DXMCB200_INTERACT_STAGE 0
-#endif
 
 // A warp's private window into its shard region of an output buffer. Slots are claimed a tile at a time, and AHEAD of need:
 // `prepare` issues the atomic as soon as the current tile might not take one more slot per lane, `take` first looks at its
@@ -846,7 +843,9 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
 // form tried: a block-level sort and a per-warp Rayleigh queue in shared memory (round 1), and handing Rayleigh events and
 // Compton events with two rejected trials on to channel-pure follow-up passes through lists in HBM (round 2: 2.77e9 -> 2.64e9
 // histories/s; Rayleigh alone: 2.66e9). The kernel is bound by the latency of its loads and atomics, not by issue slots, and
-// every extra pass adds a load-compute-atomic-store chain per event it touches (profiles/README.md).
+// every extra pass adds a load-compute-atomic-store chain per event it touches. Staging each thread's next event through 64 bytes
+// of shared memory with cp.async does hide the event load (this kernel 191 -> 171 ms per 1e9 histories), but the 96 KB of shared
+// memory per SM come out of the L1 of every co-resident kernel: 3.04e9 -> 2.83e9 overall (profiles/README.md).
 template <int L, bool kStats, bool kAggregate>
 __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_constant__ KernelParams P)
 {
@@ -864,25 +863,6 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     const unsigned outShard = (blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)) % kShards;
     TileWriter out;
     unsigned survivors = 0; // photons this warp has stored
-#if DXMCB200_INTERACT_STAGE
-    // Every thread streams ITS next event through its own 64-byte slot of shared memory with cp.async: requested at the top of a
-    // trip, right after the current record has been taken into registers, and awaited at the top of the next one, so the record's
-    // trip through HBM and L2 overlaps the sampling (28 % of the kernel's stall samples waited for it). A thread only ever
-    // reads its own slot: no barrier, cp.async.wait_group is enough.
-    __shared__ EventRecord staged[kThreads];
-    EventRecord* const mine = staged + threadIdx.x;
-    auto request = [&](unsigned slot) {
-        if (slot < nSlots) {
-            const unsigned dst = static_cast<unsigned>(__cvta_generic_to_shared(mine));
-            const char* src = reinterpret_cast<const char*>(region + slot);
-#pragma unroll
-            for (unsigned k = 0; k < sizeof(EventRecord); k += 16)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + k), "l"(src + k) : "memory");
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    request((blockIdx.x / kShards) * kThreads + threadIdx.x);
-#endif
     for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
         const unsigned i = base + threadIdx.x;
 #if DXMCB200_INTERACT_PREFETCH
@@ -898,16 +878,8 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
             }
         }
 #endif
-#if DXMCB200_INTERACT_STAGE
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-        const uint4 where = i < nSlots ? mine->where : make_uint4(0u, kNoEvent, 0u, 0u);
-        const float4 stagedPosE = mine->posE, stagedDirW = mine->dirW;
-        const uint4 stagedRng = mine->rng;
-        request(i + blocksPerShard * kThreads); // the slot is free again: the next trip's record is on its way
-#else
         const EventRecord* e = region + min(i, nSlots - 1u);
         const uint4 where = i < nSlots ? recLoad(&e->where) : make_uint4(0u, kNoEvent, 0u, 0u);
-#endif
         if (__any_sync(kFull, where.y != kNoEvent))
             out.prepare(P.outCursors + outShard, kSurvivorTile, lane);
         bool alive = false; // the photon goes on to the next wave
@@ -940,13 +912,8 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
         if (where.y != kNoEvent) {
             Pending pe;
             {
-#if DXMCB200_INTERACT_STAGE
-                const float4 a = stagedPosE, b = stagedDirW;
-                const uint4 c = stagedRng;
-#else
                 const float4 a = recLoad(&e->posE), b = recLoad(&e->dirW);
                 const uint4 c = recLoad(&e->rng);
-#endif
                 p.px = a.x, p.py = a.y, p.pz = a.z, p.energy = a.w;
                 p.dx = b.x, p.dy = b.y, p.dz = b.z, p.weight = b.w;
                 rng.state = (static_cast<uint64_t>(c.y) << 32) | c.x;
