@@ -391,10 +391,21 @@ def main():
     for k in range(0, count, max(1, count // 20)):  # ~20 exposures spread over the rank's share: the counters must sample the whole scan
         sc.b200_run_strided(first + k * stride, 1, 1)
     st = ctx.stats()
-    ctx.enable_stats(False)
     sample_hist = max(st["histories"], 1)
     L = st["lookups"] / sample_hist
     Sev = st["score_events"] / sample_hist
+    # the same sample with the reference's own tracking (Woodcock against the global majorant everywhere): the look-ups per history
+    # of the REFERENCE ALGORITHM, which is what SURVEY 8d's per-history figure B_alg = 6 L + 24 S was defined on (and round 1 reported)
+    L_ref = L
+    if os.environ.get("DXMCB200_TRACKING", "1") != "0":
+        ctx.set_tracking(0)
+        ctx.clear()
+        for k in range(0, count, max(1, count // 20)):
+            sc.b200_run_strided(first + k * stride, 1, 1)
+        ref_st = ctx.stats()
+        L_ref = ref_st["lookups"] / max(ref_st["histories"], 1)
+        ctx.set_tracking(1)
+    ctx.enable_stats(False)
     peak, peak_src = measured_peak()
     # Algorithmic bytes: 6 B per voxel look-up (u8 material + f32 density + u8 measurement of the reference layout),
     # all issued by transportKernel (the air walk's few look-ups included in L); 24 B per scoring event (read + write of f32
@@ -429,6 +440,17 @@ def main():
                 "interactions_per_history": st["interactions"] / sample_hist, "air_walks_per_history": st["air_walks"] / sample_hist,
                 "bricks_crossed_per_history": st["bricks_crossed"] / sample_hist,
                 "pipeline_ms_per_step": kernel_total_ms / args.steps, "peak_source": peak_src}
+    # the same two figures per unit of the reference algorithm's work (a history costs 6 L_ref + 24 S algorithmic bytes in the
+    # reference; the product does the history with fewer look-ups): comparable with round 1 and across tracking modes
+    b_ref = 6.0 * L_ref + 24.0 * Sev
+    t_ms, t_cnt = per_kernel["transport"]
+    ref_transport = 6.0 * L_ref * hist_rank * args.steps / max(t_ms * 1e-3, 1e-12) / 1e9
+    roofline["reference_algorithm"] = {
+        "lookups_per_history": L_ref, "bytes_per_history": b_ref,
+        "transportKernel": {"achieved": ref_transport, "frac": ref_transport / peak},
+        "whole_pipeline": {"achieved": hist_rank * b_ref / pipeline_s / 1e9, "frac": hist_rank * b_ref / pipeline_s / 1e9 / peak},
+        "note": "algorithmic bytes of the work as the reference does it (look-ups counted with DXMCB200_TRACKING=0 on the same sample) over the measured "
+                "device times; `achieved` / `frac` above count only the look-ups the product actually makes"}
     if reduce_ms:
         roofline["all_reduce_ms_per_step"] = float(np.mean(reduce_ms))
         roofline["all_reduce_share_of_step"] = float(np.mean(reduce_ms)) / ms_per_step

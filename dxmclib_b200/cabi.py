@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
     "dxmcb200_physics_backend", "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_set_pool_limit", "dxmcb200_trim_pool",
-    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks", "dxmcb200_get_brick_distance", "dxmcb200_get_grid_form",
+    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks", "dxmcb200_get_brick_distance", "dxmcb200_get_grid_form", "dxmcb200_trace_air_runs",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_exposure_table", "dxmcb200_generate_exposures", "dxmcb200_run_range", "dxmcb200_run_resident", "dxmcb200_run_strided", "dxmcb200_run_strided_monitored",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce", "dxmcb200_comm_create", "dxmcb200_comm_destroy", "dxmcb200_reduce_collect",
     "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",
@@ -331,6 +331,15 @@ class Context:
                                                 s.ctypes.data_as(_f32p), idx.ctypes.data_as(_i64p), entry.ctypes.data_as(_f32p)),
                   "dxmcb200_trace_indices")
         return idx, entry
+
+    def trace_air_runs(self, pos, direction):
+        """(length, cubes crossed, exits the grid, starts in an air brick, reaches the world, end point) of the air run of fixed rays"""
+        p = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(-1, 3)
+        length, info, end = np.zeros(p.shape[0], np.float32), np.zeros(p.shape[0], np.uint32), np.zeros((p.shape[0], 3), np.float32)
+        self._chk(self.l.dxmcb200_trace_air_runs(self.h, C.c_uint64(p.shape[0]), p.ctypes.data_as(_f32p), d.ctypes.data_as(_f32p), length.ctypes.data_as(_f32p),
+                  info.ctypes.data_as(C.POINTER(C.c_uint32)), end.ctypes.data_as(_f32p)), "dxmcb200_trace_air_runs")
+        return length, info & 0xffff, (info >> 16) & 1, (info >> 17) & 1, (info >> 18) & 1, end
 
     def sample_particles(self, exposure: Exposure, exposure_index, seed, n):
         out = np.zeros((n, 8), np.float32)

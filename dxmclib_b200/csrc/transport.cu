@@ -1390,6 +1390,33 @@ __global__ void sampleParticlesKernel(dxmcb200_exposure e, BeamView beams, uint6
     o[7] = p.weight;
 }
 
+// test hook of the empty-space traversal: the air run of fixed rays (entry into the world first, like a birth)
+__global__ void traceAirRunsKernel(WorldView w, BrickView b, uint64_t nRays, const float* pos, const float* dir, float* outLength, uint32_t* outInfo,
+    float* outEnd)
+{
+    const uint64_t r = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x;
+    if (r >= nRays)
+        return;
+    Photon p {};
+    p.px = pos[3 * r], p.py = pos[3 * r + 1], p.pz = pos[3 * r + 2];
+    p.dx = dir[3 * r], p.dy = dir[3 * r + 1], p.dz = dir[3 * r + 2];
+    float length = 0.0f;
+    uint32_t info = 0;
+    if (transportToWorld(w, p)) {
+        info |= 1u << 18; // reaches the world
+        if (inAirBrick(w, b, p.px, p.py, p.pz)) {
+            bool exits = false;
+            uint32_t crossed = 0;
+            length = airRunLength(w, b, p, exits, crossed);
+            info |= crossed | (exits ? 1u << 16 : 0u) | (1u << 17); // cubes crossed, leaves the grid, started in an air brick
+            advance(p, length);
+        }
+    }
+    outLength[r] = length;
+    outInfo[r] = info;
+    outEnd[3 * r] = p.px, outEnd[3 * r + 1] = p.py, outEnd[3 * r + 2] = p.pz;
+}
+
 template <int L>
 __global__ void sampleInteractionKernel(LutView lut, int kind, uint8_t material, float energy, uint64_t seed, uint64_t n, float* out)
 {
@@ -3141,6 +3168,41 @@ int dxmcb200_trace_indices(dxmcb200_ctx* c, uint64_t nRays, const float* pos, co
     cudaFree(dS);
     cudaFree(dEn);
     cudaFree(dI);
+    return DXMCB200_OK;
+}
+
+int dxmcb200_trace_air_runs(dxmcb200_ctx* c, uint64_t nRays, const float* pos, const float* dir, float* outLength, uint32_t* outInfo, float* outEnd)
+{
+    if (!c || (!c->dVoxels && !c->dPalette) || !c->dLutBlob || !pos || !dir || !outLength || !outInfo || !outEnd || nRays == 0)
+        return DXMCB200_ERR_STATE;
+    CU_CHECK(c, cudaSetDevice(c->device));
+    const int st = ensureBricks(c);
+    if (st != DXMCB200_OK)
+        return st;
+    if (c->bricks.nWords == 0) {
+        c->error = "no air bricks (tracking mode 0, or a grid without air)";
+        return DXMCB200_ERR_STATE;
+    }
+    float *dP = nullptr, *dD = nullptr, *dL = nullptr, *dE = nullptr;
+    uint32_t* dI = nullptr;
+    CU_CHECK(c, cudaMalloc(&dP, nRays * 12));
+    CU_CHECK(c, cudaMalloc(&dD, nRays * 12));
+    CU_CHECK(c, cudaMalloc(&dL, nRays * 4));
+    CU_CHECK(c, cudaMalloc(&dI, nRays * 4));
+    CU_CHECK(c, cudaMalloc(&dE, nRays * 12));
+    CU_CHECK(c, cudaMemcpy(dP, pos, nRays * 12, cudaMemcpyHostToDevice));
+    CU_CHECK(c, cudaMemcpy(dD, dir, nRays * 12, cudaMemcpyHostToDevice));
+    traceAirRunsKernel<<<static_cast<unsigned>((nRays + 127) / 128), 128, 0, c->stream>>>(c->world, c->bricks, nRays, dP, dD, dL, dI, dE);
+    CU_CHECK(c, cudaGetLastError());
+    CU_CHECK(c, cudaStreamSynchronize(c->stream));
+    CU_CHECK(c, cudaMemcpy(outLength, dL, nRays * 4, cudaMemcpyDeviceToHost));
+    CU_CHECK(c, cudaMemcpy(outInfo, dI, nRays * 4, cudaMemcpyDeviceToHost));
+    CU_CHECK(c, cudaMemcpy(outEnd, dE, nRays * 12, cudaMemcpyDeviceToHost));
+    cudaFree(dP);
+    cudaFree(dD);
+    cudaFree(dL);
+    cudaFree(dI);
+    cudaFree(dE);
     return DXMCB200_OK;
 }
 

@@ -321,6 +321,14 @@ int dxmcb200_enable_stats(dxmcb200_ctx*, int on);
 /* a9/a10: AttenuationLutInterpolator::operator() and maxAttenuationInverse (attenuationinterpolator.hpp:207-248) */
 int dxmcb200_eval_attenuation(dxmcb200_ctx*, uint64_t n, const uint8_t* material, const float* energy,
     float* out_photo_compton_rayleigh /* [n][3] */, float* out_max_inverse /* [n] */);
+/* Test hook of the empty-space traversal (tracking mode 1): for fixed rays, enter the world like a birth does and, from an air
+ * brick, follow the run of air bricks (the Siddon / Amanatides-Woo style traversal over the brick grid, crossing at most
+ * DXMCB200_WALK_MAX_CUBES all-air cubes). length [n]: ray parameter of the run's end; info [n]: bits 0-15 cubes crossed, bit 16
+ * the ray leaves the grid there, bit 17 the entry point lies in an air brick, bit 18 the ray reaches the world; end [n][3]: the
+ * point reached. Bit-identical to the CPU restatement's airRunLength. */
+int dxmcb200_trace_air_runs(dxmcb200_ctx*, uint64_t n_rays, const float* pos /*[n][3]*/, const float* dir /*[n][3]*/, float* length, uint32_t* info,
+    float* end);
+
 /* a6/a7/a5: for ray r, entry point by transportParticleToWorld then positions pos += dir*step[k], reporting
  * indexFromPosition or -1 once outside (transport.hpp:485-521, 702-728). steps are shared by all rays. */
 int dxmcb200_trace_indices(dxmcb200_ctx*, uint64_t n_rays, const float* pos /*[n][3]*/, const float* dir /*[n][3]*/,

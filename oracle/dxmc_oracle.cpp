@@ -1270,6 +1270,39 @@ int dxmc_oracle_eval_attenuation(dxmc_oracle* h, uint64_t n, const uint8_t* mate
 }
 
 // a5/a6/a7 for fixed rays and a fixed list of step lengths (same contract as dxmcb200_trace_indices)
+// the air run of fixed rays, as dxmcb200_trace_air_runs reports it (include/dxmcb200.h)
+int dxmc_oracle_trace_air_runs(dxmc_oracle* h, uint64_t nRays, const float* pos, const float* dir, float* outLength, uint32_t* outInfo, float* outEnd)
+{
+    auto* o = reinterpret_cast<Oracle*>(h);
+    if (!o || !o->bricks.enabled)
+        return DXMCB200_ERR_STATE;
+    for (uint64_t r = 0; r < nRays; ++r) {
+        Particle p {};
+        for (int i = 0; i < 3; ++i) {
+            p.pos[i] = pos[3 * r + i];
+            p.dir[i] = dir[3 * r + i];
+        }
+        float length = 0;
+        uint32_t info = 0;
+        if (o->transportParticleToWorld(p)) {
+            info |= 1u << 18;
+            if (o->inAirBrick(p.pos)) {
+                bool exits = false;
+                const auto before = o->brickSteps;
+                length = o->airRunLength(p, exits);
+                info |= static_cast<uint32_t>(o->brickSteps - before) | (exits ? 1u << 16 : 0u) | (1u << 17);
+                for (int i = 0; i < 3; ++i)
+                    p.pos[i] += p.dir[i] * length;
+            }
+        }
+        outLength[r] = length;
+        outInfo[r] = info;
+        for (int i = 0; i < 3; ++i)
+            outEnd[3 * r + i] = p.pos[i];
+    }
+    return DXMCB200_OK;
+}
+
 int dxmc_oracle_trace_indices(dxmc_oracle* h, uint64_t nRays, const float* pos, const float* dir, uint32_t nSteps, const float* steps,
     int64_t* outIdx, float* outEntry)
 {

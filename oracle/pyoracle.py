@@ -174,6 +174,15 @@ class Oracle:
                   "dxmc_oracle_trace_indices")
         return idx, entry
 
+    def trace_air_runs(self, pos, direction):
+        """(length, cubes crossed, exits the grid, starts in an air brick, reaches the world, end point) of the air run of fixed rays"""
+        p = np.ascontiguousarray(pos, np.float32).reshape(-1, 3)
+        d = np.ascontiguousarray(direction, np.float32).reshape(-1, 3)
+        length, info, end = np.zeros(p.shape[0], np.float32), np.zeros(p.shape[0], np.uint32), np.zeros((p.shape[0], 3), np.float32)
+        self._chk(self.l.dxmc_oracle_trace_air_runs(self.h, C.c_uint64(p.shape[0]), p.ctypes.data_as(_f32p), d.ctypes.data_as(_f32p), length.ctypes.data_as(_f32p),
+                  info.ctypes.data_as(C.POINTER(C.c_uint32)), end.ctypes.data_as(_f32p)), "dxmc_oracle_trace_air_runs")
+        return length, info & 0xffff, (info >> 16) & 1, (info >> 17) & 1, (info >> 18) & 1, end
+
     def sample_particles(self, exposure, exposure_index, seed, n):
         out = np.zeros((n, 8), np.float32)
         self._chk(self.l.dxmc_oracle_sample_particles(self.h, C.byref(exposure), C.c_uint64(exposure_index), C.c_uint64(seed), C.c_uint64(n),

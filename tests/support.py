@@ -307,3 +307,52 @@ def allowed_outliers(tested, n_sigma_tail=0.0027):
     Gaussian tail puts 0.27 % of them there, the count is binomial, the bound is its mean plus three standard deviations (+1)."""
     expected = n_sigma_tail * tested
     return expected + 3.0 * np.sqrt(expected) + 1.0
+
+
+def air_run_rays(flat, n, seed):
+    """Fixed rays for the traversal tests: sources on a sphere around the grid aimed at random points inside it; a tenth of the
+    rays run along an axis (two zero direction components)."""
+    rng = np.random.default_rng(seed)
+    ext = np.array(flat["extent_safe"], np.float64)
+    lo, hi = ext[0::2], ext[1::2]
+    centre, half = (lo + hi) / 2, (hi - lo) / 2
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    pos = centre + u * 2.5 * np.linalg.norm(half)
+    target = lo + rng.uniform(0.02, 0.98, (n, 3)) * (hi - lo)
+    d = target - pos
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    k = n // 10
+    axis = rng.integers(0, 3, k)
+    pos[:k] = target[:k]
+    pos[np.arange(k), axis] = lo[axis] - 50.0
+    d[:k] = 0.0
+    d[np.arange(k), axis] = 1.0
+    return pos.astype(np.float32), d.astype(np.float32)
+
+
+def assert_air_runs_true(flat, bricks, entry, d32, result, max_cubes=3):
+    """Ground truth for trace_air_runs by dense sampling of the brick flags along each ray: every point of a run lies in an air
+    brick (or outside the grid), and a run that ended neither at the grid's edge nor at the cube cap stops in front of a non-air
+    brick. `entry`: the rays' entry points into the world (trace_indices)."""
+    length, crossed, exits, in_air, reaches, _ = result
+    dim, sp, ext = np.array(flat["dim"], np.int64), np.array(flat["spacing"], np.float64), np.array(flat["extent_safe"], np.float64)
+    lo = ext[0::2]
+    shift, nb = np.array(bricks["shift"]), np.array(bricks["nb"])
+    air = bricks["air"].reshape(nb[2], nb[1], nb[0]).astype(bool)
+    assert reaches.mean() > 0.95 and in_air.mean() > 0.3 and (crossed[in_air == 1] >= 1).all() and crossed.max() <= max_cubes
+
+    def is_air(points):  # [m, 3] -> air brick or outside the grid
+        vox = np.floor((points - lo) / sp).astype(np.int64)
+        outside = ((vox < 0) | (vox >= dim)).any(axis=1)
+        b = np.clip(vox, 0, dim - 1) >> shift
+        return outside | air[b[:, 2], b[:, 1], b[:, 0]]
+
+    sel = np.flatnonzero((in_air == 1) & np.isfinite(length))
+    e64, d64, len64 = entry[sel].astype(np.float64), d32[sel].astype(np.float64), length[sel].astype(np.float64)
+    for f in np.linspace(0.001, 0.999, 97):  # points strictly inside the run
+        assert is_air(e64 + d64 * (len64 * f)[:, None]).all(), f"a run crosses a non-air brick at {f:.3f} of its length"
+    stopped = (exits[sel] == 0) & (crossed[sel] < max_cubes)
+    assert stopped.sum() > 200
+    beyond = e64[stopped] + d64[stopped] * (len64[stopped] + 0.01 * sp.min())[:, None]
+    assert (~is_air(beyond)).mean() > 0.999, "runs that stopped inside the grid must stop in front of a non-air brick"

@@ -78,3 +78,21 @@ def test_brick_layout_rule(product):
     assert int(np.prod(b["nb"])) <= 16384
     # a homogeneous world has no brick that is thin compared with the majorant (which is the same material): no air bricks
     assert not b["air"].any() and b["f_air"] == 0
+
+
+@pytest.mark.parametrize("name,build,mm", [
+    ("air_gap", lambda lib: T.air_gap_scene(lib), 8.0),
+    ("ct_spiral", lambda lib: T.ct_scene(lib, histories=100), 16.0),
+])
+def test_air_run_traversal_is_true_against_dense_sampling(product, name, build, mm):
+    """The restatement's ray / brick-grid traversal (airRunLength: the path's Siddon / Amanatides-Woo style traversal, crossing
+    whole all-air cubes) against ground truth: dense sampling of the brick flags along 20000 fixed rays. The kernels' traversal is
+    compared with this one bit for bit in tests/test_gpu_empty_space.py."""
+    flat = T.flatten_scene(build(product))
+    o = pyoracle.Oracle()
+    o.load(flat)
+    o.set_tracking(1, mm)
+    pos32, d32 = T.air_run_rays(flat, 20000, seed=3)
+    result = o.trace_air_runs(pos32, d32)
+    _, entry = o.trace_indices(pos32, d32, np.zeros(0, np.float32))
+    T.assert_air_runs_true(flat, o.bricks(), entry, d32, result)

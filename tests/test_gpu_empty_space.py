@@ -103,6 +103,23 @@ def test_follows_oracle_history_by_history(gpu, product, name, model):
     ctx.close()
 
 
+@pytest.mark.parametrize("name", ["air_gap", "ct_spiral", "ctdi"])
+def test_air_run_traversal_bit_exact_and_true(gpu, product, name):
+    """The ray / brick-grid traversal of the air walk (the path's Siddon / Amanatides-Woo style traversal) for fixed rays:
+    run length, cubes crossed and the exit flag are the bits of the CPU restatement's, and the run is TRUE against dense sampling
+    of the brick flags along the ray: every point of the run lies in an air brick (or outside the grid), and a run that ended
+    neither at the grid's edge nor at the cube cap ends on the face of a non-air brick."""
+    _, flat, _, ctx, o = _both(product, name)
+    pos32, d32 = T.air_run_rays(flat, 20000, seed=11)
+    got = ctx.trace_air_runs(pos32, d32)
+    want = o.trace_air_runs(pos32, d32)
+    for a, b in zip(got, want):
+        assert T.bit_equal(np.ascontiguousarray(a), np.ascontiguousarray(b))
+    _, entry = ctx.trace_indices(pos32, d32, np.zeros(0, np.float32))
+    T.assert_air_runs_true(flat, ctx.bricks(flat["luts"]["n_materials"]), entry, d32, got)
+    ctx.close()
+
+
 def test_record_grid_follows_oracle(gpu, product):
     sc, flat, exps, ctx, o = _both(product, "air_gap", palette_break=True)
     ctx.run(exps, 0, len(exps), model=1, seed=23)
