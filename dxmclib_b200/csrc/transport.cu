@@ -4,27 +4,30 @@
 // photons to each other through record buffers in HBM. Every kernel keeps all 32 lanes of a warp on ONE kind of
 // work; the divergent stages of a history (birth, stepping, interaction) never share a warp:
 //
+//   exposureKernel   (a0) Source::getExposure(i) for all i from one parameter block (dxmc/sourcemodel.hpp), SURVEY 8f3.
 //   generateKernel   (a) Exposure::sampleParticle + transportParticleToWorld (exposure.hpp:280-304,
-//                    transport.hpp:702-728, 733-741), one history per thread; photons that reach the voxel grid
-//                    are compacted (warp ballot + one atomic per warp) into 64-byte photon records carrying their
-//                    own counter-derived PCG32 stream, log10(E), the LUT segment and the Woodcock majorant.
+//                    transport.hpp:702-728, 733-741), one history per thread, and the first air walk of photons born into an
+//                    air brick; photons that reach the dense part of the grid become 64-byte photon records carrying their own
+//                    counter-derived PCG32 stream, log10(E), the LUT segment and the Woodcock majorant.
 //   transportKernel  (b) Woodcock delta tracking (transport.hpp:640-700), persistent grid. A lane steps one photon
-//                    until it leaves the world, is killed by Russian roulette, or a real / forced interaction is
-//                    due; events are appended to the event buffer as 80-byte records, and the lane re-fills from
-//                    the photon buffer through a per-warp cp.async ring in shared memory.
+//                    until it leaves the world, is killed by Russian roulette, a real / forced interaction is due, or it
+//                    stands in an air brick after a virtual collision; events go to the event buffer as 64-byte records, air-bound
+//                    photons to the air-walk buffer, and empty lanes take the next records of the wave straight from global
+//                    memory (tiles of 256 records per atomic, prefetched into L2).
+//   airWalkKernel    (b') empty-space traversal (DESIGN.md section 4b): photons that a Woodcock step left in an "air" brick
+//                    are walked through the run of air bricks on their ray (Siddon / Amanatides-Woo style traversal of the
+//                    brick grid in whole all-air cubes) against the regional majorant of air, then rejoin the next wave. Not
+//                    part of the reference's algorithm; dxmcb200_set_tracking(ctx, 0) switches it off and leaves the
+//                    reference's Woodcock loop everywhere.
 //   interactKernel   (c)+(d) computeInteractions[Forced] (transport.hpp:523-638): photoelectric / Compton /
 //                    Rayleigh sampling against the LUTs, 64-bit fixed-point scoring, Russian roulette; surviving
-//                    photons are compacted into the NEXT wave's photon buffer.
+//                    photons go to the NEXT wave's photon buffer.
 //
-//   airWalkKernel    (b') empty-space traversal (DESIGN.md section 4b): photons that a Woodcock step left in an "air" brick
-//                    are walked through the run of air bricks on their ray (Siddon / Amanatides-Woo traversal of the
-//                    brick grid) against the regional majorant of air, then rejoin the next wave. Births take the same
-//                    walk inside generateKernel. Not part of the reference's algorithm; dxmcb200_set_tracking(ctx, 0)
-//                    switches it off and leaves the reference's Woodcock loop everywhere.
-//
-// One wave = births + survivors of the previous wave, at most `waveRecords` photons; the host tops every wave up
-// with new births until all histories are issued and then drains. Scoring is integer atomics and every history
-// carries its own random stream, so results do not depend on the wave size, scheduling or GPU partition.
+// Output slots are claimed by warps a tile at a time and ahead of need (TileWriter), so no atomic's round trip stalls a warp;
+// slots a warp claimed and did not use are dead markers. One wave = births + survivors of the previous wave, at most
+// `waveRecords` photons; the host tops every wave up with new births until all histories are issued and then drains. Two
+// such pipelines run on two streams. Scoring is integer atomics and every history carries its own random stream, so results
+// do not depend on the wave size, scheduling or GPU partition.
 #include "hostio.cuh"
 #include "physics.cuh"
 #include "../include/dxmc/sourcemodel.hpp"
@@ -583,9 +586,6 @@ constexpr unsigned kTile = 256; // photon records a warp of transportKernel clai
 constexpr unsigned kEventTile = 64; // event slots a warp claims with one atomic
 constexpr unsigned kSurvivorTile = 64; // next-wave photon slots a warp of interactKernel claims with one atomic
 constexpr unsigned kAirTile = 64; // air-walk slots a warp of transportKernel claims with one atomic
-#ifndef DXMCB200_INTERACT_PREFETCH
-#define DXMCB200_INTERACT_PREFETCH 0
-#endif
 
 // A warp's private window into its shard region of an output buffer. Slots are claimed a tile at a time, and AHEAD of need:
 // `prepare` issues the atomic as soon as the current tile might not take one more slot per lane, `take` first looks at its
@@ -865,19 +865,6 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     unsigned survivors = 0; // photons this warp has stored
     for (unsigned base = (blockIdx.x / kShards) * kThreads; base < nSlots; base += blocksPerShard * kThreads) {
         const unsigned i = base + threadIdx.x;
-#if DXMCB200_INTERACT_PREFETCH
-        { // the events of the warp's next trip: 32 x 80 bytes = 20 lines
-            const unsigned next = base + blocksPerShard * kThreads + (threadIdx.x & ~31u);
-            if (next < nSlots && lane < 20u) {
-                const char* line = reinterpret_cast<const char*>(region + next) + 128u * lane;
-#if DXMCB200_INTERACT_PREFETCH == 1
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(line));
-#else
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(line));
-#endif
-            }
-        }
-#endif
         const EventRecord* e = region + min(i, nSlots - 1u);
         const uint4 where = i < nSlots ? recLoad(&e->where) : make_uint4(0u, kNoEvent, 0u, 0u);
         if (__any_sync(kFull, where.y != kNoEvent))
