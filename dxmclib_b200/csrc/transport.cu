@@ -1544,6 +1544,16 @@ namespace {
         }                                                                                          \
     } while (0)
 
+// Host -> device copy that has LANDED when it returns. cudaMemcpy from pageable memory may return while the DMA from its staging
+// buffer is still in flight, and only the legacy stream orders later work behind it; the context's streams are non-blocking, so a
+// kernel launched right after such a copy could read the old contents. Copying on the context's stream and waiting for it is
+// ordered and complete.
+cudaError_t uploadNow(const dxmcb200_ctx* c, void* dst, const void* src, size_t bytes)
+{
+    const cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->stream);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(c->stream);
+}
+
 int gridFor(const dxmcb200_ctx* c, uint64_t n)
 {
     const uint64_t blocks = (n + 255) / 256;
@@ -1871,9 +1881,9 @@ int ensureBricks(dxmcb200_ctx* c)
         c->dBrickBits = nullptr;
         c->dBrickDistance = nullptr;
         CU_CHECK(c, cudaMalloc(&c->dBrickBits, bitmap.size() * sizeof(uint32_t)));
-        CU_CHECK(c, cudaMemcpy(c->dBrickBits, bitmap.data(), bitmap.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+        CU_CHECK(c, uploadNow(c, c->dBrickBits, bitmap.data(), bitmap.size() * sizeof(uint32_t)));
         CU_CHECK(c, cudaMalloc(&c->dBrickDistance, 8 * nBricks));
-        CU_CHECK(c, cudaMemcpy(c->dBrickDistance, c->hDistance.data(), 8 * nBricks, cudaMemcpyHostToDevice));
+        CU_CHECK(c, uploadNow(c, c->dBrickDistance, c->hDistance.data(), 8 * nBricks));
         b.air = c->dBrickBits;
         b.distance = c->dBrickDistance;
     }
@@ -2199,7 +2209,7 @@ int dxmcb200_create(int device, dxmcb200_ctx** out)
     if (cudaSetDevice(device) != cudaSuccess || cudaDeviceGetAttribute(&c->smCount, cudaDevAttrMultiProcessorCount, device) != cudaSuccess
         || cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreate(&c->evStart) != cudaSuccess
         || cudaEventCreate(&c->evStop) != cudaSuccess
-        || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemset(c->dCounters, 0, sizeof(Counters)) != cudaSuccess) {
+        || cudaMalloc(&c->dCounters, sizeof(Counters)) != cudaSuccess || cudaMemsetAsync(c->dCounters, 0, sizeof(Counters), c->stream) != cudaSuccess) {
         dxmcb200_destroy(c);
         return DXMCB200_ERR_CUDA;
     }
@@ -2536,7 +2546,7 @@ int dxmcb200_set_luts(dxmcb200_ctx* c, const dxmcb200_luts* l)
     cudaFree(c->dLutBlob);
     c->dLutBlob = nullptr;
     CU_CHECK(c, cudaMalloc(&c->dLutBlob, total * sizeof(float)));
-    CU_CHECK(c, cudaMemcpy(c->dLutBlob, blob.data(), total * sizeof(float), cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, c->dLutBlob, blob.data(), total * sizeof(float)));
     c->lut.nMaterials = l->n_materials;
     c->lut.nSegments = l->n_segments;
     c->lut.linearIndex = l->linear_index;
@@ -2625,7 +2635,7 @@ int dxmcb200_set_beam_tables(dxmcb200_ctx* c, uint32_t nSpectra, const dxmcb200_
         c->error = "beam table blob overflow";
         return DXMCB200_ERR_STATE;
     }
-    CU_CHECK(c, cudaMemcpy(c->dBeamBlob, host.data(), bytes, cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, c->dBeamBlob, host.data(), bytes));
     c->beams.spectra = reinterpret_cast<const SpectrumView*>(toDevice(sv));
     c->beams.heels = reinterpret_cast<const HeelView*>(toDevice(hv));
     c->beams.bowties = reinterpret_cast<const BowtieView*>(toDevice(bv));
@@ -2696,7 +2706,7 @@ int dxmcb200_upload_exposures(dxmcb200_ctx* c, const dxmcb200_exposure* exposure
         c->nExposuresResident = 0;
         CU_CHECK(c, cudaMalloc(&c->dExposures, n * sizeof(dxmcb200_exposure)));
     }
-    CU_CHECK(c, cudaMemcpy(c->dExposures, exposures, n * sizeof(dxmcb200_exposure), cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, c->dExposures, exposures, n * sizeof(dxmcb200_exposure)));
     c->nExposuresResident = n;
     c->hExposures.assign(exposures, exposures + n);
     return DXMCB200_OK;
@@ -3114,8 +3124,8 @@ int dxmcb200_eval_attenuation(dxmcb200_ctx* c, uint64_t n, const uint8_t* materi
     CU_CHECK(c, cudaMalloc(&dE, n * 4));
     CU_CHECK(c, cudaMalloc(&dO, n * 12));
     CU_CHECK(c, cudaMalloc(&dX, n * 4));
-    CU_CHECK(c, cudaMemcpy(dM, material, n, cudaMemcpyHostToDevice));
-    CU_CHECK(c, cudaMemcpy(dE, energy, n * 4, cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, dM, material, n));
+    CU_CHECK(c, uploadNow(c, dE, energy, n * 4));
     evalAttenuationKernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, c->stream>>>(c->lut, n, dM, dE, dO, dX);
     CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -3141,10 +3151,10 @@ int dxmcb200_trace_indices(dxmcb200_ctx* c, uint64_t nRays, const float* pos, co
     CU_CHECK(c, cudaMalloc(&dS, std::max<size_t>(nSteps, 1) * 4));
     CU_CHECK(c, cudaMalloc(&dEn, nRays * 12));
     CU_CHECK(c, cudaMalloc(&dI, nRays * (nSteps + 1) * 8));
-    CU_CHECK(c, cudaMemcpy(dP, pos, nRays * 12, cudaMemcpyHostToDevice));
-    CU_CHECK(c, cudaMemcpy(dD, dir, nRays * 12, cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, dP, pos, nRays * 12));
+    CU_CHECK(c, uploadNow(c, dD, dir, nRays * 12));
     if (nSteps)
-        CU_CHECK(c, cudaMemcpy(dS, steps, nSteps * 4, cudaMemcpyHostToDevice));
+        CU_CHECK(c, uploadNow(c, dS, steps, nSteps * 4));
     traceIndicesKernel<<<static_cast<unsigned>((nRays + 127) / 128), 128, 0, c->stream>>>(c->world, nRays, dP, dD, nSteps, dS, dI, dEn);
     CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
@@ -3177,8 +3187,8 @@ int dxmcb200_trace_air_runs(dxmcb200_ctx* c, uint64_t nRays, const float* pos, c
     CU_CHECK(c, cudaMalloc(&dL, nRays * 4));
     CU_CHECK(c, cudaMalloc(&dI, nRays * 4));
     CU_CHECK(c, cudaMalloc(&dE, nRays * 12));
-    CU_CHECK(c, cudaMemcpy(dP, pos, nRays * 12, cudaMemcpyHostToDevice));
-    CU_CHECK(c, cudaMemcpy(dD, dir, nRays * 12, cudaMemcpyHostToDevice));
+    CU_CHECK(c, uploadNow(c, dP, pos, nRays * 12));
+    CU_CHECK(c, uploadNow(c, dD, dir, nRays * 12));
     traceAirRunsKernel<<<static_cast<unsigned>((nRays + 127) / 128), 128, 0, c->stream>>>(c->world, c->bricks, nRays, dP, dD, dL, dI, dE);
     CU_CHECK(c, cudaGetLastError());
     CU_CHECK(c, cudaStreamSynchronize(c->stream));
