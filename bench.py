@@ -504,11 +504,15 @@ def main():
         if world == 1 and args.config in (3, 4, 5):
             # the reference's DEFAULT call: OUTPUTMODE::DOSE with the source's dose calibration (transport.hpp:838-839), which for
             # a CT source runs a second Transport over the CTDI phantom (source.hpp:925-988) inside the call
-            t1 = time.perf_counter()
-            r = e2e_step(S.OUT_DOSE, True)
-            dose_s = time.perf_counter() - t1
-            e2e["dose_mode_with_calibration"] = {"value": total_hist_all / dose_s, "unit": "histories/s", "seconds": dose_s, "dose_units": r.units,
-                                                 "note": "histories of the main run / wall time of the whole call incl. the calibration run"}
+            dose_calls = []
+            for _ in range(2):
+                t1 = time.perf_counter()
+                r = e2e_step(S.OUT_DOSE, True)
+                dose_calls.append(time.perf_counter() - t1)
+            dose_s = float(np.mean(dose_calls))
+            e2e["dose_mode_with_calibration"] = {"value": total_hist_all / dose_s, "unit": "histories/s", "seconds": dose_s,
+                                                 "seconds_per_call": [round(x, 3) for x in dose_calls], "dose_units": r.units,
+                                                 "note": "histories of the main run / wall time of the whole call incl. the calibration run (mean of two calls)"}
 
     # ---- CPU baseline: the unmodified reference on this box's host cores, bounded sample of the same workload
     cpu = None
