@@ -21,7 +21,7 @@ _u64p = C.POINTER(C.c_uint64)
 # every symbol include/dxmcb200.h declares
 CABI_SYMBOLS = [
     "dxmcb200_physics_backend", "dxmcb200_device_count", "dxmcb200_create", "dxmcb200_destroy", "dxmcb200_last_error", "dxmcb200_set_world", "dxmcb200_material_max_density", "dxmcb200_set_pool_limit", "dxmcb200_trim_pool",
-    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks", "dxmcb200_get_brick_distance", "dxmcb200_get_grid_form", "dxmcb200_trace_air_runs",
+    "dxmcb200_set_luts", "dxmcb200_set_beam_tables", "dxmcb200_suggest_fixed_point", "dxmcb200_set_fixed_point", "dxmcb200_set_tracking", "dxmcb200_get_bricks", "dxmcb200_get_brick_distance", "dxmcb200_get_grid_form", "dxmcb200_trace_air_runs", "dxmcb200_tube_bremsstrahlung",
     "dxmcb200_clear", "dxmcb200_history_stream", "dxmcb200_run", "dxmcb200_upload_exposures", "dxmcb200_exposure_table", "dxmcb200_generate_exposures", "dxmcb200_run_range", "dxmcb200_run_resident", "dxmcb200_run_strided", "dxmcb200_run_strided_monitored",
     "dxmcb200_last_run_ms", "dxmcb200_get_result", "dxmcb200_get_raw", "dxmcb200_accumulators", "dxmcb200_reduce", "dxmcb200_comm_create", "dxmcb200_comm_destroy", "dxmcb200_reduce_collect",
     "dxmcb200_get_stats", "dxmcb200_get_kernel_times", "dxmcb200_enable_stats", "dxmcb200_eval_attenuation", "dxmcb200_trace_indices", "dxmcb200_sample_particles",

@@ -30,6 +30,7 @@
 // do not depend on the wave size, scheduling or GPU partition.
 #include "hostio.cuh"
 #include "physics.cuh"
+#include "spectrum.cuh"
 #include "../include/dxmc/sourcemodel.hpp"
 
 #include <algorithm>
@@ -3166,6 +3167,50 @@ int dxmcb200_trace_indices(dxmcb200_ctx* c, uint64_t nRays, const float* pos, co
     cudaFree(dEn);
     cudaFree(dI);
     return DXMCB200_OK;
+}
+
+int dxmcb200_tube_bremsstrahlung(float tubeVoltage, uint32_t nBins, const float* energies, const float* tungstenAttenuation, uint32_t nAngles,
+    const float* angles, float* out)
+{
+    if (!energies || !tungstenAttenuation || !angles || !out || nBins == 0 || nAngles == 0)
+        return DXMCB200_ERR_ARG;
+    int devices = 0;
+    if (cudaGetDeviceCount(&devices) != cudaSuccess || devices <= 0)
+        return DXMCB200_ERR_NO_DEVICE;
+    float *dE = nullptr, *dA = nullptr, *dT = nullptr, *dO = nullptr;
+    cudaError_t e = spectrum::uploadTables();
+    if (e == cudaSuccess)
+        e = cudaMalloc(&dE, nBins * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&dT, nBins * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&dA, nAngles * sizeof(float));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&dO, static_cast<size_t>(nBins) * nAngles * sizeof(float));
+    cudaStream_t stream = nullptr;
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dE, energies, nBins * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dT, tungstenAttenuation, nBins * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(dA, angles, nAngles * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) {
+        spectrum::bremsstrahlungKernel<<<nBins * nAngles, spectrum::kMaxDepthSteps, 0, stream>>>(tubeVoltage, nBins, dE, dT, dA, dO);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(out, dO, static_cast<size_t>(nBins) * nAngles * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+    if (stream)
+        cudaStreamDestroy(stream);
+    cudaFree(dE);
+    cudaFree(dT);
+    cudaFree(dA);
+    cudaFree(dO);
+    return e == cudaSuccess ? DXMCB200_OK : DXMCB200_ERR_CUDA;
 }
 
 int dxmcb200_trace_air_runs(dxmcb200_ctx* c, uint64_t nRays, const float* pos, const float* dir, float* outLength, uint32_t* outInfo, float* outEnd)

@@ -177,16 +177,30 @@ T betheHeitlerSpectra(const T T0, const T hv, const T takeoffAngle)
 
 // K-alpha / K-beta lines scaled to the bremsstrahlung produced at the line energy; the fifth slot is unused
 template <Floating T>
-std::array<std::pair<T, T>, 5> characteristicTungstenKedge(const T T0, const T takeoffAngle)
+constexpr std::array<T, 4> tungstenKLineEnergies() { return { 59.3, 58.0, 67.2, 69.1 }; }
+
+// ... from the bremsstrahlung yields at the four line energies, wherever they were evaluated
+template <Floating T>
+std::array<std::pair<T, T>, 5> characteristicTungstenKedge(const std::array<T, 4>& bremsstrahlungAtLines)
 {
-    constexpr std::array<T, 4> lineEnergy { 59.3, 58.0, 67.2, 69.1 };
+    constexpr std::array<T, 4> lineEnergy = tungstenKLineEnergies<T>();
     constexpr std::array<T, 4> lineFraction { 0.505, 0.291, 0.162, 0.042 };
     constexpr auto P = T { 0.33 };
     constexpr auto omega_k = T { 0.94 };
     constexpr auto rk = T { 4.4 };
     std::array<std::pair<T, T>, 5> lines {};
     for (std::size_t i = 0; i < 4; ++i)
-        lines[i] = { lineEnergy[i], (1 + P) * lineFraction[i] * rk * omega_k * betheHeitlerSpectra(T0, lineEnergy[i], takeoffAngle) };
+        lines[i] = { lineEnergy[i], (1 + P) * lineFraction[i] * rk * omega_k * bremsstrahlungAtLines[i] };
     return lines;
+}
+
+template <Floating T>
+std::array<std::pair<T, T>, 5> characteristicTungstenKedge(const T T0, const T takeoffAngle)
+{
+    constexpr std::array<T, 4> lineEnergy = tungstenKLineEnergies<T>();
+    std::array<T, 4> yields {};
+    for (std::size_t i = 0; i < 4; ++i)
+        yields[i] = betheHeitlerSpectra(T0, lineEnergy[i], takeoffAngle);
+    return characteristicTungstenKedge(yields);
 }
 }

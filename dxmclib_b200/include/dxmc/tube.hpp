@@ -10,9 +10,12 @@
 #include "dxmc/hostparallel.hpp"
 #include "dxmc/material.hpp"
 #include "dxmc/types.hpp"
+#include "dxmcb200.h"
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <execution>
 #include <numeric>
 #include <optional>
@@ -62,11 +65,15 @@ public:
     std::vector<T> getSpecter(const std::vector<T>& energies, const T anodeAngle, bool normalize = true) const
     {
         std::vector<T> fluence(energies.size());
-        // one Bethe-Heitler depth integral per energy bin, independent of each other (reference tube.hpp:191-208)
-        detail::parallelFor(energies.size(),
-            [&](std::size_t i) { fluence[i] = BetheHeitlerCrossSection::betheHeitlerSpectra(m_kV, energies[i], anodeAngle); });
+        std::array<std::pair<T, T>, 5> lines {};
+        if (!bremsstrahlungOnDevice(energies, anodeAngle, fluence, lines)) {
+            // one Bethe-Heitler depth integral per energy bin, independent of each other (reference tube.hpp:191-208)
+            detail::parallelFor(energies.size(),
+                [&](std::size_t i) { fluence[i] = BetheHeitlerCrossSection::betheHeitlerSpectra(m_kV, energies[i], anodeAngle); });
+            lines = BetheHeitlerCrossSection::characteristicTungstenKedge(m_kV, m_takeOff);
+        }
         // a K line goes into the first bin at or above its energy when that bin is within 2 keV
-        for (const auto& [lineEnergy, lineYield] : BetheHeitlerCrossSection::characteristicTungstenKedge(m_kV, m_takeOff)) {
+        for (const auto& [lineEnergy, lineYield] : lines) {
             const auto bin = std::lower_bound(energies.begin(), energies.end(), lineEnergy);
             if (bin != energies.end() && std::abs(lineEnergy - *bin) <= T { 2.0 })
                 fluence[std::distance(energies.begin(), bin)] += lineYield;
@@ -139,6 +146,40 @@ public:
     void setEnergyResolution(T energyResolution) { m_binWidth = energyResolution; }
 
 protected:
+    // The depth integrals of all bins (at anodeAngle) and of the four K lines (at the tube's own take-off angle) in one launch of
+    // dxmcb200_tube_bremsstrahlung, when DXMCB200_DEVICE_SPECTRUM=1 asks for it (T = float only). false: not requested, or the
+    // device path failed (said on stderr); the caller then evaluates them on the host, which is the default and the
+    // reference's way (its tables are bit-identical to the reference's, the device's agree to 2e-5).
+    bool bremsstrahlungOnDevice(const std::vector<T>& energies, const T anodeAngle, std::vector<T>& fluence, std::array<std::pair<T, T>, 5>& lines) const
+    {
+        if constexpr (!std::is_same_v<T, float>) {
+            return false;
+        } else {
+            const char* env = std::getenv("DXMCB200_DEVICE_SPECTRUM");
+            if (!env || env[0] != '1' || energies.empty())
+                return false;
+            const auto lineEnergy = BetheHeitlerCrossSection::tungstenKLineEnergies<float>();
+            std::vector<float> hv(energies.begin(), energies.end());
+            hv.insert(hv.end(), lineEnergy.begin(), lineEnergy.end());
+            std::vector<float> att(hv.size());
+            for (std::size_t i = 0; i < hv.size(); ++i)
+                att[i] = static_cast<float>(Material::getTotalAttenuation(BetheHeitlerCrossSection::TUNGSTEN_ATOMIC_NUMBER, hv[i]));
+            const float angles[2] = { anodeAngle, m_takeOff };
+            std::vector<float> out(2 * hv.size());
+            const int st = dxmcb200_tube_bremsstrahlung(m_kV, static_cast<std::uint32_t>(hv.size()), hv.data(), att.data(), 2, angles, out.data());
+            if (st != DXMCB200_OK) {
+                std::fprintf(stderr, "[dxmcb200] DXMCB200_DEVICE_SPECTRUM=1: device spectrum failed (status %d), evaluating on the host\n", st);
+                return false;
+            }
+            const std::size_t n = energies.size();
+            std::copy(out.begin(), out.begin() + static_cast<std::ptrdiff_t>(n), fluence.begin());
+            std::array<float, 4> atLines {};
+            for (std::size_t i = 0; i < 4; ++i)
+                atLines[i] = out[hv.size() + n + i];
+            lines = BetheHeitlerCrossSection::characteristicTungstenKedge(atLines);
+            return true;
+        }
+    }
     T elementFiltration(const char* symbol) const
     {
         const auto it = std::find_if(m_filters.begin(), m_filters.end(), [&](const auto& f) { return f.first.name().compare(symbol) == 0; });

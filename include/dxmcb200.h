@@ -118,6 +118,17 @@ typedef struct dxmcb200_exposure {
     uint64_t histories;
 } dxmcb200_exposure;
 
+/* ---- tube spectrum ------------------------------------------------------ */
+/* Thick-target tungsten bremsstrahlung of Poludniowski & Evans as the reference evaluates it per energy bin and take-off angle
+ * (betheHeitlerCrossSection.hpp:368-407 from tube.hpp:191-208 and beamfilters.hpp:465-505: 141 depths x 200 electron energies per
+ * bin, 0.4 s of host time for a CT source with heel model): out[a * n_bins + b] = betheHeitlerSpectra(tube_voltage, energies[b],
+ * angles[a]) on the calling thread's current CUDA device. tungsten_attenuation[b] = Material::getTotalAttenuation(74, energies[b])
+ * from the host's element data. Same single-precision operations in the same order as the host code, CUDA's libm instead of the
+ * host's (2e-5 relative on a normalised spectrum). Tube::getSpecter uses it when DXMCB200_DEVICE_SPECTRUM=1; the default is the
+ * host path, whose tables are bit-identical to the reference's. */
+int dxmcb200_tube_bremsstrahlung(float tube_voltage, uint32_t n_bins, const float* energies, const float* tungsten_attenuation, uint32_t n_angles,
+    const float* angles, float* out);
+
 /* ---- physics data ----------------------------------------------------------------------- */
 /* Name of the element data source the host-side table builders (Material, AttenuationLut, Tube) of this library were
  * compiled against: "xraylib" (what the reference uses, src/material.cpp:23-375) or the in-repo "xrl_lite (approximate ...)".
