@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(kMaxDepthSteps) bremsstrahlungKernel(float T0,
     }
 }
 
-inline cudaError_t uploadTables()
+inline cudaError_t uploadTables(cudaStream_t stream)
 {
     static ElectronTables host;
     static bool filled = false;
@@ -163,7 +163,8 @@ inline cudaError_t uploadTables()
         }
         filled = true;
     }
-    return cudaMemcpyToSymbol(kTables, &host, sizeof(host)); // per device: cheap (4.5 KB), done at every call
+    // per device and cheap (4.5 KB): done at every call, on the stream the kernel is launched on (ordered before it)
+    return cudaMemcpyToSymbolAsync(kTables, &host, sizeof(host), 0, cudaMemcpyHostToDevice, stream);
 }
 
 } // namespace dxmcb200::spectrum

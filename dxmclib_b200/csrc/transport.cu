@@ -3178,9 +3178,7 @@ int dxmcb200_tube_bremsstrahlung(float tubeVoltage, uint32_t nBins, const float*
     if (cudaGetDeviceCount(&devices) != cudaSuccess || devices <= 0)
         return DXMCB200_ERR_NO_DEVICE;
     float *dE = nullptr, *dA = nullptr, *dT = nullptr, *dO = nullptr;
-    cudaError_t e = spectrum::uploadTables();
-    if (e == cudaSuccess)
-        e = cudaMalloc(&dE, nBins * sizeof(float));
+    cudaError_t e = cudaMalloc(&dE, nBins * sizeof(float));
     if (e == cudaSuccess)
         e = cudaMalloc(&dT, nBins * sizeof(float));
     if (e == cudaSuccess)
@@ -3190,6 +3188,8 @@ int dxmcb200_tube_bremsstrahlung(float tubeVoltage, uint32_t nBins, const float*
     cudaStream_t stream = nullptr;
     if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess)
+        e = spectrum::uploadTables(stream);
     if (e == cudaSuccess)
         e = cudaMemcpyAsync(dE, energies, nBins * sizeof(float), cudaMemcpyHostToDevice, stream);
     if (e == cudaSuccess)
