@@ -144,25 +144,24 @@ __global__ void __launch_bounds__(kMaxDepthSteps) bremsstrahlungKernel(float T0,
 
 inline cudaError_t uploadTables(cudaStream_t stream)
 {
-    static ElectronTables host;
-    static bool filled = false;
-    if (!filled) {
+    static const ElectronTables host = [] { // thread-safe one-time conversion of the double tables
+        ElectronTables t {};
         for (int i = 0; i < tw::kDepths; ++i) {
-            host.depthF[i] = static_cast<float>(tw::depthF[i]);
-            host.depthM[i] = static_cast<float>(tw::depthM[i]);
+            t.depthF[i] = static_cast<float>(tw::depthF[i]);
+            t.depthM[i] = static_cast<float>(tw::depthM[i]);
             for (int j = 0; j < tw::kEnergies; ++j) {
-                host.densityF[i][j] = static_cast<float>(tw::densityF[i][j]);
-                host.densityM[i][j] = static_cast<float>(tw::densityM[i][j]);
+                t.densityF[i][j] = static_cast<float>(tw::densityF[i][j]);
+                t.densityM[i][j] = static_cast<float>(tw::densityM[i][j]);
             }
         }
         for (int j = 0; j < tw::kEnergies; ++j)
-            host.relEnergy[j] = static_cast<float>(tw::relEnergy[j]);
+            t.relEnergy[j] = static_cast<float>(tw::relEnergy[j]);
         for (int i = 0; i < 5; ++i) {
-            host.twVoltage[i] = static_cast<float>(tw::twVoltage[i]);
-            host.twConstant[i] = static_cast<float>(tw::twConstant[i]);
+            t.twVoltage[i] = static_cast<float>(tw::twVoltage[i]);
+            t.twConstant[i] = static_cast<float>(tw::twConstant[i]);
         }
-        filled = true;
-    }
+        return t;
+    }();
     // per device and cheap (4.5 KB): done at every call, on the stream the kernel is launched on (ordered before it)
     return cudaMemcpyToSymbolAsync(kTables, &host, sizeof(host), 0, cudaMemcpyHostToDevice, stream);
 }
