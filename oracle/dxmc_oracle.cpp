@@ -334,8 +334,10 @@ struct Oracle {
         dose[idx] += energyImparted;
         nEvents[idx] += 1;
         variance[idx] += energyImparted * energyImparted;
-        fixedEnergy[idx] += std::llrint(std::ldexp(energyImparted, energyBits));
-        fixedEnergySq[idx] += static_cast<std::uint64_t>(std::llrint(std::ldexp(energyImparted * energyImparted, energySqBits)));
+        if (std::isfinite(energyImparted)) { // the product drops a non-finite deposit (csrc/transport.cu deposit()); the float sums above keep the reference's behaviour
+            fixedEnergy[idx] += std::llrint(std::ldexp(energyImparted, energyBits));
+            fixedEnergySq[idx] += static_cast<std::uint64_t>(std::llrint(std::ldexp(energyImparted * energyImparted, energySqBits)));
+        }
         ++stats.score_events;
     }
 
