@@ -535,6 +535,7 @@ public:
     dxmcb200_ctx* context() const { return m_ctx.get(); }
     std::uint64_t preparedExposures() const { return m_totalExposures; }
     std::uint64_t preparedHistories() const { return m_histories; }
+    std::chrono::duration<double> lastRunTime() const { return m_lastRunTime; } // what Result::simulationTime reports
     void release() { m_ctx.reset(); }
 
     const AttenuationLut<T>& attenuationLut() const { return m_attenuationLut; }
