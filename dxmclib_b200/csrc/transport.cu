@@ -231,6 +231,15 @@ __device__ __forceinline__ void loadPhoton(const PhotonRecord* r, Photon& p, Rng
     logE = d.x, maxAttInv = d.y, seg = __float_as_uint(d.z), extra = d.w;
 }
 
+// dead marker: energy 0 in a whole record of zeros (a consumer loads all four parts of a record before it looks at the energy)
+__device__ __forceinline__ void storeDeadPhoton(PhotonRecord* r)
+{
+    recStore(&r->posE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    recStore(&r->dirW, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+    recStore(&r->rng, make_uint4(0u, 0u, 0u, 0u));
+    recStore(&r->lut, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+}
+
 __device__ __forceinline__ void storeEvent(EventRecord* e, const Photon& p, const Rng& rng, float logE, uint32_t seg, uint32_t voxel, uint32_t material,
     float eventProbability)
 {
@@ -826,7 +835,7 @@ __global__ void __launch_bounds__(kThreads, DXMCB200_TK_MINBLOCKS) transportKern
     });
     if constexpr (kAir)
         airborne.finish(lane, kAirTile, P.photonRegion, [&](unsigned slot) {
-            recStore(&P.airborne[static_cast<size_t>(myShard) * P.photonRegion + slot].posE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+            storeDeadPhoton(&P.airborne[static_cast<size_t>(myShard) * P.photonRegion + slot]);
         });
 
     if constexpr (kStats) {
@@ -969,7 +978,7 @@ __global__ void __launch_bounds__(kThreads, 6) interactKernel(const __grid_const
     if (lane == 0 && survivors)
         atomicAdd(&P.outCursors[outShard].live, survivors);
     out.finish(lane, kSurvivorTile, P.photonRegion, [&](unsigned slot) { // dead markers (energy 0): transportKernel drops them at the re-fill
-        recStore(&P.photonsOut[static_cast<size_t>(outShard) * P.photonRegion + slot].posE, make_float4(0.0f, 0.0f, 0.0f, 0.0f));
+        storeDeadPhoton(&P.photonsOut[static_cast<size_t>(outShard) * P.photonRegion + slot]);
     });
     if constexpr (kStats) {
         const unsigned long long i = warpSum(cInter), sc = warpSum(cScores);
